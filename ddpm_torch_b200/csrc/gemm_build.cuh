@@ -1,0 +1,63 @@
+// ddpm_gemm_desc (C ABI) -> GemmLaunch (tensor maps + kernel params)
+#pragma once
+#include "../../include/ddpm_b200.h"
+#include "gemm_host.cuh"
+
+namespace ddpm {
+
+inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
+    memset(&g, 0, sizeof g);
+    g.mode = d.mode;
+    g.block_n = d.block_n ? d.block_n : pick_block_n(d.N);
+    if (g.block_n != 64 && g.block_n != 128 && g.block_n != 256) return fail(-10, "block_n must be 64/128/256");
+    if (d.N % 32) return fail(-10, "N=%d must be a multiple of 32", d.N);
+    GemmParams& p = g.p;
+    p.M = d.M; p.N = d.N; p.W = d.W; p.H = d.H;
+    p.out = d.out; p.ldo = d.ldo; p.out_z_stride = d.out_z_stride; p.out_tap_stride = d.out_tap_stride; p.flags = d.flags;
+    p.bias = d.bias; p.rowvec = d.rowvec; p.rowvec_ld = d.rowvec_ld; p.rows_per_vec = d.rows_per_vec > 0 ? d.rows_per_vec : 1;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual); p.ldr = d.ldr; p.alpha = d.alpha;
+    p.b_k_base = d.b_k_base; p.a_z_n = d.a_z_n; p.b_z = d.b_z;
+    p.taps = d.taps > 0 ? d.taps : 1; p.splits = d.splits > 0 ? d.splits : 1; p.kblocks = d.kblocks;
+    p.a_c_base = d.a_c_base; p.b_c_base = d.b_c_base;
+    const int gz = d.grid_z > 0 ? d.grid_z : 1;
+    const int n_tiles = (d.N + g.block_n - 1) / g.block_n;
+    const int m_tiles = (d.M + 127) / 128;
+    g.grid = dim3(m_tiles, n_tiles, gz);
+    int rc;
+    if (d.mode == GEMM_KK) {
+        if (!pick_box(d.W, d.H, 128, p.w_t, p.h_t, p.n_t)) return fail(-11, "KK: unsupported geometry W=%d H=%d", d.W, d.H);
+        p.nseg = d.nseg;
+        if (d.nseg < 1 || d.nseg > 3) return fail(-11, "KK: nseg must be 1..3");
+        int slabs = 0;
+        for (int s = 0; s < d.nseg; ++s) {
+            p.seg[s] = GemmSeg{d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]};
+            if (d.seg_taps[s] != 1 && d.seg_taps[s] != 9) return fail(-11, "KK: taps must be 1 or 9");
+            slabs += d.seg_taps[s] * d.seg_kchunks[s];
+        }
+        for (int i = 0; i < 3; ++i) {
+            if (!d.a_ptr[i]) { g.a[i] = g.a[0]; continue; }
+            if ((rc = make_tmap_4d(&g.a[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.NB, d.a_ld[i], 64, p.w_t, p.h_t, p.n_t))) return rc;
+        }
+        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n))) return rc;
+        g.flops = 2.0 * d.M * d.N * 64.0 * slabs * gz;
+    } else if (d.mode == GEMM_MNMN) {
+        if (!pick_box(d.W, d.H, 64, p.wk_t, p.hk_t, p.nk_t)) return fail(-11, "MNMN: unsupported geometry W=%d H=%d", d.W, d.H);
+        if (d.M % 64) return fail(-11, "MNMN: M must be a multiple of 64");
+        if ((rc = make_tmap_4d(&g.a[0], d.a_ptr[0], d.a_C[0], d.W, d.H, d.NB, d.a_ld[0], 64, p.wk_t, p.hk_t, p.nk_t))) return rc;
+        g.a[1] = g.a[2] = g.a[0];
+        if ((rc = make_tmap_4d(&g.b, d.b_ptr, d.b_K, d.W, d.H, d.NB, d.b_ld, 64, p.wk_t, p.hk_t, p.nk_t))) return rc;
+        g.flops = 2.0 * d.M * d.N * 64.0 * d.kblocks * p.taps * (gz / (p.taps * p.splits));
+    } else if (d.mode == GEMM_KMN) {
+        if (!pick_box(d.W, d.H, 128, p.w_t, p.h_t, p.n_t)) return fail(-11, "KMN: unsupported geometry W=%d H=%d", d.W, d.H);
+        if (d.H != 1 || d.W % 64) return fail(-11, "KMN: B operand needs a (C, tokens%%64==0, 1, batch) tensor");
+        if ((rc = make_tmap_4d(&g.a[0], d.a_ptr[0], d.a_C[0], d.W, d.H, d.NB, d.a_ld[0], 64, p.w_t, p.h_t, p.n_t))) return rc;
+        g.a[1] = g.a[2] = g.a[0];
+        if ((rc = make_tmap_4d(&g.b, d.b_ptr, d.b_K, d.W, d.H, d.NB, d.b_ld, 64, 64, 1, 1))) return rc;
+        g.flops = 2.0 * d.M * d.N * 64.0 * d.kblocks * gz;
+    } else {
+        return fail(-10, "unknown gemm mode %d", d.mode);
+    }
+    return 0;
+}
+
+}  // namespace ddpm

@@ -1,0 +1,278 @@
+// tcgen05 implicit-GEMM engine: one warp-specialised kernel template that serves
+//   KK  : A K-major (NHWC pixel tiles, optional 3x3 taps, up to 3 channel segments), B K-major (packed weights / K^T)
+//         -> conv3x3 fwd + dgrad, conv1x1, fused conv2+skip, linear, Q.K^T, dO.V^T
+//   MNMN: A MN-major, B MN-major, K runs over pixels -> conv wgrad (per tap, split-K, fp32 red), P^T.dO, dS^T.Q
+//   KMN : A K-major, B MN-major, K runs over tokens  -> P.V, dS.K
+// Tile: M=128 rows x BLOCK_N columns, BLOCK_K=64 bf16 per stage (one 128-byte swizzle span), fp32 accumulators in TMEM.
+// Roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2-5 = epilogue (TMEM -> regs -> global).
+#pragma once
+#include "ptx.cuh"
+
+namespace ddpm {
+
+enum GemmMode { GEMM_KK = 0, GEMM_MNMN = 1, GEMM_KMN = 2 };
+enum EpiFlags { EPI_OUT_F32 = 1, EPI_ATOMIC = 2 };
+
+struct GemmSeg {
+    int map;       // which A tensor map (0..2)
+    int taps;      // 1 or 9 (3x3, pad 1, stride 1; tap t -> dx = t%3-1, dy = t/3-1)
+    int kchunks;   // channel chunks of 64 in this segment
+    int c_base;    // first channel coordinate inside the map
+};
+
+struct GemmParams {
+    int M, N;                 // valid rows / columns of the output (per z slice)
+    // row-space (K-major A) or K-space (MN-major operands) geometry of the NHWC tensor behind the 4D maps (C, W, H, N)
+    int W, H;                 // spatial dims (plain matrices: W = rows, H = 1)
+    int w_t, h_t, n_t;        // TMA box over (W,H,N): product = 128 (K-major A rows) ; MN-major K-block boxes use wk_t,hk_t,nk_t
+    int wk_t, hk_t, nk_t;     // product = 64
+    // KK
+    int nseg; GemmSeg seg[3];
+    int b_k_base;             // first K coordinate in the B map
+    int a_z_n, b_z;           // per-blockIdx.z increments: A 'n' coordinate, B batch coordinate
+    // MNMN / KMN
+    int taps;                 // MNMN: 1 or 9 (shift applied to B)
+    int splits;               // MNMN: split-K factor; z = (batch*taps + tap)*splits + split
+    int kblocks;              // K extent in blocks of 64 (per batch)
+    int a_c_base, b_c_base;   // channel-coordinate bases
+    // epilogue
+    void* out; int ldo; long long out_z_stride; long long out_tap_stride; int flags;
+    const float* bias;        // [N] or null
+    const float* rowvec;      // [M/rows_per_vec][rowvec_ld] or null (timestep-embedding projection per image)
+    int rowvec_ld, rows_per_vec;
+    const __nv_bfloat16* residual; int ldr;   // [M][ldr] or null
+    float alpha;
+};
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = 128 * 64 * 2;
+    static constexpr int B_BYTES = BLOCK_N * 64 * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& y, int& x) {
+    const int hw = W * H;
+    n = p / hw;
+    const int r = p - n * hw;
+    y = r / W;
+    x = r - y * W;
+}
+
+template <int BLOCK_N, int MODE, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+    using SM = GemmSmem<BLOCK_N, STAGES>;
+    constexpr int A_MN = (MODE == GEMM_MNMN) ? 1 : 0;
+    constexpr int B_MN = (MODE == GEMM_KK) ? 0 : 1;
+    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y, z = blockIdx.z;
+
+    // ---- number of K slabs (uniform over the CTA)
+    int num_slabs;
+    int tap = 0, split = 0, batch = z;
+    if (MODE == GEMM_KK) {
+        num_slabs = 0;
+        for (int s = 0; s < p.nseg; ++s) num_slabs += p.seg[s].taps * p.seg[s].kchunks;
+    } else if (MODE == GEMM_MNMN) {
+        split = z % p.splits;
+        tap = (z / p.splits) % p.taps;
+        batch = z / (p.splits * p.taps);
+        const int per = (p.kblocks + p.splits - 1) / p.splits;
+        const int kb0 = split * per;
+        int kb1 = kb0 + per; if (kb1 > p.kblocks) kb1 = p.kblocks;
+        num_slabs = kb1 > kb0 ? kb1 - kb0 : 0;
+    } else {
+        num_slabs = p.kblocks;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int slab = 0;
+            bool ok = true;
+            auto acquire = [&](int sl) -> uint8_t* {
+                const int st = sl % STAGES;
+                const uint32_t ph = (sl / STAGES) & 1;
+                if (!mbar_wait(&empty_bar[st], ph ^ 1, 1)) { ok = false; return nullptr; }
+                mbar_expect_tx(&full_bar[st], SM::STAGE_BYTES);
+                return smem + st * SM::STAGE_BYTES;
+            };
+            if (MODE == GEMM_KK) {
+                int n0, y0, x0;
+                pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
+                n0 += z * p.a_z_n;
+                int kcount = 0;
+                for (int s = 0; s < p.nseg && ok; ++s) {
+                    const GemmSeg sg = p.seg[s];
+                    const CUtensorMap* mA = sg.map == 0 ? &tmA0 : (sg.map == 1 ? &tmA1 : &tmA2);
+                    for (int t = 0; t < sg.taps && ok; ++t) {
+                        const int dx = sg.taps == 9 ? (t % 3) - 1 : 0;
+                        const int dy = sg.taps == 9 ? (t / 3) - 1 : 0;
+                        for (int kc = 0; kc < sg.kchunks; ++kc, ++slab, ++kcount) {
+                            uint8_t* st = acquire(slab);
+                            if (!st) break;
+                            uint64_t* fb = &full_bar[slab % STAGES];
+                            tma_load_4d(st, mA, fb, sg.c_base + kc * 64, x0 + dx, y0 + dy, n0);
+                            tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+                        }
+                    }
+                }
+            } else if (MODE == GEMM_MNMN) {
+                const int per = (p.kblocks + p.splits - 1) / p.splits;
+                const int kb0 = split * per;
+                const int dx = p.taps == 9 ? (tap % 3) - 1 : 0;
+                const int dy = p.taps == 9 ? (tap / 3) - 1 : 0;
+                for (int i = 0; i < num_slabs; ++i, ++slab) {
+                    uint8_t* st = acquire(slab);
+                    if (!st) break;
+                    uint64_t* fb = &full_bar[slab % STAGES];
+                    int n0, y0, x0;
+                    pix_decompose((kb0 + i) * 64, p.W, p.H, n0, y0, x0);
+                    n0 += batch;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_4d(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
+#pragma unroll
+                    for (int b = 0; b < BLOCK_N / 64; ++b)
+                        tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, x0 + dx, y0 + dy, n0);
+                }
+            } else {  // GEMM_KMN
+                int n0, y0, x0;
+                pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
+                n0 += z * p.a_z_n;
+                for (int i = 0; i < num_slabs; ++i, ++slab) {
+                    uint8_t* st = acquire(slab);
+                    if (!st) break;
+                    uint64_t* fb = &full_bar[slab % STAGES];
+                    tma_load_4d(st, &tmA0, fb, p.a_c_base + i * 64, x0, y0, n0);
+#pragma unroll
+                    for (int b = 0; b < BLOCK_N / 64; ++b)
+                        tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, i * 64, 0, z);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, A_MN, B_MN);
+            for (int slab = 0; slab < num_slabs; ++slab) {
+                const int st = slab % STAGES;
+                const uint32_t ph = (slab / STAGES) & 1;
+                if (!mbar_wait(&full_bar[st], ph, 2)) break;
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + st * SM::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // K-major: 16 elements = 32 B inside the swizzle span; MN-major: 16 K-rows of 128 B
+                    const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                             : umma_smem_desc(a_addr + k * 32, 16, 1024);
+                    const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                             : umma_smem_desc(b_addr + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (slab | k) != 0);
+                }
+                umma_commit(&empty_bar[st]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ======================= epilogue: 4 warps <-> 4 TMEM lane quarters =======================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // accumulator row
+        bool ok = true;
+        if (num_slabs > 0) ok = mbar_wait(tmem_full, 0, 3);
+        tc_fence_after();
+        const int row = m_tile * 128 + r;
+        const bool row_ok = ok && row < p.M && num_slabs > 0;
+        const long long zoff = (MODE == GEMM_MNMN) ? (long long)batch * p.out_z_stride + (long long)tap * p.out_tap_stride
+                                                  : (long long)z * p.out_z_stride;
+        const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            const int col = n_tile * BLOCK_N + c0;
+            if (col >= p.N) break;                    // uniform across the CTA
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
+            }
+            if (rv) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + col + j);
+            }
+            if (p.residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + col);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const uint4 u = __ldg(rp + j4);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 t2 = __bfloat1622float2(h[e]);
+                        f[j4 * 8 + e * 2] += t2.x; f[j4 * 8 + e * 2 + 1] += t2.y;
+                    }
+                }
+            }
+            if (p.flags & EPI_ATOMIC) {
+                float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)row * p.ldo + col;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(o + j, f[j]);
+            } else if (p.flags & EPI_OUT_F32) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + zoff + (long long)row * p.ldo + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + (long long)row * p.ldo + col);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                    o[j] = u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace ddpm

@@ -1,0 +1,161 @@
+"""Parity of the tcgen05 implicit-GEMM engine (csrc/umma_gemm.cuh) through the C ABI (ddpm_gemm_run)
+against plain fp32 PyTorch on the same bf16-rounded inputs.  Tolerances: fp32 outputs 2e-5 rel-L2
+(fp32 accumulation order only), bf16 outputs 4e-3 rel-L2 (one bf16 rounding)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(d):
+    from ddpm_torch_b200 import _lib
+    _lib.check(_lib.lib().ddpm_gemm_run(C.byref(d), _lib.stream_ptr()), "gemm_run")
+    torch.cuda.synchronize()
+    assert _lib.lib().ddpm_device_error_flag() == 0, "bounded wait timed out inside the kernel"
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def bf(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def new_desc():
+    from ddpm_torch_b200._lib import GemmDesc
+    d = GemmDesc()
+    d.alpha = 1.0
+    d.grid_z = 1
+    return d
+
+
+@pytest.mark.parametrize("N", [64, 128, 256, 384])
+@pytest.mark.parametrize("M,K", [(256, 192), (200, 64), (1024, 512)])
+def test_kk_plain_gemm(M, K, N):
+    Mp = 1 << (M - 1).bit_length()          # map geometry wants a power-of-two row extent; extra rows are zero
+    A = torch.zeros(Mp, K, device="cuda", dtype=torch.bfloat16); A[:M] = bf(M, K, seed=1)
+    Bm = bf(N, K, seed=2, scale=0.1)
+    bias = torch.randn(N, device="cuda"); rowvec = torch.randn((M + 63) // 64, N, device="cuda")
+    res = bf(M, N, seed=3)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = new_desc()
+    d.mode = 0; d.M = M; d.N = N; d.W = Mp; d.H = 1; d.NB = 1
+    d.a_ptr[0] = A.data_ptr(); d.a_C[0] = K; d.a_ld[0] = K
+    d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 1; d.seg_kchunks[0] = K // 64; d.seg_cbase[0] = 0
+    d.b_ptr = Bm.data_ptr(); d.b_K = K; d.b_rows = N; d.b_batch = 1; d.b_ld = K; d.b_bs = 0
+    d.out = out.data_ptr(); d.ldo = N
+    d.bias = bias.data_ptr(); d.rowvec = rowvec.data_ptr(); d.rowvec_ld = N; d.rows_per_vec = 64
+    d.residual = res.data_ptr(); d.ldr = N; d.alpha = 0.5
+    _run(d)
+    ref = 0.5 * (A[:M].float() @ Bm.float().t()) + bias + rowvec.repeat_interleave(64, 0)[:M] + res.float()
+    assert rel(out.float(), ref) < 4e-3
+
+
+def test_kk_batched_qk():
+    B, T, Cc = 3, 256, 64
+    qkv = bf(B, T, 3 * Cc, seed=5)
+    out = torch.full((B, T, T), float("nan"), device="cuda")
+    d = new_desc()
+    d.mode = 0; d.M = T; d.N = T; d.W = T; d.H = 1; d.NB = B
+    d.a_ptr[0] = qkv.data_ptr(); d.a_C[0] = 3 * Cc; d.a_ld[0] = 3 * Cc
+    d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 1; d.seg_kchunks[0] = Cc // 64; d.seg_cbase[0] = 0
+    d.b_ptr = qkv.data_ptr(); d.b_K = 3 * Cc; d.b_rows = T; d.b_batch = B; d.b_ld = 3 * Cc; d.b_bs = T * 3 * Cc
+    d.b_k_base = Cc; d.a_z_n = 1; d.b_z = 1; d.grid_z = B
+    d.out = out.data_ptr(); d.ldo = T; d.out_z_stride = T * T; d.flags = 1; d.alpha = 0.125
+    _run(d)
+    q, k = qkv[..., :Cc].float(), qkv[..., Cc:2 * Cc].float()
+    ref = 0.125 * torch.einsum("bic,bjc->bij", q, k)
+    assert rel(out, ref) < 2e-5
+
+
+def pack_w(w):
+    """OIHW fp32 -> [Co][tap*Ci + ci] bf16 (K-major, tap-major K)."""
+    Co, Ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(Co, kh * kw * Ci).contiguous().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (2, 16, 16), (4, 8, 8), (16, 4, 4), (3, 4, 4), (1, 128, 128), (1, 64, 64)])
+@pytest.mark.parametrize("Cout", [64, 128, 256])
+def test_kk_conv3x3_concat_skip(B, H, W, Cout):
+    C1, C2 = 64, 128
+    x1 = bf(B, H, W, C1, seed=1); x2 = bf(B, H, W, C2, seed=2)           # two concat sources (NHWC)
+    xs = bf(B, H, W, 64, seed=3)                                         # raw input of a fused 1x1 skip
+    w = torch.randn(Cout, C1 + C2, 3, 3, device="cuda") * 0.05
+    ws = torch.randn(Cout, 64, 1, 1, device="cuda") * 0.1
+    bias = torch.randn(Cout, device="cuda"); temb = torch.randn(B, Cout, device="cuda")
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    # segments iterate (segment, tap, chunk): K order = seg0[tap][c1], seg1[tap][c2], skip[c]
+    wp = torch.cat([pack_w(w[:, :C1]), pack_w(w[:, C1:]), pack_w(ws)], dim=1).contiguous()
+    K = wp.shape[1]
+    d = new_desc()
+    d.mode = 0; d.M = B * H * W; d.N = Cout; d.W = W; d.H = H; d.NB = B
+    for i, (t, c) in enumerate(((x1, C1), (x2, C2), (xs, 64))):
+        d.a_ptr[i] = t.data_ptr(); d.a_C[i] = c; d.a_ld[i] = c
+    d.nseg = 3
+    for i, (taps, kc) in enumerate(((9, C1 // 64), (9, C2 // 64), (1, 1))):
+        d.seg_map[i] = i; d.seg_taps[i] = taps; d.seg_kchunks[i] = kc; d.seg_cbase[i] = 0
+    d.b_ptr = wp.data_ptr(); d.b_K = K; d.b_rows = Cout; d.b_batch = 1; d.b_ld = K
+    d.out = out.data_ptr(); d.ldo = Cout
+    d.bias = bias.data_ptr(); d.rowvec = temb.data_ptr(); d.rowvec_ld = Cout; d.rows_per_vec = H * W
+    _run(d)
+    xin = torch.cat([x1, x2], dim=-1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, w.to(torch.bfloat16).float(), bias, padding=1) + temb[:, :, None, None] \
+        + F.conv2d(xs.float().permute(0, 3, 1, 2), ws.to(torch.bfloat16).float())
+    assert rel(out.float().permute(0, 3, 1, 2), ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,W,splits", [(2, 32, 32, 3), (4, 16, 16, 2), (8, 8, 8, 1), (16, 4, 4, 2)])
+@pytest.mark.parametrize("Ci", [64, 128, 256])
+def test_mnmn_conv_wgrad(B, H, W, splits, Ci):
+    Co = 128
+    dy = bf(B, H, W, Co, seed=1, scale=0.1); a = bf(B, H, W, Ci, seed=2)
+    out = torch.zeros(9, Co, Ci, device="cuda")
+    d = new_desc()
+    d.mode = 1; d.M = Co; d.N = Ci; d.W = W; d.H = H; d.NB = B
+    d.a_ptr[0] = dy.data_ptr(); d.a_C[0] = Co; d.a_ld[0] = Co
+    d.b_ptr = a.data_ptr(); d.b_K = Ci; d.b_ld = Ci
+    d.taps = 9; d.splits = splits; d.kblocks = B * H * W // 64; d.grid_z = 9 * splits
+    d.out = out.data_ptr(); d.ldo = Ci; d.out_tap_stride = Co * Ci; d.flags = 3
+    _run(d)
+    x = a.float().permute(0, 3, 1, 2)
+    w = torch.zeros(Co, Ci, 3, 3, device="cuda", requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    F.conv2d(x, w, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 0, 1).reshape(9, Co, Ci)
+    assert rel(out, ref) < 2e-5
+
+
+def test_mnmn_bmm_ptdo():
+    B, T, Cc = 2, 256, 64
+    P = bf(B, T, T, seed=1, scale=0.1); dO = bf(B, T, Cc, seed=2)
+    out = torch.zeros(B, T, Cc, device="cuda")
+    d = new_desc()
+    d.mode = 1; d.M = T; d.N = Cc; d.W = T; d.H = 1; d.NB = B
+    d.a_ptr[0] = P.data_ptr(); d.a_C[0] = T; d.a_ld[0] = T
+    d.b_ptr = dO.data_ptr(); d.b_K = Cc; d.b_ld = Cc
+    d.taps = 1; d.splits = 1; d.kblocks = T // 64; d.grid_z = B
+    d.out = out.data_ptr(); d.ldo = Cc; d.out_z_stride = T * Cc; d.flags = 1
+    _run(d)
+    ref = torch.einsum("bij,bic->bjc", P.float(), dO.float())
+    assert rel(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("Cc", [64, 256])
+def test_kmn_pv(Cc):
+    B, T = 2, 256
+    P = bf(B, T, T, seed=1, scale=0.1); qkv = bf(B, T, 3 * Cc, seed=2)
+    out = torch.full((B, T, Cc), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = new_desc()
+    d.mode = 2; d.M = T; d.N = Cc; d.W = T; d.H = 1; d.NB = B
+    d.a_ptr[0] = P.data_ptr(); d.a_C[0] = T; d.a_ld[0] = T
+    d.b_ptr = qkv.data_ptr(); d.b_K = 3 * Cc; d.b_ld = 3 * Cc; d.b_c_base = 2 * Cc
+    d.kblocks = T // 64; d.a_z_n = 1; d.grid_z = B
+    d.out = out.data_ptr(); d.ldo = Cc; d.out_z_stride = T * Cc
+    _run(d)
+    ref = torch.einsum("bij,bjc->bic", P.float(), qkv[..., 2 * Cc:].float())
+    assert rel(out.float(), ref) < 4e-3
