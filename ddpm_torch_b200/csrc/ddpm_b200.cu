@@ -1,6 +1,7 @@
 // libddpm_b200.so — single translation unit (device-side error flag and kernels share one module).
 #include <cstdarg>
 #include "gemm_build.cuh"
+#include "kernels_simt.cuh"
 
 using namespace ddpm;
 

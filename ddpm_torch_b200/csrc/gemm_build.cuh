@@ -5,6 +5,14 @@
 
 namespace ddpm {
 
+// standard segment: 1 tap (1x1) or 9 taps (3x3, stride 1, pad 1)
+inline GemmSeg make_seg(int map, int taps, int kchunks, int c_base) {
+    GemmSeg g; memset(&g, 0, sizeof g);
+    g.map = map; g.taps = taps; g.kchunks = kchunks; g.c_base = c_base; g.cmul = 1;
+    if (taps == 9) for (int t = 0; t < 9; ++t) { g.dx[t] = (signed char)(t % 3 - 1); g.dy[t] = (signed char)(t / 3 - 1); }
+    return g;
+}
+
 inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     memset(&g, 0, sizeof g);
     g.mode = d.mode;
@@ -30,8 +38,8 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
         if (d.nseg < 1 || d.nseg > 3) return fail(-11, "KK: nseg must be 1..3");
         int slabs = 0;
         for (int s = 0; s < d.nseg; ++s) {
-            p.seg[s] = GemmSeg{d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]};
             if (d.seg_taps[s] != 1 && d.seg_taps[s] != 9) return fail(-11, "KK: taps must be 1 or 9");
+            p.seg[s] = make_seg(d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]);
             slabs += d.seg_taps[s] * d.seg_kchunks[s];
         }
         for (int i = 0; i < 3; ++i) {

@@ -1,0 +1,747 @@
+// CUDA-core kernels of the engine: everything that is not a tensor-core contraction
+// (GroupNorm, SiLU, dropout, softmax, q_sample / MSE / p_sample tails, layout converters) plus a generic
+// tiled conv / wgrad / strided-GEMM used for the geometries the tcgen05 engine does not take
+// (Ci=3 / Co=3, stride-2 down-convs, channel counts that are not multiples of 64, tiny token counts).
+// All activations are NHWC bf16; statistics, reductions and accumulators are fp32 (fp64 for GroupNorm sums).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ddpm {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float silu_f(float y) { return y / (1.f + __expf(-y)); }
+__device__ __forceinline__ float silu_grad_f(float y) {
+    const float s = 1.f / (1.f + __expf(-y));
+    return s * (1.f + y * (1.f - s));
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// counter-based RNG for dropout: Philox4x32-10 keyed by (seed, layer); counter = element index / 4
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask for 8 consecutive elements starting at element index e (multiple of 8)
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t layer, unsigned long long e, float p) {
+    const uint32_t thr = (uint32_t)(p * 4294967296.0);
+    const uint4 r0 = philox4x32((uint32_t)(e >> 2), (uint32_t)(e >> 34), (uint32_t)seed ^ (layer * 0x9E3779B1u), (uint32_t)(seed >> 32));
+    const uint4 r1 = philox4x32((uint32_t)((e >> 2) + 1), (uint32_t)(e >> 34), (uint32_t)seed ^ (layer * 0x9E3779B1u), (uint32_t)(seed >> 32));
+    uint32_t m = 0;
+    m |= (r0.x >= thr) << 0; m |= (r0.y >= thr) << 1; m |= (r0.z >= thr) << 2; m |= (r0.w >= thr) << 3;
+    m |= (r1.x >= thr) << 4; m |= (r1.y >= thr) << 5; m |= (r1.z >= thr) << 6; m |= (r1.w >= thr) << 7;
+    return m;
+}
+
+// ============================================================================ timestep embedding (functions.py:10-26)
+__global__ void k_timestep_embedding(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    const float k = logf(10000.f) / (float)(half - 1);
+    const float f = expf(-(float)j * k);
+    const float a = (float)t[b] * f;
+    out[(size_t)b * dim + j] = sinf(a);
+    out[(size_t)b * dim + half + j] = cosf(a);
+    if ((dim & 1) && j == 0) out[(size_t)b * dim + dim - 1] = 0.f;
+}
+
+// ============================================================================ generic strided batched GEMM (CUDA cores)
+// C[z][m][n] = alpha * sum_k A(z,m,k) * B(z,k,n) (+ bias[n]) (+ C if accumulate); element strides are arbitrary.
+// TA/TB/TC in {float, bf16}.  Optional SiLU on A at load (temb MLP).  64x64x16 tile, 256 threads, 4x4 per thread.
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+struct SgemmParams {
+    const void* A; const void* B; void* C; const float* bias;
+    int M, N, K;
+    long long sa_m, sa_k, sa_z, sb_k, sb_n, sb_z, sc_m, sc_n, sc_z;
+    float alpha; int accumulate; int silu_a;
+};
+
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) {
+    __shared__ float As[16][65];
+    __shared__ float Bs[16][65];
+    const TA* A = reinterpret_cast<const TA*>(p.A) + (long long)blockIdx.z * p.sa_z;
+    const TB* Bm = reinterpret_cast<const TB*>(p.B) + (long long)blockIdx.z * p.sb_z;
+    TC* C = reinterpret_cast<TC*>(p.C) + (long long)blockIdx.z * p.sc_z;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+        for (int i = threadIdx.x; i < 1024; i += 256) {
+            const int kk = i & 15, r = i >> 4;
+            const int m = m0 + r, k = k0 + kk;
+            float a = 0.f, b = 0.f;
+            if (m < p.M && k < p.K) { a = ldf<TA>(A + (long long)m * p.sa_m + (long long)k * p.sa_k); if (p.silu_a) a = silu_f(a); }
+            const int n = n0 + r;
+            if (n < p.N && k < p.K) b = ldf<TB>(Bm + (long long)k * p.sb_k + (long long)n * p.sb_n);
+            As[kk][r] = a; Bs[kk][r] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.N) continue;
+            float v = acc[i][j] * p.alpha;
+            if (p.bias) v += p.bias[n];
+            TC* c = C + (long long)m * p.sc_m + (long long)n * p.sc_n;
+            if (p.accumulate) v += ldf<TC>(c);
+            stf<TC>(c, v);
+        }
+    }
+}
+
+// ============================================================================ GroupNorm (32 groups, eps 1e-6; unet.py:18-20)
+// stats: per (b, group) {sum, sumsq} accumulated in fp64 atomics; input = channel-concat of up to two NHWC tensors.
+struct GnSrc { const bf16* x0; const bf16* x1; int C0, C1; };   // C = C0 + C1, both multiples of 8
+
+// Launch with blockDim.x = (256/oct)*oct (oct = C/8 <= 256) so that every thread owns ONE channel octet for its whole
+// pixel loop: per-channel partial sums stay in registers and are flushed once.
+__global__ void __launch_bounds__(256) k_gn_stats(GnSrc s, double* __restrict__ stats /*[B][32][2]*/, int HW, int pix_per_block) {
+    const int C = s.C0 + s.C1;
+    const int oct = C >> 3;                       // 16-byte octets per pixel
+    const int cg = C >> 5;                        // channels per group
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_block;
+    int p1 = p0 + pix_per_block; if (p1 > HW) p1 = HW;
+    __shared__ float sh[64];                      // [32][2]
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
+    const int c = o * 8;
+    const bool first = c < s.C0;
+    float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pp = p0 + lp; pp < p1; pp += pstep) {
+        const long long pix = (long long)b * HW + pp;
+        const bf16* src = first ? s.x0 + pix * s.C0 + c : s.x1 + pix * s.C1 + (c - s.C0);
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] += f[e] * f[e]; }
+    }
+    {   // flush: merge elements that share a group before touching shared memory
+        int gcur = c / cg; float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (c + e) / cg;
+            if (g != gcur) { atomicAdd(&sh[gcur * 2], a1); atomicAdd(&sh[gcur * 2 + 1], a2); a1 = a2 = 0.f; gcur = g; }
+            a1 += su[e]; a2 += sq[e];
+        }
+        atomicAdd(&sh[gcur * 2], a1); atomicAdd(&sh[gcur * 2 + 1], a2);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&stats[(long long)b * 64 + i], (double)sh[i]);
+}
+
+// finalize: {sum,sumsq} -> {mean, rstd} (fp32) ; n = HW * C/32
+__global__ void k_gn_finalize(const double* __restrict__ stats, float* __restrict__ mr, int count, double inv_n, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double m = stats[2 * i] * inv_n;
+    double var = stats[2 * i + 1] * inv_n - m * m;
+    if (var < 0) var = 0;
+    mr[2 * i] = (float)m;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// y = act(gn(x)) [* dropout] -> bf16 NHWC [B,HW,C]
+struct GnApply {
+    GnSrc s; const float* mr; const float* gamma; const float* beta; bf16* y;
+    int HW; long long total_oct; int silu; float drop_p; unsigned long long seed; uint32_t layer;
+};
+__global__ void __launch_bounds__(256) k_gn_apply(const GnApply a) {
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total_oct; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / oct;
+        const int c = (int)(i % oct) * 8;
+        const int b = (int)(pix / a.HW);
+        const bf16* src = c < a.s.C0 ? a.s.x0 + pix * a.s.C0 + c : a.s.x1 + pix * a.s.C1 + (c - a.s.C0);
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), f);
+        uint32_t keep = 0xffu;
+        if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)i * 8, a.drop_p);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (c + e) / cg;
+            const float m = a.mr[(b * 32 + g) * 2], r = a.mr[(b * 32 + g) * 2 + 1];
+            float y = (f[e] - m) * r * __ldg(a.gamma + c + e) + __ldg(a.beta + c + e);
+            if (a.silu) y = silu_f(y);
+            f[e] = ((keep >> e) & 1u) ? y * keep_scale : 0.f;
+        }
+        *reinterpret_cast<uint4*>(a.y + pix * C + c) = pack8(f);
+    }
+}
+
+// backward of y = act(gn(x))*mask:  phase 1 reduces, phase 2 applies.
+// red[b][g][2] (fp64): S1 = sum dyh, S2 = sum dyh*xh   where dyh = dy*act'(yn)*mask*gamma ;  dgamma[c] += dy_n*xh ; dbeta[c] += dy_n
+struct GnBwd {
+    GnSrc s; const bf16* dy; const float* mr; const float* gamma; const float* beta;
+    double* red; float* dgamma; float* dbeta;
+    bf16* dx0; bf16* dx1; int acc0, acc1;                         // destinations for the two sources (accumulate flags)
+    int HW; int pix_per_block; int silu; float drop_p; unsigned long long seed; uint32_t layer; long long total_oct;
+};
+__global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwd a) {   // blockDim.x = (256/oct)*oct, see k_gn_stats
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * a.pix_per_block;
+    int p1 = p0 + a.pix_per_block; if (p1 > a.HW) p1 = a.HW;
+    extern __shared__ float sh[];                 // [32][2] S1,S2 ; then [C] dgamma ; [C] dbeta
+    float* sg = sh + 64; float* sb = sg + C;
+    for (int i = threadIdx.x; i < 64 + 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
+    const int c = o * 8;
+    const bool first = c < a.s.C0;
+    float ga[8], be[8], m[8], r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c + e) / cg;
+        ga[e] = __ldg(a.gamma + c + e); be[e] = __ldg(a.beta + c + e);
+        m[e] = a.mr[(b * 32 + g) * 2]; r[e] = a.mr[(b * 32 + g) * 2 + 1];
+    }
+    float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pp = p0 + lp; pp < p1; pp += pstep) {
+        const long long pix = (long long)b * a.HW + pp;
+        const bf16* src = first ? a.s.x0 + pix * a.s.C0 + c : a.s.x1 + pix * a.s.C1 + (c - a.s.C0);
+        float x[8], d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), x);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.dy + pix * C + c)), d);
+        uint32_t keep = 0xffu;
+        if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(pix * oct + o) * 8, a.drop_p);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (x[e] - m[e]) * r[e];
+            float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
+            if (a.silu) dn *= silu_grad_f(xh * ga[e] + be[e]);
+            dg[e] += dn * xh; db[e] += dn;
+            const float dh = dn * ga[e];
+            s1[e] += dh; s2[e] += dh * xh;
+        }
+    }
+    {
+        int gcur = c / cg; float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(&sg[c + e], dg[e]); atomicAdd(&sb[c + e], db[e]);
+            const int g = (c + e) / cg;
+            if (g != gcur) { atomicAdd(&sh[gcur * 2], a1); atomicAdd(&sh[gcur * 2 + 1], a2); a1 = a2 = 0.f; gcur = g; }
+            a1 += s1[e]; a2 += s2[e];
+        }
+        atomicAdd(&sh[gcur * 2], a1); atomicAdd(&sh[gcur * 2 + 1], a2);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&a.red[(long long)b * 64 + i], (double)sh[i]);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(&a.dgamma[i], sg[i]); atomicAdd(&a.dbeta[i], sb[i]); }
+}
+__global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwd a) {
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const float inv_n = 1.f / ((float)a.HW * (float)cg);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total_oct; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / oct;
+        const int c = (int)(i % oct) * 8;
+        const int b = (int)(pix / a.HW);
+        const bool first = c < a.s.C0;
+        const bf16* src = first ? a.s.x0 + pix * a.s.C0 + c : a.s.x1 + pix * a.s.C1 + (c - a.s.C0);
+        float x[8], d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), x);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.dy + pix * C + c)), d);
+        uint32_t keep = 0xffu;
+        if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)i * 8, a.drop_p);
+        bf16* dst = first ? a.dx0 + pix * a.s.C0 + c : a.dx1 + pix * a.s.C1 + (c - a.s.C0);
+        const int acc = first ? a.acc0 : a.acc1;
+        float o[8];
+        if (acc) unpack8(*reinterpret_cast<const uint4*>(dst), o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (c + e) / cg;
+            const float m = a.mr[(b * 32 + g) * 2], r = a.mr[(b * 32 + g) * 2 + 1];
+            const float ga = __ldg(a.gamma + c + e);
+            const float xh = (x[e] - m) * r;
+            float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
+            if (a.silu) dn *= silu_grad_f(xh * ga + __ldg(a.beta + c + e));
+            const float dh = dn * ga;
+            const float s1 = (float)a.red[(b * 32 + g) * 2] * inv_n, s2 = (float)a.red[(b * 32 + g) * 2 + 1] * inv_n;
+            const float v = r * (dh - s1 - xh * s2);
+            o[e] = acc ? o[e] + v : v;
+        }
+        *reinterpret_cast<uint4*>(dst) = pack8(o);
+    }
+}
+
+// ============================================================================ generic conv (CUDA cores)
+// out[b,oy,ox,co] = sum_{tap,ci} in[b, iy(oy,ky), ix(ox,kx), ci] * Wp[co][tap*Cin + ci]  (+bias +rowvec[b] +residual)
+// map 0: iy = oy*stride + ky - pad ; map 1 (dgrad of the stride-2 conv): iy = (oy-ky)/2 when even ; map 2: nearest-2x
+// upsample fused: iy = (oy+ky-1)>>1 on the 2x grid.
+enum ConvMap { MAP_NORMAL = 0, MAP_TRANSPOSED2 = 1, MAP_UPSAMPLE2 = 2 };
+struct ConvG {
+    GnSrc in; const bf16* wp; long long ldw;     // packed weights [Co][ldw]
+    const float* bias; const float* rowvec; int rowvec_ld; const bf16* residual;
+    void* out; int out_nchw_f32;
+    int B, Hi, Wi, Ho, Wo, Co, ksize, stride, pad, map;
+    int accumulate;                              // out += (bf16 NHWC only)
+};
+__device__ __forceinline__ bool conv_map_coord(int map, int o, int k, int stride, int pad, int n_in, int& i) {
+    if (map == MAP_NORMAL) { i = o * stride + k - pad; return i >= 0 && i < n_in; }
+    if (map == MAP_TRANSPOSED2) { const int d = o - k; i = d >> 1; return d >= 0 && !(d & 1) && i < n_in; }
+    const int u = o + k - 1; i = u >> 1; return u >= 0 && i < n_in;
+}
+__global__ void __launch_bounds__(256) k_conv_generic(const ConvG c) {
+    __shared__ float As[16][65];
+    __shared__ float Bs[16][65];
+    const int Cin = c.in.C0 + c.in.C1;
+    const int taps = c.ksize * c.ksize;
+    const int P = c.B * c.Ho * c.Wo;
+    const int p0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lp = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;     // loader: row (pixel / co) and 4-wide k offset
+    // loader pixel coordinates
+    const int pl = p0 + lp;
+    int lb = 0, loy = 0, lox = 0;
+    if (pl < P) { lb = pl / (c.Ho * c.Wo); const int r = pl % (c.Ho * c.Wo); loy = r / c.Wo; lox = r % c.Wo; }
+    float acc[4][4] = {};
+    for (int t = 0; t < taps; ++t) {
+        const int ky = c.ksize == 3 ? t / 3 : 0, kx = c.ksize == 3 ? t % 3 : 0;
+        int iy = 0, ix = 0;
+        bool valid = pl < P;
+        if (c.ksize == 3 || c.map != MAP_NORMAL || c.stride != 1) {
+            valid = valid && conv_map_coord(c.map, loy, ky, c.stride, c.pad, c.Hi, iy) && conv_map_coord(c.map, lox, kx, c.stride, c.pad, c.Wi, ix);
+        } else { iy = loy; ix = lox; }
+        const long long ipix = ((long long)lb * c.Hi + iy) * c.Wi + ix;
+        for (int k0 = 0; k0 < Cin; k0 += 16) {
+            {   // A tile: 64 pixels x 16 channels
+                const int ci = k0 + lk;
+                float f[4] = {0, 0, 0, 0};
+                if (valid && ci < Cin) {
+                    const bf16* src = ci < c.in.C0 ? c.in.x0 + ipix * c.in.C0 + ci : c.in.x1 + ipix * c.in.C1 + (ci - c.in.C0);
+                    const uint2 u = *reinterpret_cast<const uint2*>(src);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    const float2 a0 = __bfloat1622float2(h[0]), a1 = __bfloat1622float2(h[1]);
+                    f[0] = a0.x; f[1] = a0.y; f[2] = a1.x; f[3] = a1.y;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) As[lk + e][lp] = f[e];
+            }
+            {   // B tile: 64 out-channels x 16 k
+                const int co = co0 + lp, ci = k0 + lk;
+                float f[4] = {0, 0, 0, 0};
+                if (co < c.Co && ci < Cin) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(c.wp + (long long)co * c.ldw + (long long)t * Cin + ci);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    const float2 a0 = __bfloat1622float2(h[0]), a1 = __bfloat1622float2(h[1]);
+                    f[0] = a0.x; f[1] = a0.y; f[2] = a1.x; f[3] = a1.y;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) Bs[lk + e][lp] = f[e];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pp = p0 + ty * 4 + i;
+        if (pp >= P) continue;
+        const int b = pp / (c.Ho * c.Wo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + tx * 4 + j;
+            if (co >= c.Co) continue;
+            float v = acc[i][j];
+            if (c.bias) v += c.bias[co];
+            if (c.rowvec) v += c.rowvec[(long long)b * c.rowvec_ld + co];
+            if (c.residual) v += __bfloat162float(c.residual[(long long)pp * c.Co + co]);
+            if (c.out_nchw_f32) {
+                const int r = pp % (c.Ho * c.Wo);
+                reinterpret_cast<float*>(c.out)[((long long)b * c.Co + co) * (c.Ho * c.Wo) + r] = v;
+            } else {
+                bf16* o = reinterpret_cast<bf16*>(c.out) + (long long)pp * c.Co + co;
+                if (c.accumulate) v += __bfloat162float(*o);
+                *o = __float2bfloat16_rn(v);
+            }
+        }
+    }
+}
+
+// generic wgrad: dW[co][ci][tap] (strides given) += sum_p dy[p][co] * in[map(p,tap)][ci]   (fp32 atomics, split over pixels)
+struct WgradG {
+    const bf16* dy; GnSrc in; float* dw; long long s_co, s_ci, s_tap;
+    int B, Hi, Wi, Ho, Wo, Co, ksize, stride, pad, map, pix_per_split;
+};
+__global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
+    __shared__ float As[16][65];   // [pixel][co]
+    __shared__ float Bs[16][65];   // [pixel][ci]
+    const int Cin = c.in.C0 + c.in.C1;
+    const int taps = c.ksize * c.ksize;
+    const int t = blockIdx.z % taps, split = blockIdx.z / taps;
+    const int ky = c.ksize == 3 ? t / 3 : 0, kx = c.ksize == 3 ? t % 3 : 0;
+    const int P = c.B * c.Ho * c.Wo;
+    const int co0 = blockIdx.y * 64, ci0 = blockIdx.x * 64;
+    const int pbeg = split * c.pix_per_split;
+    int pend = pbeg + c.pix_per_split; if (pend > P) pend = P;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lpix = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;   // loader: pixel in chunk, 4-wide channel offset
+    float acc[4][4] = {};
+    for (int pc = pbeg; pc < pend; pc += 16) {
+        const int pp = pc + lpix;
+        float fa[4] = {0, 0, 0, 0}, fb[4] = {0, 0, 0, 0};
+        if (pp < pend) {
+            const int b = pp / (c.Ho * c.Wo), r = pp % (c.Ho * c.Wo), oy = r / c.Wo, ox = r % c.Wo;
+            const int co = co0 + lc;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (co + e < c.Co) fa[e] = __bfloat162float(c.dy[(long long)pp * c.Co + co + e]);
+            int iy, ix;
+            bool valid = conv_map_coord(c.map, oy, ky, c.stride, c.pad, c.Hi, iy) && conv_map_coord(c.map, ox, kx, c.stride, c.pad, c.Wi, ix);
+            if (c.ksize == 1 && c.map == MAP_NORMAL && c.stride == 1) { iy = oy; ix = ox; valid = true; }
+            if (valid) {
+                const long long ipix = ((long long)b * c.Hi + iy) * c.Wi + ix;
+                const int ci = ci0 + lc;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int cc = ci + e;
+                    if (cc < Cin) fb[e] = __bfloat162float(cc < c.in.C0 ? c.in.x0[ipix * c.in.C0 + cc] : c.in.x1[ipix * c.in.C1 + (cc - c.in.C0)]);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { As[lpix][lc + e] = fa[e]; Bs[lpix][lc + e] = fb[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= c.Co) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = ci0 + tx * 4 + j;
+            if (ci >= Cin) continue;
+            atomicAdd(c.dw + co * c.s_co + ci * c.s_ci + t * c.s_tap, acc[i][j]);
+        }
+    }
+}
+
+// ============================================================================ in_conv: NCHW fp32 [B,Ci<=4,H,W] -> NHWC bf16 [B,H,W,Co], 3x3 pad 1
+__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, const float* __restrict__ w /*OIHW fp32*/,
+                                                const float* __restrict__ bias, bf16* __restrict__ out,
+                                                int B, int Ci, int H, int W, int Co) {
+    extern __shared__ float sw[];                 // [Co][Ci*9] + [Co]
+    const int K = Ci * 9;
+    for (int i = threadIdx.x; i < Co * K; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Co; i += blockDim.x) sw[Co * K + i] = bias[i];
+    __syncthreads();
+    const int oct = Co >> 3;
+    const long long total = (long long)B * H * W * oct;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / oct;
+        const int c0 = (int)(i % oct) * 8;
+        const int b = (int)(pix / (H * W)), r = (int)(pix % (H * W)), y = r / W, xx = r % W;
+        float in[36];
+        for (int ci = 0; ci < Ci; ++ci)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+                in[ci * 9 + t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)b * Ci + ci) * H + iy) * W + ix) : 0.f;
+            }
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float s = sw[Co * K + c0 + e];
+            const float* wr = sw + (c0 + e) * K;
+            for (int k = 0; k < K; ++k) s += in[k] * wr[k];
+            o[e] = s;
+        }
+        *reinterpret_cast<uint4*>(out + pix * Co + c0) = pack8(o);
+    }
+}
+// wgrad of in_conv: dW[co][ci][tap] += sum_p dy[p][co] * x[b,ci,iy,ix]  ; one block per (co-octet range), split over pixels
+__global__ void __launch_bounds__(256) k_in_conv_wgrad(const bf16* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                                      float* __restrict__ dbias, int B, int Ci, int H, int W, int Co, int pix_per_block) {
+    // thread <-> output channel (Co <= 256); loops over its pixel range; accumulates K=Ci*9 partials in registers
+    const int co = threadIdx.x;
+    const long long P = (long long)B * H * W;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    long long p1 = p0 + pix_per_block; if (p1 > P) p1 = P;
+    float acc[36]; float accb = 0.f;
+    for (int k = 0; k < 36; ++k) acc[k] = 0.f;
+    __shared__ float sx[36];
+    for (long long p = p0; p < p1; ++p) {
+        const int b = (int)(p / (H * W)), r = (int)(p % (H * W)), y = r / W, xx = r % W;
+        __syncthreads();
+        if (threadIdx.x < Ci * 9) {
+            const int ci = threadIdx.x / 9, t = threadIdx.x % 9;
+            const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+            sx[threadIdx.x] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long long)b * Ci + ci) * H + iy) * W + ix] : 0.f;
+        }
+        __syncthreads();
+        if (co < Co) {
+            const float d = __bfloat162float(dy[p * Co + co]);
+            accb += d;
+            for (int k = 0; k < Ci * 9; ++k) acc[k] += d * sx[k];
+        }
+    }
+    if (co < Co) {
+        for (int k = 0; k < Ci * 9; ++k) atomicAdd(dw + (long long)co * Ci * 9 + k, acc[k]);
+        atomicAdd(dbias + co, accb);
+    }
+}
+
+// ============================================================================ column sums: per image and total
+// dy [B][HW][C] bf16 -> per_img[b][ld] (+=, fp32 atomics, optional) and total[c] (+=)
+__global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, float* per_img, int ld, float* total, int HW, int C, int pix_per_block) {
+    // blockDim.x = (256/oct)*oct: one channel octet per thread
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_block;
+    int p1 = p0 + pix_per_block; if (p1 > HW) p1 = HW;
+    const int oct = C >> 3;
+    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = p0 + lp; p < p1; p += pstep) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((long long)b * HW + p) * C + o * 8)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (per_img) atomicAdd(per_img + (long long)b * ld + o * 8 + e, s[e]);
+        if (total) atomicAdd(total + o * 8 + e, s[e]);
+    }
+}
+
+// ============================================================================ softmax over rows of S fp32 [rows][T] -> P bf16
+__global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int T) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* s = S + row * T;
+    float mx = -3.0e38f;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, s[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) sum += __expf(s[j] - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < T; j += 32) P[row * T + j] = __float2bfloat16_rn(__expf(s[j] - mx) * inv);
+}
+// dS = P * (dP - rowsum(dP*P)) * scale  -> bf16
+__global__ void __launch_bounds__(256) k_softmax_bwd(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
+                                                    long long rows, int T, float scale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    float dot = 0.f;
+    for (int j = lane; j < T; j += 32) dot += __bfloat162float(P[row * T + j]) * dP[row * T + j];
+    dot = warp_sum(dot);
+    for (int j = lane; j < T; j += 32)
+        dS[row * T + j] = __float2bfloat16_rn(__bfloat162float(P[row * T + j]) * (dP[row * T + j] - dot) * scale);
+}
+
+// ============================================================================ nearest 2x upsample (unet.py:199) and its adjoint
+__global__ void k_upsample2x(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+    const int oct = C >> 3;
+    const long long total = (long long)B * 4 * H * W * oct;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / oct; const int o = (int)(i % oct);
+        const int b = (int)(pix / (4 * H * W)), r = (int)(pix % (4 * H * W)), y = r / (2 * W), x = r % (2 * W);
+        reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(in) + (((long long)b * H + (y >> 1)) * W + (x >> 1)) * oct + o);
+    }
+}
+__global__ void k_upsample2x_bwd(const bf16* __restrict__ dout, bf16* __restrict__ din, int B, int H, int W, int C, int accumulate) {
+    const int oct = C >> 3;
+    const long long total = (long long)B * H * W * oct;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / oct; const int o = (int)(i % oct);
+        const int b = (int)(pix / (H * W)), r = (int)(pix % (H * W)), y = r / W, x = r % W;
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + (((long long)b * 2 * H + 2 * y + (q >> 1)) * 2 * W + 2 * x + (q & 1)) * oct + o), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += f[e];
+        }
+        if (accumulate) {
+            float f[8];
+            unpack8(reinterpret_cast<const uint4*>(din)[i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += f[e];
+        }
+        reinterpret_cast<uint4*>(din)[i] = pack8(s);
+    }
+}
+// dst (+)= src  (bf16, 8 at a time)
+__global__ void k_add_bf16(bf16* __restrict__ dst, const bf16* __restrict__ src, long long n_oct, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_oct; i += (long long)gridDim.x * blockDim.x) {
+        if (!accumulate) { reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i); continue; }
+        float a[8], b[8];
+        unpack8(reinterpret_cast<const uint4*>(dst)[i], a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src) + i), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += b[e];
+        reinterpret_cast<uint4*>(dst)[i] = pack8(a);
+    }
+}
+
+// ============================================================================ diffusion tails
+// q_sample (diffusion.py:92-97): x_t = sqrt_ab[t]*x0 + sqrt_1m_ab[t]*noise, fp32 NCHW, same op order as the reference
+__global__ void k_qsample(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
+                          const float* __restrict__ tab_a, const float* __restrict__ tab_s, float* __restrict__ xt, int per_img, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img);
+        const float a = tab_a[t[b]], s = tab_s[t[b]];
+        xt[i] = __fadd_rn(__fmul_rn(a, x0[i]), __fmul_rn(s, noise[i]));
+    }
+}
+// per-sample MSE (diffusion.py:239, functions.py:99-101) and d(loss)/d(eps) = gscale[b] * 2*(eps-target)/per_img as NHWC bf16
+__global__ void __launch_bounds__(256) k_mse(const float* __restrict__ eps, const float* __restrict__ target, float* __restrict__ losses, int per_img) {
+    const int b = blockIdx.x;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < per_img; i += blockDim.x) {
+        const float d = target[(long long)b * per_img + i] - eps[(long long)b * per_img + i];
+        s += d * d;
+    }
+    __shared__ float sh[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float tsum = 0.f; for (int w = 0; w < 8; ++w) tsum += sh[w]; losses[b] = tsum / (float)per_img; }
+}
+// grad of out_conv output: d_eps[b,c,h,w] fp32 NCHW -> bf16 NHWC padded to Cp channels (zeros)
+__global__ void k_mse_grad(const float* __restrict__ eps, const float* __restrict__ target, const float* __restrict__ gscale,
+                           bf16* __restrict__ dout, int B, int C, int HW, int Cp) {
+    const long long total = (long long)B * HW * Cp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp); const long long pix = i / Cp; const int b = (int)(pix / HW), r = (int)(pix % HW);
+        float v = 0.f;
+        if (c < C) {
+            const long long j = ((long long)b * C + c) * HW + r;
+            v = gscale[b] * 2.f * (eps[j] - target[j]) / (float)(C * HW);
+        }
+        dout[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void k_nchw_f32_to_nhwc_bf16(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C, int HW, int Cp) {
+    const long long total = (long long)B * HW * Cp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp); const long long pix = i / Cp; const int b = (int)(pix / HW), r = (int)(pix % HW);
+        dst[i] = __float2bfloat16_rn(c < C ? src[((long long)b * C + c) * HW + r] : 0.f);
+    }
+}
+// p_sample_step tail (diffusion.py:107-158, eps-prediction, fixed variance, clip_denoised):
+//   x0 = clamp(c0*x_t - c1*eps, -1, 1) ; mean = c2*x0 + c3*x_t ; x = mean + nz*sigma*z        coef = {c0,c1,c2,c3,sigma}
+__global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict__ x /*in: x_t, out: x_{t-1}*/, const float* __restrict__ z,
+                               const float* __restrict__ coef, int nonzero, long long total) {
+    const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], sg = coef[4];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float xt = x[i];
+        float x0 = __fsub_rn(__fmul_rn(c0, xt), __fmul_rn(c1, eps[i]));
+        x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        const float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, xt));
+        const float nz = nonzero ? 1.f : 0.f;
+        x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sg), z ? z[i] : 0.f));
+    }
+}
+
+// ============================================================================ weight (re)packing
+// OIHW fp32 -> fwd pack [Co][ld_f] at column k_off + tap*Ci + ci (bf16)   and   dgrad pack [Ci][ld_d] at tap'*Co + co,
+// tap' = flip ? 8 - tap : tap   (flip for stride-1 3x3; no flip for the stride-2 gather form and 1x1)
+__global__ void k_pack_conv_w(const float* __restrict__ w, bf16* fwd, long long ld_f, int k_off, bf16* dgr, long long ld_d, int flip,
+                              int Co, int Ci, int taps) {
+    const long long total = (long long)Co * Ci * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
+        const bf16 v = __float2bfloat16_rn(w[i]);
+        if (fwd) fwd[(long long)co * ld_f + k_off + (long long)t * Ci + ci] = v;
+        if (dgr) dgr[(long long)ci * ld_d + (long long)(flip ? taps - 1 - t : t) * Co + co] = v;
+    }
+}
+// packed grad [tap][Co][Ci] fp32 -> OIHW fp32 (=)
+__global__ void k_unpack_conv_grad(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps) {
+    const long long total = (long long)Co * Ci * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
+        g[i] = packed[((long long)t * Co + co) * Ci + ci];
+    }
+}
+__global__ void k_fill_f32(float* p, float v, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+// small fp32 elementwise helpers for the timestep-embedding MLP backward: dx = dy * silu'(x)
+__global__ void k_silu_bwd_f32(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dx[i] = dy[i] * silu_grad_f(x[i]);
+}
+
+}  // namespace ddpm

@@ -15,9 +15,11 @@ enum EpiFlags { EPI_OUT_F32 = 1, EPI_ATOMIC = 2 };
 
 struct GemmSeg {
     int map;       // which A tensor map (0..2)
-    int taps;      // 1 or 9 (3x3, pad 1, stride 1; tap t -> dx = t%3-1, dy = t/3-1)
+    int taps;      // number of spatial taps (1..9)
     int kchunks;   // channel chunks of 64 in this segment
     int c_base;    // first channel coordinate inside the map
+    int cmul;      // coordinate multiplier of the tile origin (1; 2 for stride-2 maps built with elementStrides=2)
+    signed char dx[9], dy[9];   // per-tap coordinate offsets (3x3 pad 1: dx = t%3-1, dy = t/3-1)
 };
 
 struct GemmParams {
@@ -132,13 +134,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const GemmSeg sg = p.seg[s];
                     const CUtensorMap* mA = sg.map == 0 ? &tmA0 : (sg.map == 1 ? &tmA1 : &tmA2);
                     for (int t = 0; t < sg.taps && ok; ++t) {
-                        const int dx = sg.taps == 9 ? (t % 3) - 1 : 0;
-                        const int dy = sg.taps == 9 ? (t / 3) - 1 : 0;
+                        const int xc = x0 * sg.cmul + sg.dx[t];
+                        const int yc = y0 * sg.cmul + sg.dy[t];
                         for (int kc = 0; kc < sg.kchunks; ++kc, ++slab, ++kcount) {
                             uint8_t* st = acquire(slab);
                             if (!st) break;
                             uint64_t* fb = &full_bar[slab % STAGES];
-                            tma_load_4d(st, mA, fb, sg.c_base + kc * 64, x0 + dx, y0 + dy, n0);
+                            tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
                             tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
                         }
                     }
