@@ -29,6 +29,12 @@ class GemmDesc(C.Structure):
     ]
 
 
+class UnetCfg(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("hid_channels", C.c_int), ("out_channels", C.c_int),
+                ("levels", C.c_int), ("ch_mult", C.c_int * 8), ("num_res_blocks", C.c_int), ("attn", C.c_int * 8),
+                ("temb_dim", C.c_int), ("drop_rate", C.c_float)]
+
+
 _lib = None
 
 
@@ -46,8 +52,41 @@ def lib():
         L.ddpm_device_error_flag.restype = C.c_int
         L.ddpm_gemm_run.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
         L.ddpm_gemm_run.restype = C.c_int
+        vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_uint64
+        sig = {
+            "ddpm_unet_create": ([C.POINTER(UnetCfg), C.POINTER(vp)], i32),
+            "ddpm_unet_destroy": ([vp], None),
+            "ddpm_unet_num_params": ([vp], i32),
+            "ddpm_unet_param_info": ([vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32 * 4), C.POINTER(i64)], i32),
+            "ddpm_unet_flat_elems": ([vp], i64),
+            "ddpm_unet_workspace_bytes": ([vp, i32, i32, i32, i32], i64),
+            "ddpm_unet_plan": ([vp, i32, i32, i32, i32, vp, vp, vp, i64], i32),
+            "ddpm_unet_repack": ([vp, vp], i32),
+            "ddpm_unet_forward": ([vp, vp, vp, vp, u64, vp], i32),
+            "ddpm_unet_backward": ([vp, vp, vp], i32),
+            "ddpm_train_forward": ([vp, vp, vp, vp, vp, vp, vp, u64, vp], i32),
+            "ddpm_train_backward": ([vp, vp, vp], i32),
+            "ddpm_sampler_setup": ([vp, i32, vp, vp], i32),
+            "ddpm_sampler_reset": ([vp, i32, vp], i32),
+            "ddpm_sampler_step": ([vp, vp, vp, u64, vp], i32),
+            "ddpm_unet_plan_stats": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
+            "ddpm_unet_launches_per_forward": ([vp], i32),
+        }
+        for name, (args, res) in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
         _lib = L
     return _lib
+
+
+EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "ddpm_gemm_run",
+           "ddpm_unet_create", "ddpm_unet_destroy", "ddpm_unet_num_params", "ddpm_unet_param_info",
+           "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
+           "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",
+           "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_unet_plan_stats",
+           "ddpm_unet_launches_per_forward"]
 
 
 def check(rc, what=""):

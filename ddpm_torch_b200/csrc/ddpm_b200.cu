@@ -1,9 +1,18 @@
 // libddpm_b200.so — single translation unit (device-side error flag and kernels share one module).
 #include <cstdarg>
-#include "gemm_build.cuh"
-#include "kernels_simt.cuh"
+#include <new>
+#include "unet_engine_impl.cuh"
 
 using namespace ddpm;
+
+struct ddpm_unet {
+    UnetEngine e;
+    // sampler tables (device, owned by the handle; allocated by ddpm_sampler_setup, never per step)
+    long long* d_tmodel = nullptr; float* d_coef = nullptr; int S = 0;
+    const float* train_target = nullptr;
+};
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
 
 extern "C" {
 
@@ -12,9 +21,10 @@ const char* ddpm_last_error(void) { return last_error().c_str(); }
 int ddpm_runtime_check(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(-1, "no CUDA device / driver"); }
+    int dev = 0; cudaGetDevice(&dev);
     cudaDeviceProp pr;
-    DDPM_CUDA_OK(cudaGetDeviceProperties(&pr, 0));
-    if (pr.major != 10) return fail(-1, "device 0 is sm_%d%d, this library is sm_100a only", pr.major, pr.minor);
+    DDPM_CUDA_OK(cudaGetDeviceProperties(&pr, dev));
+    if (pr.major != 10) return fail(-1, "device %d is sm_%d%d, this library is sm_100a only", dev, pr.major, pr.minor);
     if (!tmap_encode_fn()) return fail(-3, "cuTensorMapEncodeTiled unavailable");
     return 0;
 }
@@ -32,5 +42,155 @@ int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream) {
     if (rc) return rc;
     return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
+
+// ------------------------------------------------------------------------------------------------ UNet engine
+int ddpm_unet_create(const ddpm_unet_cfg* cfg, ddpm_unet** out) {
+    if (!cfg || !out) return fail(-30, "null argument");
+    if (cfg->levels < 1 || cfg->levels > 8) return fail(-30, "levels must be 1..8");
+    if (cfg->hid_channels <= 0 || cfg->hid_channels % 32) return fail(-30, "hid_channels must be a positive multiple of 32");
+    if (cfg->num_res_blocks < 1) return fail(-30, "num_res_blocks must be >= 1");
+    ddpm_unet* h = new (std::nothrow) ddpm_unet();
+    if (!h) return fail(-30, "out of host memory");
+    h->e.cfg = *cfg;
+    if (h->e.cfg.temb_dim <= 0) h->e.cfg.temb_dim = 4 * cfg->hid_channels;
+    h->e.register_params();
+    *out = h;
+    return 0;
+}
+void ddpm_unet_destroy(ddpm_unet* h) {
+    if (!h) return;
+    if (h->d_tmodel) cudaFree(h->d_tmodel);
+    if (h->d_coef) cudaFree(h->d_coef);
+    delete h;
+}
+int ddpm_unet_num_params(const ddpm_unet* h) { return (int)h->e.params.size(); }
+int ddpm_unet_param_info(const ddpm_unet* h, int i, const char** name, int* ndim, int dims[4], long long* offset) {
+    if (i < 0 || i >= (int)h->e.params.size()) return fail(-30, "param index out of range");
+    const ParamInfo& p = h->e.params[i];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = p.nd;
+    if (dims) for (int k = 0; k < 4; ++k) dims[k] = p.dims[k];
+    if (offset) *offset = p.off;
+    return 0;
+}
+long long ddpm_unet_flat_elems(const ddpm_unet* h) { return h->e.flat_elems; }
+
+long long ddpm_unet_workspace_bytes(ddpm_unet* h, int B, int H, int W, int training) {
+    UnetEngine& e = h->e;
+    e.P = nullptr; e.G = nullptr; e.ws = nullptr; e.planned = false;
+    e.zf_cursor = e.zb_cursor = 0;
+    const int rc = e.plan(B, H, W, training != 0, true);
+    if (rc) return rc;
+    return (long long)(e.cursor + e.zf_cursor + e.zb_cursor + 8192);
+}
+int ddpm_unet_plan(ddpm_unet* h, int B, int H, int W, int training, float* params_flat, float* grads_flat, void* workspace, long long workspace_bytes) {
+    UnetEngine& e = h->e;
+    if (!params_flat || !workspace) return fail(-30, "params / workspace pointer is null");
+    if (training && !grads_flat) return fail(-30, "training plan needs a gradient buffer");
+    int rc = ddpm_runtime_check(); if (rc) return rc;
+    e.planned = false;
+    e.P = params_flat; e.G = grads_flat; e.ws = static_cast<uint8_t*>(workspace); e.ws_bytes = (size_t)workspace_bytes;
+    e.zf_cursor = e.zb_cursor = 0;
+    if ((rc = e.plan(B, H, W, training != 0, true))) return rc;
+    if ((long long)(e.cursor + e.zf_cursor + e.zb_cursor + 8192) > workspace_bytes)
+        return fail(-32, "workspace too small: need %lld bytes, got %lld", (long long)(e.cursor + e.zf_cursor + e.zb_cursor + 8192), workspace_bytes);
+    if ((rc = e.plan(B, H, W, training != 0, false))) return rc;
+    if ((long long)e.cursor > workspace_bytes) return fail(-32, "workspace overflow (internal)");
+    return e.build();
+}
+#define NEED_PLAN(h) do { if (!(h) || !(h)->e.planned) return fail(-33, "ddpm_unet_plan has not been called"); } while (0)
+
+int ddpm_unet_repack(ddpm_unet* h, void* stream) { NEED_PLAN(h); return h->e.run_list(h->e.pack_ops, static_cast<cudaStream_t>(stream)); }
+
+int ddpm_unet_forward(ddpm_unet* h, const float* x, const int64_t* t, float* eps, uint64_t dropout_seed, void* stream) {
+    NEED_PLAN(h);
+    UnetEngine& e = h->e;
+    e.x_in = x; e.t_in = reinterpret_cast<const long long*>(t); e.eps_dst = eps; e.drop_seed = dropout_seed;
+    return e.run_list(e.fwd_ops, static_cast<cudaStream_t>(stream));
+}
+int ddpm_unet_backward(ddpm_unet* h, const float* d_eps, void* stream) {
+    NEED_PLAN(h);
+    UnetEngine& e = h->e;
+    if (!e.train) return fail(-33, "plan was built without training");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Cout = e.cfg.out_channels, HW = e.H * e.W;
+    k_nchw_f32_to_nhwc_bf16<<<grid_for((long long)e.B * HW * 8), 256, 0, st>>>(d_eps, e.at<bf16>(e.deps_off), e.B, Cout, HW, 8);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return e.run_list(e.bwd_ops, st);
+}
+int ddpm_train_forward(ddpm_unet* h, const float* x0, const int64_t* t, const float* noise, const float* tab_a, const float* tab_s,
+                       float* losses, uint64_t dropout_seed, void* stream) {
+    NEED_PLAN(h);
+    UnetEngine& e = h->e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int per_img = e.cfg.in_channels * e.H * e.W;
+    const long long total = (long long)e.B * per_img;
+    float* xt = e.at<float>(e.xt_off); float* eps = e.at<float>(e.eps_off);
+    k_qsample<<<grid_for(total), 256, 0, st>>>(x0, noise, reinterpret_cast<const long long*>(t), tab_a, tab_s, xt, per_img, total);
+    DDPM_CUDA_OK(cudaGetLastError());
+    e.x_in = xt; e.t_in = reinterpret_cast<const long long*>(t); e.eps_dst = eps; e.drop_seed = dropout_seed;
+    const int rc = e.run_list(e.fwd_ops, st);
+    if (rc) return rc;
+    h->train_target = noise;
+    k_mse<<<e.B, 256, 0, st>>>(eps, noise, losses, e.cfg.out_channels * e.H * e.W);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int ddpm_train_backward(ddpm_unet* h, const float* gscale, void* stream) {
+    NEED_PLAN(h);
+    UnetEngine& e = h->e;
+    if (!e.train || !h->train_target) return fail(-33, "ddpm_train_forward must precede ddpm_train_backward on a training plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HW = e.H * e.W;
+    k_mse_grad<<<grid_for((long long)e.B * HW * 8), 256, 0, st>>>(e.at<float>(e.eps_off), h->train_target, gscale, e.at<bf16>(e.deps_off),
+                                                                 e.B, e.cfg.out_channels, HW, 8);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return e.run_list(e.bwd_ops, st);
+}
+
+int ddpm_sampler_setup(ddpm_unet* h, int S, const int64_t* t_model_host, const float* coef_host) {
+    if (!h || S <= 0) return fail(-30, "bad sampler setup");
+    if (h->d_tmodel) { cudaFree(h->d_tmodel); h->d_tmodel = nullptr; }
+    if (h->d_coef) { cudaFree(h->d_coef); h->d_coef = nullptr; }
+    DDPM_CUDA_OK(cudaMalloc(&h->d_tmodel, (size_t)S * 8));
+    DDPM_CUDA_OK(cudaMalloc(&h->d_coef, (size_t)S * 6 * 4));
+    DDPM_CUDA_OK(cudaMemcpy(h->d_tmodel, t_model_host, (size_t)S * 8, cudaMemcpyHostToDevice));
+    DDPM_CUDA_OK(cudaMemcpy(h->d_coef, coef_host, (size_t)S * 6 * 4, cudaMemcpyHostToDevice));
+    h->S = S;
+    return 0;
+}
+int ddpm_sampler_reset(ddpm_unet* h, int first_step, void* stream) {
+    NEED_PLAN(h);
+    if (first_step < 0 || first_step >= h->S) return fail(-30, "first_step out of range");
+    k_set_int<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(h->e.at<int>(h->e.counter_off), first_step);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, void* stream) {
+    NEED_PLAN(h);
+    if (!h->d_coef) return fail(-33, "ddpm_sampler_setup has not been called");
+    UnetEngine& e = h->e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long* tbuf = e.at<long long>(e.tbuf_off); float* cc = e.at<float>(e.coefcur_off); float* eps = e.at<float>(e.eps_off);
+    k_sampler_prep<<<1, 256, 0, st>>>(e.at<int>(e.counter_off), h->d_tmodel, h->d_coef, tbuf, cc, e.B);
+    DDPM_CUDA_OK(cudaGetLastError());
+    e.x_in = x; e.t_in = tbuf; e.eps_dst = eps; e.drop_seed = 0;
+    const int rc = e.run_list(e.fwd_ops, st);
+    if (rc) return rc;
+    const long long total = (long long)e.B * e.cfg.out_channels * e.H * e.W;
+    k_psample_tail<<<grid_for(total), 256, 0, st>>>(eps, x, z, cc, (unsigned long long)seed, total);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd, int* n_bwd, int* n_tc, int* n_gen, double* ff, double* bf) {
+    if (n_fwd) *n_fwd = (int)h->e.fwd_ops.size();
+    if (n_bwd) *n_bwd = (int)h->e.bwd_ops.size();
+    if (n_tc) *n_tc = h->e.n_tc_gemms;
+    if (n_gen) *n_gen = h->e.n_generic;
+    if (ff) *ff = h->e.fwd_flops;
+    if (bf) *bf = h->e.bwd_flops;
+    return 0;
+}
+int ddpm_unet_launches_per_forward(const ddpm_unet* h) { return (int)h->e.fwd_ops.size(); }
 
 }  // extern "C"

@@ -87,17 +87,22 @@ struct SgemmParams {
     const void* A; const void* B; void* C; const float* bias;
     int M, N, K;
     long long sa_m, sa_k, sa_z, sb_k, sb_n, sb_z, sc_m, sc_n, sc_z;
-    float alpha; int accumulate; int silu_a;
+    float alpha; int accumulate; int silu_a;      // accumulate: 1 = C += (read-modify-write), 2 = atomicAdd (TC = float only)
 };
 
+template <typename TC> __device__ __forceinline__ void atomic_addf(TC* p, float v);
+template <> __device__ __forceinline__ void atomic_addf<float>(float* p, float v) { atomicAdd(p, v); }
+template <> __device__ __forceinline__ void atomic_addf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(__bfloat162float(*p) + v); }
+
 template <typename TA, typename TB, typename TC>
-__global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) {
+__device__ __forceinline__ void sgemm_body(const SgemmParams& p, int bz) {
     __shared__ float As[16][65];
     __shared__ float Bs[16][65];
-    const TA* A = reinterpret_cast<const TA*>(p.A) + (long long)blockIdx.z * p.sa_z;
-    const TB* Bm = reinterpret_cast<const TB*>(p.B) + (long long)blockIdx.z * p.sb_z;
-    TC* C = reinterpret_cast<TC*>(p.C) + (long long)blockIdx.z * p.sc_z;
+    const TA* A = reinterpret_cast<const TA*>(p.A) + (long long)bz * p.sa_z;
+    const TB* Bm = reinterpret_cast<const TB*>(p.B) + (long long)bz * p.sb_z;
+    TC* C = reinterpret_cast<TC*>(p.C) + (long long)bz * p.sc_z;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    if (m0 >= p.M || n0 >= p.N) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[4][4] = {};
     for (int k0 = 0; k0 < p.K; k0 += 16) {
@@ -134,10 +139,30 @@ __global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) {
             float v = acc[i][j] * p.alpha;
             if (p.bias) v += p.bias[n];
             TC* c = C + (long long)m * p.sc_m + (long long)n * p.sc_n;
+            if (p.accumulate == 2) { atomic_addf<TC>(c, v); continue; }
             if (p.accumulate) v += ldf<TC>(c);
             stf<TC>(c, v);
         }
     }
+}
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) { sgemm_body<TA, TB, TC>(p, blockIdx.z); }
+// table-driven: blockIdx.z selects an independent problem (per-ResBlock timestep projections)
+__global__ void __launch_bounds__(256) k_sgemm_table(const SgemmParams* __restrict__ table) {
+    const SgemmParams p = table[blockIdx.z];
+    sgemm_body<float, float, float>(p, 0);
+}
+// column sums of an fp32 [M][N] matrix (bias grads of the timestep MLP): out[n] += sum_m A[m][n]
+__global__ void k_colsum_f32(const float* __restrict__ A, float* __restrict__ out, int M, int N, long long lda) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += A[(long long)m * lda + n];
+    atomicAdd(out + n, s);
+}
+__global__ void k_add_f32(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
 }
 
 // ============================================================================ GroupNorm (32 groups, eps 1e-6; unet.py:18-20)
@@ -228,6 +253,7 @@ struct GnBwd {
     GnSrc s; const bf16* dy; const float* mr; const float* gamma; const float* beta;
     double* red; float* dgamma; float* dbeta;
     bf16* dx0; bf16* dx1; int acc0, acc1;                         // destinations for the two sources (accumulate flags)
+    const bf16* addend;                                           // optional [B,HW,C] term added to dx (skip-path gradient)
     int HW; int pix_per_block; int silu; float drop_p; unsigned long long seed; uint32_t layer; long long total_oct;
 };
 __global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwd a) {   // blockDim.x = (256/oct)*oct, see k_gn_stats
@@ -301,8 +327,9 @@ __global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwd a) {
         if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)i * 8, a.drop_p);
         bf16* dst = first ? a.dx0 + pix * a.s.C0 + c : a.dx1 + pix * a.s.C1 + (c - a.s.C0);
         const int acc = first ? a.acc0 : a.acc1;
-        float o[8];
+        float o[8], ad[8];
         if (acc) unpack8(*reinterpret_cast<const uint4*>(dst), o);
+        if (a.addend) unpack8(__ldg(reinterpret_cast<const uint4*>(a.addend + pix * C + c)), ad);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int g = (c + e) / cg;
@@ -313,7 +340,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwd a) {
             if (a.silu) dn *= silu_grad_f(xh * ga + __ldg(a.beta + c + e));
             const float dh = dn * ga;
             const float s1 = (float)a.red[(b * 32 + g) * 2] * inv_n, s2 = (float)a.red[(b * 32 + g) * 2 + 1] * inv_n;
-            const float v = r * (dh - s1 - xh * s2);
+            const float v = r * (dh - s1 - xh * s2) + (a.addend ? ad[e] : 0.f);
             o[e] = acc ? o[e] + v : v;
         }
         *reinterpret_cast<uint4*>(dst) = pack8(o);
@@ -428,6 +455,7 @@ __global__ void __launch_bounds__(256) k_conv_generic(const ConvG c) {
 struct WgradG {
     const bf16* dy; GnSrc in; float* dw; long long s_co, s_ci, s_tap;
     int B, Hi, Wi, Ho, Wo, Co, ksize, stride, pad, map, pix_per_split;
+    int Co_valid;                                 // rows of dW actually written (dy may be channel-padded)
 };
 __global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
     __shared__ float As[16][65];   // [pixel][co]
@@ -482,7 +510,7 @@ __global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int co = co0 + ty * 4 + i;
-        if (co >= c.Co) continue;
+        if (co >= c.Co_valid) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int ci = ci0 + tx * 4 + j;
@@ -559,7 +587,8 @@ __global__ void __launch_bounds__(256) k_in_conv_wgrad(const bf16* __restrict__ 
 
 // ============================================================================ column sums: per image and total
 // dy [B][HW][C] bf16 -> per_img[b][ld] (+=, fp32 atomics, optional) and total[c] (+=)
-__global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, float* per_img, int ld, float* total, int HW, int C, int pix_per_block) {
+__global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, float* per_img, int ld, float* total, float* total2,
+                                               int HW, int C, int C_valid, int pix_per_block) {
     // blockDim.x = (256/oct)*oct: one channel octet per thread
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_block;
@@ -575,8 +604,10 @@ __global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, flo
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
+        if (o * 8 + e >= C_valid) break;
         if (per_img) atomicAdd(per_img + (long long)b * ld + o * 8 + e, s[e]);
         if (total) atomicAdd(total + o * 8 + e, s[e]);
+        if (total2) atomicAdd(total2 + o * 8 + e, s[e]);
     }
 }
 
@@ -702,17 +733,36 @@ __global__ void k_nchw_f32_to_nhwc_bf16(const float* __restrict__ src, bf16* __r
 }
 // p_sample_step tail (diffusion.py:107-158, eps-prediction, fixed variance, clip_denoised):
 //   x0 = clamp(c0*x_t - c1*eps, -1, 1) ; mean = c2*x0 + c3*x_t ; x = mean + nz*sigma*z        coef = {c0,c1,c2,c3,sigma}
+//   coef[5] = nonzero flag (t>0) as float, coef[6] = step index (for the built-in noise stream)
+//   z == nullptr and seed != 0: the noise is drawn in-kernel (Philox4x32-10 + Box-Muller; NOT torch's stream)
 __global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict__ x /*in: x_t, out: x_{t-1}*/, const float* __restrict__ z,
-                               const float* __restrict__ coef, int nonzero, long long total) {
-    const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], sg = coef[4];
+                               const float* __restrict__ coef, unsigned long long seed, long long total) {
+    const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], sg = coef[4], nz = coef[5];
+    const uint32_t step = (uint32_t)coef[6];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const float xt = x[i];
         float x0 = __fsub_rn(__fmul_rn(c0, xt), __fmul_rn(c1, eps[i]));
         x0 = fminf(fmaxf(x0, -1.f), 1.f);
         const float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, xt));
-        const float nz = nonzero ? 1.f : 0.f;
-        x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sg), z ? z[i] : 0.f));
+        float zz = 0.f;
+        if (z) zz = z[i];
+        else if (seed) {
+            const uint4 r = philox4x32((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)seed ^ (step * 0x9E3779B1u), (uint32_t)(seed >> 32));
+            const float u1 = ((float)r.x + 1.f) * 2.3283064365386963e-10f, u2 = (float)r.y * 2.3283064365386963e-10f;
+            zz = sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+        }
+        x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sg), zz));
     }
+}
+// one block: fetch step i = *counter, broadcast t_model[i] to t_buf[B], copy the coefficient row, then advance the counter
+__global__ void k_sampler_prep(int* __restrict__ counter, const long long* __restrict__ t_model, const float* __restrict__ coef_table /*[S][6]*/,
+                               long long* __restrict__ t_buf, float* __restrict__ coef_cur /*[7]*/, int B) {
+    const int i = *counter;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) t_buf[b] = t_model[i];
+    if (threadIdx.x < 6) coef_cur[threadIdx.x] = coef_table[i * 6 + threadIdx.x];
+    if (threadIdx.x == 6) coef_cur[6] = (float)i;
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = i - 1;
 }
 
 // ============================================================================ weight (re)packing
@@ -728,12 +778,24 @@ __global__ void k_pack_conv_w(const float* __restrict__ w, bf16* fwd, long long 
         if (dgr) dgr[(long long)ci * ld_d + (long long)(flip ? taps - 1 - t : t) * Co + co] = v;
     }
 }
-// packed grad [tap][Co][Ci] fp32 -> OIHW fp32 (=)
-__global__ void k_unpack_conv_grad(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps) {
+// dgrad pack with a padded Co (out_conv: Co=3 -> 8): dgr[ci][tap'*Cop + co]
+__global__ void k_pack_conv_w_padded(const float* __restrict__ w, bf16* dgr, long long ld_d, int flip, int Co, int Cop, int Ci, int taps) {
     const long long total = (long long)Co * Ci * taps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
-        g[i] = packed[((long long)t * Co + co) * Ci + ci];
+        dgr[(long long)ci * ld_d + (long long)(flip ? taps - 1 - t : t) * Cop + co] = __float2bfloat16_rn(w[i]);
+    }
+}
+
+// packed grad [tap][Co][Ci] fp32 -> OIHW fp32 (=)
+// (the scratch is cleared behind the read so the next backward starts from zeros without a memset)
+__global__ void k_unpack_conv_grad(float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps) {
+    const long long total = (long long)Co * Ci * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
+        const long long j = ((long long)t * Co + co) * Ci + ci;
+        g[i] = packed[j];
+        packed[j] = 0.f;
     }
 }
 __global__ void k_fill_f32(float* p, float v, long long n) {

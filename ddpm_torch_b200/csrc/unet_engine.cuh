@@ -1,0 +1,346 @@
+// UNet plan builder + executor.  The network of ddpm_torch/models/unet.py:92-233 is compiled once per
+// (batch, resolution) into flat lists of kernel launches (pack / forward / backward) over a caller-owned workspace.
+// The backward list is produced tape-style: every forward block registers a closure that appends its adjoint ops.
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+#include "gemm_build.cuh"
+#include "kernels_simt.cuh"
+
+namespace ddpm {
+
+struct ParamInfo { std::string name; int nd; int dims[4]; long long numel; long long off; };
+struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
+            long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
+struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
+struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; };
+struct GnSaved { Src in; float* mr; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; };
+
+static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
+static inline int oct_threads(int C) { const int oct = C / 8; return oct <= 256 ? (256 / oct) * oct : 0; }
+
+struct UnetEngine {
+    ddpm_unet_cfg cfg;
+    std::vector<ParamInfo> params;
+    std::map<std::string, int> pidx;
+    long long flat_elems = 0;
+    // bound buffers
+    float* P = nullptr; float* G = nullptr;
+    uint8_t* ws = nullptr; size_t ws_bytes = 0;
+    // plan state
+    int B = 0, H = 0, W = 0; bool train = false; bool dry = true; size_t cursor = 0; bool planned = false;
+    std::vector<Op> pack_ops, fwd_ops, bwd_ops;
+    std::vector<std::function<void()>> tape;
+    std::map<long long, std::pair<T4, bool>> grads;     // fwd tensor offset -> (grad tensor, written?)
+    size_t zero_fwd_off = 0, zero_fwd_bytes = 0, zero_bwd_off = 0, zero_bwd_bytes = 0;   // per-pass zeroed regions
+    size_t once_zero_off = 0, once_zero_bytes = 0;                                       // zeroed at plan time only
+    std::vector<SgemmParams> tp_table_host; size_t tp_table_off = 0; int tp_max_c = 0;
+    std::vector<SgemmParams> tpw_table_host, tpd_table_host; size_t tpw_table_off = 0, tpd_table_off = 0;
+    uint32_t layer_counter = 0;
+    double fwd_flops = 0, bwd_flops = 0;
+    int n_tc_gemms = 0, n_generic = 0;
+    // per-call IO (read by ops at run time)
+    const float* x_in = nullptr; const long long* t_in = nullptr; float* eps_out = nullptr;
+    unsigned long long drop_seed = 0;
+    // diffusion-side internal buffers
+    size_t xt_off = 0, eps_off = 0, tbuf_off = 0, coefcur_off = 0, counter_off = 0, deps_off = 0;
+
+    // ------------------------------------------------------------------ parameters (reference registration order)
+    void add_param(const std::string& n, std::initializer_list<int> d) {
+        ParamInfo p; p.name = n; p.nd = (int)d.size(); p.numel = 1; int i = 0;
+        for (int v : d) { p.dims[i++] = v; p.numel *= v; }
+        for (; i < 4; ++i) p.dims[i] = 1;
+        p.off = flat_elems; flat_elems += (p.numel + 63) / 64 * 64;
+        pidx[n] = (int)params.size(); params.push_back(p);
+    }
+    void reg_lin(const std::string& p, int i, int o) { add_param(p + ".weight", {o, i}); add_param(p + ".bias", {o}); }
+    void reg_conv(const std::string& p, int i, int o, int k) { add_param(p + ".weight", {o, i, k, k}); add_param(p + ".bias", {o}); }
+    void reg_gn(const std::string& p, int n) { add_param(p + ".weight", {n}); add_param(p + ".bias", {n}); }
+    void reg_res(const std::string& p, int i, int o) {
+        reg_gn(p + ".norm1", i); reg_conv(p + ".conv1", i, o, 3); reg_lin(p + ".fc", cfg.temb_dim, o);
+        reg_gn(p + ".norm2", o); reg_conv(p + ".conv2", o, o, 3);
+        if (i != o) reg_conv(p + ".skip", i, o, 1);
+    }
+    void reg_attn(const std::string& p, int n) { reg_gn(p + ".norm", n); reg_conv(p + ".project_in", n, 3 * n, 1); reg_conv(p + ".project_out", n, n, 1); }
+    void reg_block(const std::string& p, int i, int o, bool at) { if (at) { reg_res(p + ".0", i, o); reg_attn(p + ".1", o); } else reg_res(p, i, o); }
+    int chs(int l) const { return cfg.hid_channels * cfg.ch_mult[l]; }
+    void register_params() {
+        const int ch = cfg.hid_channels, L = cfg.levels, nrb = cfg.num_res_blocks, E = cfg.temb_dim;
+        reg_lin("embed.0", ch, E); reg_lin("embed.2", E, E);
+        reg_conv("in_conv", cfg.in_channels, ch, 3);
+        for (int i = 0; i < L; ++i) {
+            const int prev = i ? chs(i - 1) : ch, cur = chs(i);
+            const std::string p = "downsamples.level_" + std::to_string(i);
+            reg_block(p + ".0", prev, cur, cfg.attn[i]);
+            for (int j = 1; j < nrb; ++j) reg_block(p + "." + std::to_string(j), cur, cur, cfg.attn[i]);
+            if (i != L - 1) reg_conv(p + "." + std::to_string(nrb) + ".1", cur, cur, 3);
+        }
+        const int mid = chs(L - 1);
+        reg_res("middle.0", mid, mid); reg_attn("middle.1", mid); reg_res("middle.2", mid, mid);
+        for (int i = 0; i < L; ++i) {
+            const int nxt = i == 0 ? ch : chs(i - 1), prev = i == L - 1 ? chs(L - 1) : chs(i + 1), cur = chs(i);
+            const std::string p = "upsamples.level_" + std::to_string(i);
+            reg_block(p + ".0", prev + cur, cur, cfg.attn[i]);
+            for (int j = 1; j < nrb; ++j) reg_block(p + "." + std::to_string(j), 2 * cur, cur, cfg.attn[i]);
+            reg_block(p + "." + std::to_string(nrb), nxt + cur, cur, cfg.attn[i]);
+            if (i != 0) reg_conv(p + "." + std::to_string(nrb + 1) + ".1", cur, cur, 3);
+        }
+        reg_gn("out_conv.0", ch); reg_conv("out_conv.2", ch, cfg.out_channels, 3);
+    }
+    const ParamInfo& pinfo(const std::string& n) const { return params[pidx.at(n)]; }
+    float* PP(const std::string& n) const { return P + pinfo(n).off; }
+    float* GP(const std::string& n) const { return G ? G + pinfo(n).off : nullptr; }
+
+    // ------------------------------------------------------------------ workspace
+    size_t alloc(size_t bytes) { const size_t o = (cursor + 1023) & ~size_t(1023); cursor = o + bytes; return o; }
+    template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
+    T4 newT(int b, int h, int w, int c) { T4 t; t.B = b; t.H = h; t.W = w; t.C = c; t.off = (long long)alloc((size_t)t.numel() * 2); return t; }
+    bf16* bp(const T4& t) const { return at<bf16>((size_t)t.off); }
+    GnSrc gsrc(const Src& s) const { GnSrc g; g.x0 = bp(s.t0); g.C0 = s.t0.C; g.x1 = s.two ? bp(s.t1) : nullptr; g.C1 = s.two ? s.t1.C : 0; return g; }
+    static Src one(const T4& t) { Src s; s.t0 = t; s.two = false; return s; }
+
+    void push(std::vector<Op>& L, const std::string& name, double flops, std::function<int(cudaStream_t)> f) {
+        Op o; o.name = name; o.flops = flops; o.run = std::move(f); L.push_back(std::move(o));
+    }
+    // grad tensor of a forward tensor; `first` tells the producer whether to overwrite (=) or accumulate (+=)
+    T4 grad_of(const T4& t, bool* first) {
+        auto it = grads.find(t.off);
+        if (it == grads.end()) { T4 g = newT(t.B, t.H, t.W, t.C); it = grads.emplace(t.off, std::make_pair(g, false)).first; }
+        if (first) { *first = !it->second.second; it->second.second = true; }
+        return it->second.first;
+    }
+    bool has_grad(const T4& t) const { auto it = grads.find(t.off); return it != grads.end() && it->second.second; }
+
+    // ------------------------------------------------------------------ op builders
+    bool tc_ok_geom(int h, int w) const { int a, b, c; return pick_box(w, h, 128, a, b, c) && pick_box(w, h, 64, a, b, c); }
+
+    // conv: out = conv(in) [+ 1x1 skip(skip_in)] + bias + rowvec[b] + residual ; packed weights [Co][ldw]
+    struct ConvSpec {
+        std::string name; Src in; int ksize = 3, stride = 1, map = MAP_NORMAL;
+        const bf16* wp = nullptr; long long ldw = 0; bool has_skip = false; Src skip_in;
+        const float* bias = nullptr; const float* rowvec = nullptr; int rowvec_ld = 0; const bf16* residual = nullptr;
+        T4 out; float* out_nchw = nullptr; int Co = 0; int Ho = 0, Wo = 0; bool accumulate = false;
+    };
+    void conv_op(std::vector<Op>& L, const ConvSpec& c, double* flops_acc) {
+        const int Cin = c.in.C(), taps = c.ksize * c.ksize;
+        const T4& i0 = c.in.t0;
+        const int Bn = i0.B;
+        const long long Pout = (long long)Bn * c.Ho * c.Wo;
+        double fl = 2.0 * Pout * c.Co * (double)(taps * Cin + (c.has_skip ? c.skip_in.C() : 0));
+        if (flops_acc) *flops_acc += fl;
+        bool tc = c.stride == 1 && c.map == MAP_NORMAL && !c.out_nchw && !c.in.two && (i0.C % 64 == 0) && (c.Co % 64 == 0) &&
+                  c.Ho == i0.H && c.Wo == i0.W && tc_ok_geom(i0.H, i0.W) && !(c.accumulate && c.residual);
+        if (c.has_skip) tc = tc && (c.skip_in.t0.C % 64 == 0) && (!c.skip_in.two || c.skip_in.t1.C % 64 == 0);
+        if (tc) {
+            ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+            d.mode = GEMM_KK; d.M = (int)Pout; d.N = c.Co; d.W = i0.W; d.H = i0.H; d.NB = Bn;
+            d.a_ptr[0] = bp(i0); d.a_C[0] = i0.C; d.a_ld[0] = i0.C;
+            d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = taps; d.seg_kchunks[0] = i0.C / 64; d.seg_cbase[0] = 0;
+            long long K = (long long)taps * Cin;
+            if (c.has_skip) {
+                d.a_ptr[1] = bp(c.skip_in.t0); d.a_C[1] = c.skip_in.t0.C; d.a_ld[1] = c.skip_in.t0.C;
+                d.seg_map[1] = 1; d.seg_taps[1] = 1; d.seg_kchunks[1] = c.skip_in.t0.C / 64; d.seg_cbase[1] = 0; d.nseg = 2;
+                K += c.skip_in.t0.C;
+                if (c.skip_in.two) {
+                    d.a_ptr[2] = bp(c.skip_in.t1); d.a_C[2] = c.skip_in.t1.C; d.a_ld[2] = c.skip_in.t1.C;
+                    d.seg_map[2] = 2; d.seg_taps[2] = 1; d.seg_kchunks[2] = c.skip_in.t1.C / 64; d.seg_cbase[2] = 0; d.nseg = 3;
+                    K += c.skip_in.t1.C;
+                }
+            }
+            d.b_ptr = c.wp; d.b_K = (int)K; d.b_rows = c.Co; d.b_batch = 1; d.b_ld = c.ldw; d.b_bs = 0;
+            d.out = bp(c.out); d.ldo = c.Co; d.alpha = 1.f; d.grid_z = 1;
+            d.bias = c.bias; d.rowvec = c.rowvec; d.rowvec_ld = c.rowvec_ld; d.rows_per_vec = c.Ho * c.Wo;
+            d.residual = c.accumulate ? (const void*)bp(c.out) : (const void*)c.residual; d.ldr = c.Co;
+            ++n_tc_gemms;
+            if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return; }
+            GemmLaunch g; int rc = build_gemm(d, g);
+            if (rc) { plan_error = rc; return; }
+            push(L, c.name, fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+            return;
+        }
+        ++n_generic;
+        ConvG g; memset(&g, 0, sizeof g);
+        g.in = gsrc(c.in); g.wp = c.wp; g.ldw = c.ldw; g.bias = c.bias; g.rowvec = c.rowvec; g.rowvec_ld = c.rowvec_ld;
+        g.residual = c.residual; g.out = c.out_nchw ? (void*)c.out_nchw : (void*)bp(c.out); g.out_nchw_f32 = c.out_nchw ? 1 : 0;
+        g.B = Bn; g.Hi = i0.H; g.Wi = i0.W; g.Ho = c.Ho; g.Wo = c.Wo; g.Co = c.Co; g.ksize = c.ksize; g.stride = c.stride;
+        g.pad = (c.map == MAP_NORMAL && c.stride == 1) ? c.ksize / 2 : 0; g.map = c.map; g.accumulate = c.accumulate ? 1 : 0;
+        const dim3 grid((unsigned)((Pout + 63) / 64), (unsigned)((c.Co + 63) / 64));
+        const bool nchw_dyn = c.out_nchw != nullptr;
+        UnetEngine* self = this;
+        push(L, c.name + "[simt]", fl, [g, grid, nchw_dyn, self](cudaStream_t st) {
+            ConvG gg = g; if (nchw_dyn && self->eps_dst) gg.out = self->eps_dst;
+            k_conv_generic<<<grid, 256, 0, st>>>(gg); return (int)cudaGetLastError(); });
+        if (c.has_skip) {
+            ConvG s = g; s.in = gsrc(c.skip_in); s.wp = c.wp + (long long)taps * Cin; s.ksize = 1; s.pad = 0; s.map = MAP_NORMAL; s.stride = 1;
+            s.bias = nullptr; s.rowvec = nullptr; s.residual = nullptr; s.accumulate = 1;
+            push(L, c.name + ".skip[simt]", 0, [s, grid](cudaStream_t st) { k_conv_generic<<<grid, 256, 0, st>>>(s); return (int)cudaGetLastError(); });
+        }
+    }
+    float* eps_dst = nullptr;   // run-time destination of the final conv (caller buffer or internal eps buffer)
+    int plan_error = 0;
+
+    // weight gradient of a conv: dW (OIHW fp32, flat grads) from dy [B,Ho,Wo,Co] and the conv input
+    void wgrad_op(const std::string& name, const T4& dy, const Src& in, int ksize, int stride, int map, float* dw, int Co_valid) {
+        const int Cin = in.C(), taps = ksize * ksize, Co = dy.C;
+        const long long P = dy.pix();
+        const double fl = 2.0 * P * Co_valid * (double)taps * Cin;
+        bwd_flops += fl;
+        const bool tc = stride == 1 && map == MAP_NORMAL && Co % 64 == 0 && Co == Co_valid && in.t0.C % 64 == 0 && (!in.two || in.t1.C % 64 == 0) &&
+                        tc_ok_geom(dy.H, dy.W) && in.t0.H == dy.H;
+        if (tc) {
+            float* scratch = nullptr; size_t sc_off = 0;
+            if (taps == 9) { sc_off = alloc_once_zero((size_t)9 * Co * Cin * 4); scratch = at<float>(sc_off); }
+            for (int s = 0; s < (in.two ? 2 : 1); ++s) {
+                const T4& a = s ? in.t1 : in.t0; const int coff = s ? in.t0.C : 0;
+                ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+                d.mode = GEMM_MNMN; d.M = Co; d.N = a.C; d.W = dy.W; d.H = dy.H; d.NB = dy.B;
+                d.a_ptr[0] = bp(dy); d.a_C[0] = Co; d.a_ld[0] = Co;
+                d.b_ptr = bp(a); d.b_K = a.C; d.b_ld = a.C;
+                d.taps = taps; d.kblocks = (int)((P + 63) / 64);
+                const int bn = pick_block_n(a.C);
+                const int tiles = ((Co + 127) / 128) * (a.C / bn) * taps;
+                int splits = (296 + tiles - 1) / tiles; if (splits > d.kblocks) splits = d.kblocks; if (splits < 1) splits = 1;
+                d.splits = splits; d.grid_z = taps * splits;
+                d.flags = EPI_OUT_F32 | EPI_ATOMIC; d.alpha = 1.f;
+                if (taps == 9) { d.out = scratch + coff; d.ldo = Cin; d.out_tap_stride = (long long)Co * Cin; }
+                else { d.out = dw + coff; d.ldo = Cin; }
+                ++n_tc_gemms;
+                if (dry) { push(bwd_ops, name, s ? 0 : fl, [](cudaStream_t) { return 0; }); continue; }
+                GemmLaunch g; int rc = build_gemm(d, g);
+                if (rc) { plan_error = rc; return; }
+                push(bwd_ops, name, s ? 0 : fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+            }
+            if (taps == 9) {
+                const int n = grid_for((long long)Co * Cin * 9);
+                push(bwd_ops, name + ".unpack", 0, [=](cudaStream_t st) { k_unpack_conv_grad<<<n, 256, 0, st>>>(scratch, dw, Co, Cin, 9); return (int)cudaGetLastError(); });
+            }
+            return;
+        }
+        ++n_generic;
+        WgradG w; memset(&w, 0, sizeof w);
+        w.dy = bp(dy); w.in = gsrc(in); w.dw = dw; w.s_co = (long long)Cin * taps; w.s_ci = taps; w.s_tap = 1;
+        w.B = dy.B; w.Hi = in.t0.H; w.Wi = in.t0.W; w.Ho = dy.H; w.Wo = dy.W; w.Co = Co; w.ksize = ksize; w.stride = stride;
+        w.pad = (map == MAP_NORMAL && stride == 1) ? ksize / 2 : 0; w.map = map; w.Co_valid = Co_valid;
+        const int tiles = ((Cin + 63) / 64) * ((Co + 63) / 64) * taps;
+        int splits = (592 + tiles - 1) / tiles; const int maxs = (int)((P + 255) / 256); if (splits > maxs) splits = maxs; if (splits < 1) splits = 1;
+        w.pix_per_split = (int)(((P + splits - 1) / splits + 15) / 16 * 16);
+        splits = (int)((P + w.pix_per_split - 1) / w.pix_per_split);
+        const dim3 grid((Cin + 63) / 64, (Co + 63) / 64, taps * splits);
+        push(bwd_ops, name + "[simt]", fl, [w, grid](cudaStream_t st) { k_wgrad_generic<<<grid, 256, 0, st>>>(w); return (int)cudaGetLastError(); });
+    }
+    size_t alloc_once_zero(size_t bytes) {   // carve from the plan-time-zeroed arena (contiguous region grown on demand)
+        const size_t o = alloc(bytes);
+        once_list.push_back({o, bytes});
+        return o;
+    }
+    std::vector<std::pair<size_t, size_t>> once_list;
+
+    // per-pass zeroed arenas (GroupNorm statistic accumulators etc.): bump-allocated inside a region zeroed by ONE memset
+    size_t zf_cursor = 0, zb_cursor = 0;
+    size_t zero_fwd(size_t bytes) { const size_t o = zf_cursor; zf_cursor += (bytes + 255) & ~size_t(255); return zero_fwd_off + o; }
+    size_t zero_bwd(size_t bytes) { const size_t o = zb_cursor; zb_cursor += (bytes + 255) & ~size_t(255); return zero_bwd_off + o; }
+
+    GnSaved gn_fwd(std::vector<Op>& L, const std::string& name, const Src& in, const std::string& pname, const T4& out, int silu, float drop_p) {
+        const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
+        GnSaved sv; sv.in = in; sv.silu = silu; sv.drop_p = train ? drop_p : 0.f; sv.layer = ++layer_counter;
+        sv.gamma = PP(pname + ".weight"); sv.beta = PP(pname + ".bias"); sv.dgamma = GP(pname + ".weight"); sv.dbeta = GP(pname + ".bias");
+        double* stats = at<double>(zero_fwd((size_t)Bn * 64 * 8));
+        sv.mr = at<float>(alloc((size_t)Bn * 64 * 4));
+        const GnSrc gs = gsrc(in);
+        const int thr = oct_threads(C);
+        int nblk = (592 + Bn - 1) / Bn; if (nblk > HW / 8) nblk = HW / 8; if (nblk < 1) nblk = 1;
+        const int ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
+        const dim3 g1(nblk, Bn);
+        float* mr = sv.mr;
+        push(L, name + ".stats", 0, [=](cudaStream_t st) {
+            k_gn_stats<<<g1, thr, 0, st>>>(gs, stats, HW, ppb);
+            k_gn_finalize<<<(Bn * 32 + 127) / 128, 128, 0, st>>>(stats, mr, Bn * 32, 1.0 / ((double)HW * (C / 32)), 1e-6f);
+            return (int)cudaGetLastError(); });
+        GnApply a; a.s = gs; a.mr = mr; a.gamma = sv.gamma; a.beta = sv.beta; a.y = bp(out); a.HW = HW;
+        a.total_oct = (long long)Bn * HW * (C / 8); a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer;
+        const int n = grid_for(a.total_oct);
+        UnetEngine* self = this;
+        push(L, name + ".apply", 0, [a, n, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed;
+            k_gn_apply<<<n, 256, 0, st>>>(aa); return (int)cudaGetLastError(); });
+        return sv;
+    }
+    // dx(in) (=|+=) gn_bwd(dy) + addend ; dgamma/dbeta accumulate into the flat grads
+    void gn_bwd(const std::string& name, const GnSaved& sv, const T4& dy, const bf16* addend) {
+        const Src& in = sv.in;
+        const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
+        GnBwd a; memset(&a, 0, sizeof a);
+        a.s = gsrc(in); a.dy = bp(dy); a.mr = sv.mr; a.gamma = sv.gamma; a.beta = sv.beta;
+        a.red = at<double>(zero_bwd((size_t)Bn * 64 * 8)); a.dgamma = sv.dgamma; a.dbeta = sv.dbeta;
+        bool f0 = true, f1 = true;
+        const T4 g0 = grad_of(in.t0, &f0); a.dx0 = bp(g0); a.acc0 = f0 ? 0 : 1;
+        if (in.two) { const T4 g1 = grad_of(in.t1, &f1); a.dx1 = bp(g1); a.acc1 = f1 ? 0 : 1; }
+        a.addend = addend; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer; a.total_oct = (long long)Bn * HW * (C / 8);
+        const int thr = oct_threads(C);
+        int nblk = (592 + Bn - 1) / Bn; if (nblk > HW / 8) nblk = HW / 8; if (nblk < 1) nblk = 1;
+        a.pix_per_block = (HW + nblk - 1) / nblk; nblk = (HW + a.pix_per_block - 1) / a.pix_per_block;
+        const dim3 g1(nblk, Bn);
+        const size_t shm = (size_t)(64 + 2 * C) * 4;
+        const int n = grid_for(a.total_oct);
+        UnetEngine* self = this;
+        push(bwd_ops, name + ".gn_bwd", 0, [a, g1, thr, shm, n, self](cudaStream_t st) {
+            GnBwd aa = a; aa.seed = self->drop_seed;
+            k_gn_bwd_reduce<<<g1, thr, shm, st>>>(aa);
+            k_gn_bwd_apply<<<n, 256, 0, st>>>(aa);
+            return (int)cudaGetLastError(); });
+    }
+    void colsum_op(const std::string& name, const T4& dy, float* per_img, int ld, float* total, float* total2, int C_valid) {
+        const int HW = dy.H * dy.W, C = dy.C, Bn = dy.B;
+        const int thr = oct_threads(C);
+        int nblk = (592 + Bn - 1) / Bn; if (nblk > HW / 8) nblk = HW / 8; if (nblk < 1) nblk = 1;
+        const int ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
+        const dim3 g(nblk, Bn); const bf16* p = bp(dy);
+        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { k_colsum<<<g, thr, 0, st>>>(p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); });
+    }
+
+    // ------------------------------------------------------------------ packed weights
+    struct Packed { bf16* fwd = nullptr; long long ld_f = 0; bf16* dgr = nullptr; long long ld_d = 0; };
+    // fwd pack [Co][taps*Ci (+extra)], dgrad pack [Ci][taps*Co_pad]
+    Packed pack_conv(const std::string& pname, int Co, int Ci, int ksize, int extra_k, bool flip, bool want_dgrad, int co_pad = 0) {
+        const int taps = ksize * ksize;
+        Packed pk; pk.ld_f = (long long)taps * Ci + extra_k;
+        pk.fwd = at<bf16>(alloc((size_t)Co * pk.ld_f * 2));
+        const int Cop = co_pad ? co_pad : Co;
+        if (want_dgrad && train) { pk.ld_d = (long long)taps * Cop; pk.dgr = at<bf16>(co_pad ? alloc_once_zero((size_t)Ci * pk.ld_d * 2) : alloc((size_t)Ci * pk.ld_d * 2)); }
+        const float* w = PP(pname + ".weight");
+        const int n = grid_for((long long)Co * Ci * taps);
+        bf16* f = pk.fwd; bf16* dg = pk.dgr; const long long ldf = pk.ld_f, ldd = pk.ld_d; const int fl = flip ? 1 : 0;
+        if (co_pad) {   // dgrad pack rows are [Ci][taps*Cop]: the kernel indexes tap*Co + co, so pack with Co := Cop is wrong; use a strided variant
+            push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) {
+                k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, 0, nullptr, 0, fl, Co, Ci, taps);
+                k_pack_conv_w_padded<<<n, 256, 0, st>>>(w, dg, ldd, fl, Co, Cop, Ci, taps);
+                return (int)cudaGetLastError(); });
+        } else {
+            push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) { k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, 0, dg, ldd, fl, Co, Ci, taps); return (int)cudaGetLastError(); });
+        }
+        return pk;
+    }
+    void pack_extra(const std::string& pname, const Packed& into, int k_off, int Co, int Ci, bf16* dgr, long long ld_d) {
+        const float* w = PP(pname + ".weight");
+        const int n = grid_for((long long)Co * Ci);
+        bf16* f = into.fwd; const long long ldf = into.ld_f;
+        push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) { k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, k_off, dgr, ld_d, 0, Co, Ci, 1); return (int)cudaGetLastError(); });
+    }
+
+    // ------------------------------------------------------------------ blocks
+    T4 res_block(const std::string& p, const Src& x, int cout, int tp_off, int tp_ld, float* TP, float* dTP);
+    T4 attn_block(const std::string& p, const T4& x);
+    T4 down_conv(const std::string& p, const T4& x);
+    T4 up_conv(const std::string& p, const T4& x);
+    void bmm(std::vector<Op>& L, const std::string& name, int form, const bf16* A, long long lda, long long sa, const bf16* Bp, long long ldb, long long sb,
+             void* C, long long ldc, long long sc, bool c_f32, int nb, int T, int Cc, float alpha, double* fl_acc);
+    int plan(int B_, int H_, int W_, bool train_, bool dry_);
+    int build();
+    int run_list(std::vector<Op>& L, cudaStream_t st) {
+        for (auto& o : L) { const int rc = o.run(st); if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc)); }
+        return 0;
+    }
+};
+
+}  // namespace ddpm

@@ -1,0 +1,402 @@
+// UNet engine, part 2: block builders (forward ops + adjoint tape), batched attention matmuls, plan().
+#pragma once
+#include <cmath>
+#include "unet_engine.cuh"
+
+namespace ddpm {
+
+// Batched matmuls of the attention block (unet.py:43-51) and their adjoints.
+//   form 0 (NT): C[b][i][j] = alpha * sum_c A[b][i][c] * B[b][j][c]     M=i, N=j, K=c
+//   form 1 (NN): C[b][i][c] = sum_j A[b][i][j] * B[b][j][c]             M=i, N=c, K=j
+//   form 2 (TN): C[b][j][c] = sum_i A[b][i][j] * B[b][i][c]             M=j, N=c, K=i
+// A, B bf16 with row strides lda/ldb and per-batch strides = rows*ld; C bf16 or fp32.
+inline void UnetEngine::bmm(std::vector<Op>& L, const std::string& name, int form, const bf16* A, long long lda, long long sa,
+                            const bf16* Bp, long long ldb, long long sb, void* C, long long ldc, long long sc, bool c_f32,
+                            int nb, int T, int Cc, float alpha, double* fl_acc) {
+    // all attention products here are T x T x Cc shaped
+    const int M = T, N = (form == 0) ? T : Cc, K = (form == 0) ? Cc : T;
+    const double fl = 2.0 * nb * (double)M * N * K;
+    if (fl_acc) *fl_acc += fl;
+    const bool tc = (T % 128 == 0) && (Cc % 64 == 0) && ((T & (T - 1)) == 0);
+    if (tc) {
+        ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+        d.M = M; d.N = N; d.W = T; d.H = 1; d.NB = nb; d.alpha = alpha; d.grid_z = nb;
+        d.out = C; d.ldo = (int)ldc; d.out_z_stride = sc; d.flags = c_f32 ? EPI_OUT_F32 : 0;
+        d.a_ptr[0] = A; d.a_ld[0] = lda;
+        if (form == 0) {
+            d.mode = GEMM_KK; d.a_C[0] = K; d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 1; d.seg_kchunks[0] = K / 64; d.seg_cbase[0] = 0;
+            d.b_ptr = Bp; d.b_K = K; d.b_rows = N; d.b_batch = nb; d.b_ld = ldb; d.b_bs = sb; d.a_z_n = 1; d.b_z = 1;
+        } else if (form == 1) {
+            d.mode = GEMM_KMN; d.a_C[0] = K; d.b_ptr = Bp; d.b_K = N; d.b_ld = ldb; d.kblocks = K / 64; d.a_z_n = 1;
+        } else {
+            d.mode = GEMM_MNMN; d.a_C[0] = M; d.b_ptr = Bp; d.b_K = N; d.b_ld = ldb; d.taps = 1; d.splits = 1; d.kblocks = K / 64;
+        }
+        ++n_tc_gemms;
+        if (dry) { push(L, name, fl, [](cudaStream_t) { return 0; }); return; }
+        GemmLaunch g; int rc = build_gemm(d, g);
+        if (rc) { plan_error = rc; return; }
+        push(L, name, fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+        return;
+    }
+    ++n_generic;
+    SgemmParams p; memset(&p, 0, sizeof p);
+    p.A = A; p.B = Bp; p.C = C; p.M = M; p.N = N; p.K = K; p.alpha = alpha;
+    p.sa_z = sa; p.sb_z = sb; p.sc_z = sc; p.sc_m = ldc; p.sc_n = 1;
+    if (form == 0) { p.sa_m = lda; p.sa_k = 1; p.sb_k = 1; p.sb_n = ldb; }
+    else if (form == 1) { p.sa_m = lda; p.sa_k = 1; p.sb_k = ldb; p.sb_n = 1; }
+    else { p.sa_m = 1; p.sa_k = lda; p.sb_k = ldb; p.sb_n = 1; }
+    const dim3 grid((N + 63) / 64, (M + 63) / 64, nb);
+    if (c_f32) push(L, name + "[simt]", fl, [p, grid](cudaStream_t st) { k_sgemm<bf16, bf16, float><<<grid, 256, 0, st>>>(p); return (int)cudaGetLastError(); });
+    else       push(L, name + "[simt]", fl, [p, grid](cudaStream_t st) { k_sgemm<bf16, bf16, bf16><<<grid, 256, 0, st>>>(p); return (int)cudaGetLastError(); });
+}
+
+// ResidualBlock (unet.py:63-89):  out = skip(x) + conv2(drop(silu(gn2(conv1(silu(gn1(x))) + fc(silu(temb))))))
+inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, int tp_off, int tp_ld, float* TP, float* dTP) {
+    const int cin = x.C(), Bn = x.t0.B, h = x.t0.H, w = x.t0.W;
+    const bool has_skip = cin != cout;
+    T4 a1 = newT(Bn, h, w, cin);
+    const GnSaved g1 = gn_fwd(fwd_ops, p + ".norm1", x, p + ".norm1", a1, 1, 0.f);
+    const Packed w1 = pack_conv(p + ".conv1", cout, cin, 3, 0, true, true);
+    T4 h1 = newT(Bn, h, w, cout);
+    {
+        ConvSpec c; c.name = p + ".conv1"; c.in = one(a1); c.wp = w1.fwd; c.ldw = w1.ld_f; c.bias = PP(p + ".conv1.bias");
+        c.rowvec = TP + tp_off; c.rowvec_ld = tp_ld; c.out = h1; c.Co = cout; c.Ho = h; c.Wo = w;
+        conv_op(fwd_ops, c, &fwd_flops);
+    }
+    T4 a2 = newT(Bn, h, w, cout);
+    const GnSaved g2 = gn_fwd(fwd_ops, p + ".norm2", one(h1), p + ".norm2", a2, 1, cfg.drop_rate);
+    const Packed w2 = pack_conv(p + ".conv2", cout, cout, 3, has_skip ? cin : 0, true, true);
+    bf16* wsd = nullptr; float* bias2 = PP(p + ".conv2.bias");
+    if (has_skip) {
+        if (train) wsd = at<bf16>(alloc((size_t)cin * cout * 2));
+        pack_extra(p + ".skip", w2, 9 * cout, cout, cin, wsd, cout);
+        float* comb = at<float>(alloc((size_t)cout * 4));
+        const float* b2 = PP(p + ".conv2.bias"); const float* bs = PP(p + ".skip.bias");
+        push(pack_ops, "bias." + p, 0, [=](cudaStream_t st) { k_add_f32<<<(cout + 127) / 128, 128, 0, st>>>(comb, b2, bs, cout); return (int)cudaGetLastError(); });
+        bias2 = comb;
+    }
+    T4 out = newT(Bn, h, w, cout);
+    {
+        ConvSpec c; c.name = p + ".conv2"; c.in = one(a2); c.wp = w2.fwd; c.ldw = w2.ld_f; c.bias = bias2;
+        c.has_skip = has_skip; c.skip_in = x; c.residual = has_skip ? nullptr : bp(x.t0);
+        c.out = out; c.Co = cout; c.Ho = h; c.Wo = w;
+        conv_op(fwd_ops, c, &fwd_flops);
+    }
+    if (!train) return out;
+    tape.push_back([=]() {
+        const T4 dOut = grad_of(out, nullptr);
+        colsum_op(p + ".conv2.bias", dOut, nullptr, 0, GP(p + ".conv2.bias"), has_skip ? GP(p + ".skip.bias") : nullptr, cout);
+        T4 d_a2 = newT(Bn, h, w, cout);
+        { ConvSpec c; c.name = p + ".conv2.dgrad"; c.in = one(dOut); c.wp = w2.dgr; c.ldw = w2.ld_d; c.out = d_a2; c.Co = cout; c.Ho = h; c.Wo = w;
+          conv_op(bwd_ops, c, &bwd_flops); }
+        wgrad_op(p + ".conv2.wgrad", dOut, one(a2), 3, 1, MAP_NORMAL, GP(p + ".conv2.weight"), cout);
+        T4 dxs;
+        if (has_skip) {
+            dxs = newT(Bn, h, w, cin);
+            ConvSpec c; c.name = p + ".skip.dgrad"; c.in = one(dOut); c.ksize = 1; c.wp = wsd; c.ldw = cout; c.out = dxs; c.Co = cin; c.Ho = h; c.Wo = w;
+            conv_op(bwd_ops, c, &bwd_flops);
+            wgrad_op(p + ".skip.wgrad", dOut, x, 1, 1, MAP_NORMAL, GP(p + ".skip.weight"), cout);
+        }
+        gn_bwd(p + ".norm2", g2, d_a2, nullptr);
+        const T4 d_h1 = grad_of(h1, nullptr);
+        colsum_op(p + ".conv1.bias", d_h1, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"), cout);
+        T4 d_a1 = newT(Bn, h, w, cin);
+        { ConvSpec c; c.name = p + ".conv1.dgrad"; c.in = one(d_h1); c.wp = w1.dgr; c.ldw = w1.ld_d; c.out = d_a1; c.Co = cin; c.Ho = h; c.Wo = w;
+          conv_op(bwd_ops, c, &bwd_flops); }
+        wgrad_op(p + ".conv1.wgrad", d_h1, one(a1), 3, 1, MAP_NORMAL, GP(p + ".conv1.weight"), cout);
+        gn_bwd(p + ".norm1", g1, d_a1, has_skip ? bp(dxs) : bp(dOut));
+    });
+    return out;
+}
+
+// AttentionBlock (unet.py:23-60): out = x + Wo . softmax(Q^T K / sqrt(C)) V ,  q,k,v = chunk(Win . gn(x))
+inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
+    const int C = x.C, Bn = x.B, h = x.H, w = x.W, T = h * w;
+    const float scale = 1.f / sqrtf((float)C);
+    T4 xn = newT(Bn, h, w, C);
+    const GnSaved g = gn_fwd(fwd_ops, p + ".norm", one(x), p + ".norm", xn, 0, 0.f);
+    const Packed win = pack_conv(p + ".project_in", 3 * C, C, 1, 0, false, true);
+    T4 qkv = newT(Bn, h, w, 3 * C);
+    { ConvSpec c; c.name = p + ".project_in"; c.in = one(xn); c.ksize = 1; c.wp = win.fwd; c.ldw = win.ld_f; c.bias = PP(p + ".project_in.bias");
+      c.out = qkv; c.Co = 3 * C; c.Ho = h; c.Wo = w; conv_op(fwd_ops, c, &fwd_flops); }
+    float* S = at<float>(alloc((size_t)Bn * T * T * 4));
+    bf16* Pm = at<bf16>(alloc((size_t)Bn * T * T * 2));
+    const bf16* q = bp(qkv);
+    const long long ldq = 3 * C, sq = (long long)T * 3 * C;
+    bmm(fwd_ops, p + ".qk", 0, q, ldq, sq, q + C, ldq, sq, S, T, (long long)T * T, true, Bn, T, C, scale, &fwd_flops);
+    { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
+      push(fwd_ops, p + ".softmax", 0, [=](cudaStream_t st) { k_softmax_rows<<<nblk, 256, 0, st>>>(S, Pm, rows, T); return (int)cudaGetLastError(); }); }
+    T4 O = newT(Bn, h, w, C);
+    bmm(fwd_ops, p + ".pv", 1, Pm, T, (long long)T * T, q + 2 * C, ldq, sq, bp(O), C, (long long)T * C, false, Bn, T, C, 1.f, &fwd_flops);
+    const Packed wout = pack_conv(p + ".project_out", C, C, 1, 0, false, true);
+    T4 out = newT(Bn, h, w, C);
+    { ConvSpec c; c.name = p + ".project_out"; c.in = one(O); c.ksize = 1; c.wp = wout.fwd; c.ldw = wout.ld_f; c.bias = PP(p + ".project_out.bias");
+      c.residual = bp(x); c.out = out; c.Co = C; c.Ho = h; c.Wo = w; conv_op(fwd_ops, c, &fwd_flops); }
+    if (!train) return out;
+    tape.push_back([=]() {
+        const T4 dY = grad_of(out, nullptr);
+        colsum_op(p + ".project_out.bias", dY, nullptr, 0, GP(p + ".project_out.bias"), nullptr, C);
+        T4 dO = newT(Bn, h, w, C);
+        { ConvSpec c; c.name = p + ".project_out.dgrad"; c.in = one(dY); c.ksize = 1; c.wp = wout.dgr; c.ldw = wout.ld_d; c.out = dO; c.Co = C; c.Ho = h; c.Wo = w;
+          conv_op(bwd_ops, c, &bwd_flops); }
+        wgrad_op(p + ".project_out.wgrad", dY, one(O), 1, 1, MAP_NORMAL, GP(p + ".project_out.weight"), C);
+        float* dP = at<float>(alloc((size_t)Bn * T * T * 4));
+        bf16* dS = at<bf16>(alloc((size_t)Bn * T * T * 2));
+        T4 dqkv = newT(Bn, h, w, 3 * C);
+        const bf16* dOp = bp(dO); bf16* dq = bp(dqkv);
+        bmm(bwd_ops, p + ".dP", 0, dOp, C, (long long)T * C, q + 2 * C, ldq, sq, dP, T, (long long)T * T, true, Bn, T, C, 1.f, &bwd_flops);
+        bmm(bwd_ops, p + ".dV", 2, Pm, T, (long long)T * T, dOp, C, (long long)T * C, dq + 2 * C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
+        { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
+          push(bwd_ops, p + ".softmax_bwd", 0, [=](cudaStream_t st) { k_softmax_bwd<<<nblk, 256, 0, st>>>(Pm, dP, dS, rows, T, scale); return (int)cudaGetLastError(); }); }
+        bmm(bwd_ops, p + ".dQ", 1, dS, T, (long long)T * T, q + C, ldq, sq, dq, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
+        bmm(bwd_ops, p + ".dK", 2, dS, T, (long long)T * T, q, ldq, sq, dq + C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
+        colsum_op(p + ".project_in.bias", dqkv, nullptr, 0, GP(p + ".project_in.bias"), nullptr, 3 * C);
+        T4 dxn = newT(Bn, h, w, C);
+        { ConvSpec c; c.name = p + ".project_in.dgrad"; c.in = one(dqkv); c.ksize = 1; c.wp = win.dgr; c.ldw = win.ld_d; c.out = dxn; c.Co = C; c.Ho = h; c.Wo = w;
+          conv_op(bwd_ops, c, &bwd_flops); }
+        wgrad_op(p + ".project_in.wgrad", dqkv, one(xn), 1, 1, MAP_NORMAL, GP(p + ".project_in.weight"), 3 * C);
+        gn_bwd(p + ".norm", g, dxn, bp(dY));
+    });
+    return out;
+}
+
+// Downsample (unet.py:163-167): SamePad2d(3,2) = zero-pad bottom/right by one, then 3x3 stride 2
+inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
+    const int C = x.C, Bn = x.B, h = x.H, w = x.W;
+    const Packed pk = pack_conv(p, C, C, 3, 0, /*flip=*/false, true);
+    T4 out = newT(Bn, h / 2, w / 2, C);
+    { ConvSpec c; c.name = p; c.in = one(x); c.stride = 2; c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = h / 2; c.Wo = w / 2;
+      conv_op(fwd_ops, c, &fwd_flops); }
+    if (!train) return out;
+    tape.push_back([=]() {
+        const T4 dY = grad_of(out, nullptr);
+        colsum_op(p + ".bias", dY, nullptr, 0, GP(p + ".bias"), nullptr, C);
+        bool first = true; const T4 dx = grad_of(x, &first);
+        { ConvSpec c; c.name = p + ".dgrad"; c.in = one(dY); c.map = MAP_TRANSPOSED2; c.wp = pk.dgr; c.ldw = pk.ld_d; c.out = dx; c.Co = C; c.Ho = h; c.Wo = w; c.accumulate = !first;
+          conv_op(bwd_ops, c, &bwd_flops); }
+        wgrad_op(p + ".wgrad", dY, one(x), 3, 2, MAP_NORMAL, GP(p + ".weight"), C);
+    });
+    return out;
+}
+
+// Upsample (unet.py:199-202): nearest x2 then 3x3 conv
+inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
+    const int C = x.C, Bn = x.B, h = x.H, w = x.W;
+    T4 up = newT(Bn, 2 * h, 2 * w, C);
+    { const bf16* src = bp(x); bf16* dst = bp(up); const int n = grid_for((long long)Bn * 4 * h * w * (C / 8));
+      push(fwd_ops, p + ".upsample", 0, [=](cudaStream_t st) { k_upsample2x<<<n, 256, 0, st>>>(src, dst, Bn, h, w, C); return (int)cudaGetLastError(); }); }
+    const Packed pk = pack_conv(p, C, C, 3, 0, true, true);
+    T4 out = newT(Bn, 2 * h, 2 * w, C);
+    { ConvSpec c; c.name = p; c.in = one(up); c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = 2 * h; c.Wo = 2 * w;
+      conv_op(fwd_ops, c, &fwd_flops); }
+    if (!train) return out;
+    tape.push_back([=]() {
+        const T4 dY = grad_of(out, nullptr);
+        colsum_op(p + ".bias", dY, nullptr, 0, GP(p + ".bias"), nullptr, C);
+        T4 dUp = newT(Bn, 2 * h, 2 * w, C);
+        { ConvSpec c; c.name = p + ".dgrad"; c.in = one(dY); c.wp = pk.dgr; c.ldw = pk.ld_d; c.out = dUp; c.Co = C; c.Ho = 2 * h; c.Wo = 2 * w;
+          conv_op(bwd_ops, c, &bwd_flops); }
+        wgrad_op(p + ".wgrad", dY, one(up), 3, 1, MAP_NORMAL, GP(p + ".weight"), C);
+        bool first = true; const T4 dx = grad_of(x, &first);
+        const bf16* src = bp(dUp); bf16* dst = bp(dx); const int n = grid_for((long long)Bn * h * w * (C / 8)); const int acc = first ? 0 : 1;
+        push(bwd_ops, p + ".upsample_bwd", 0, [=](cudaStream_t st) { k_upsample2x_bwd<<<n, 256, 0, st>>>(src, dst, Bn, h, w, C, acc); return (int)cudaGetLastError(); });
+    });
+    return out;
+}
+
+inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
+    B = B_; H = H_; W = W_; train = train_; dry = dry_;
+    cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); grads.clear(); once_list.clear();
+    tp_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear();
+    layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0;
+    const size_t zf_total = zf_cursor, zb_total = zb_cursor;   // sizes learned by the preceding dry pass
+    zf_cursor = zb_cursor = 0;
+    zero_fwd_bytes = dry ? 0 : zf_total; zero_bwd_bytes = dry ? 0 : zb_total;
+    zero_fwd_off = alloc(dry ? 0 : zf_total); zero_bwd_off = alloc(dry ? 0 : zb_total);
+    const int ch = cfg.hid_channels, L = cfg.levels, nrb = cfg.num_res_blocks, E = cfg.temb_dim, Cin = cfg.in_channels, Cout = cfg.out_channels;
+    if (ch % 32) return fail(-30, "hid_channels must be a multiple of 32 (GroupNorm(32))");
+    if (Cin > 4) return fail(-30, "in_channels > 4 unsupported");
+    if ((H >> (L - 1)) < 1 || (H % (1 << (L - 1))) || (W % (1 << (L - 1)))) return fail(-30, "resolution not divisible by 2^(levels-1)");
+    UnetEngine* self = this;
+
+    // ---- diffusion-side buffers
+    const size_t img_elems = (size_t)B * Cin * H * W;
+    xt_off = alloc(img_elems * 4); eps_off = alloc((size_t)B * Cout * H * W * 4);
+    tbuf_off = alloc((size_t)B * 8); coefcur_off = alloc(64); counter_off = alloc(64);
+    T4 deps = newT(B, H, W, 8); deps_off = (size_t)deps.off;
+
+    // ---- zero the per-forward accumulators
+    { uint8_t* z = ws + zero_fwd_off; const size_t n = zero_fwd_bytes;
+      push(fwd_ops, "zero.fwd", 0, [z, n](cudaStream_t st) { return n ? (int)cudaMemsetAsync(z, 0, n, st) : 0; }); }
+
+    // ---- timestep embedding MLP (functions.py:10-26, unet.py:122-126) + all per-block projections (unet.py:77,86)
+    int nblocks = L * nrb + 2 + L * (nrb + 1);
+    int maxc = 0; for (int i = 0; i < L; ++i) if (chs(i) > maxc) maxc = chs(i);
+    const int tp_ld = nblocks * maxc;
+    float* emb = at<float>(alloc((size_t)B * ch * 4));
+    float* e0 = at<float>(alloc((size_t)B * E * 4));
+    float* e1 = at<float>(alloc((size_t)B * E * 4));
+    float* TP = at<float>(alloc((size_t)B * tp_ld * 4));
+    float* dTP = at<float>(zero_bwd((size_t)B * tp_ld * 4));
+    float* d_st = at<float>(zero_bwd((size_t)B * E * 4));
+    tp_table_off = alloc(sizeof(SgemmParams) * nblocks); tpw_table_off = alloc(sizeof(SgemmParams) * nblocks); tpd_table_off = alloc(sizeof(SgemmParams) * nblocks);
+    {
+        const int Bn = B;
+        push(fwd_ops, "temb.sin", 0, [=](cudaStream_t st) { k_timestep_embedding<<<(Bn * (ch / 2) + 127) / 128, 128, 0, st>>>(self->t_in, emb, Bn, ch); return (int)cudaGetLastError(); });
+        SgemmParams a; memset(&a, 0, sizeof a);
+        a.A = emb; a.B = PP("embed.0.weight"); a.C = e0; a.bias = PP("embed.0.bias"); a.M = B; a.N = E; a.K = ch;
+        a.sa_m = ch; a.sa_k = 1; a.sb_k = 1; a.sb_n = ch; a.sc_m = E; a.sc_n = 1; a.alpha = 1.f;
+        const dim3 g0((E + 63) / 64, (B + 63) / 64, 1);
+        push(fwd_ops, "temb.fc0", 2.0 * B * E * ch, [a, g0](cudaStream_t st) { k_sgemm<float, float, float><<<g0, 256, 0, st>>>(a); return (int)cudaGetLastError(); });
+        SgemmParams b = a; b.A = e0; b.B = PP("embed.2.weight"); b.C = e1; b.bias = PP("embed.2.bias"); b.K = E; b.sa_m = E; b.sb_n = E; b.silu_a = 1;
+        push(fwd_ops, "temb.fc1", 2.0 * B * E * E, [b, g0](cudaStream_t st) { k_sgemm<float, float, float><<<g0, 256, 0, st>>>(b); return (int)cudaGetLastError(); });
+        const SgemmParams* tab = at<SgemmParams>(tp_table_off);
+        const dim3 g1((maxc + 63) / 64, (B + 63) / 64, nblocks);
+        push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { k_sgemm_table<<<g1, 256, 0, st>>>(tab); return (int)cudaGetLastError(); });
+        fwd_flops += 2.0 * B * E * ch + 2.0 * B * E * E;
+    }
+    int blk = 0;
+    auto tp_entry = [&](const std::string& p, int cout) -> int {
+        const int off = blk * maxc; ++blk;
+        SgemmParams s; memset(&s, 0, sizeof s);
+        s.A = e1; s.B = PP(p + ".fc.weight"); s.C = TP + off; s.bias = PP(p + ".fc.bias"); s.M = B; s.N = cout; s.K = E;
+        s.sa_m = E; s.sa_k = 1; s.sb_k = 1; s.sb_n = E; s.sc_m = tp_ld; s.sc_n = 1; s.alpha = 1.f; s.silu_a = 1;
+        tp_table_host.push_back(s);
+        fwd_flops += 2.0 * B * cout * E;
+        if (train) {
+            // dW_fc[o][e] = sum_b silu(e1[b][e]) * dTP[b][off+o]   (computed as C'[e][o], stored transposed)
+            SgemmParams w; memset(&w, 0, sizeof w);
+            w.A = e1; w.B = dTP + off; w.C = GP(p + ".fc.weight"); w.M = E; w.N = cout; w.K = B;
+            w.sa_m = 1; w.sa_k = E; w.sb_k = tp_ld; w.sb_n = 1; w.sc_m = 1; w.sc_n = E; w.alpha = 1.f; w.silu_a = 1;
+            tpw_table_host.push_back(w);
+            // d_st[b][e] += sum_o dTP[b][off+o] * W_fc[o][e]
+            SgemmParams d; memset(&d, 0, sizeof d);
+            d.A = dTP + off; d.B = PP(p + ".fc.weight"); d.C = d_st; d.M = B; d.N = E; d.K = cout;
+            d.sa_m = tp_ld; d.sa_k = 1; d.sb_k = E; d.sb_n = 1; d.sc_m = E; d.sc_n = 1; d.alpha = 1.f; d.accumulate = 2;
+            tpd_table_host.push_back(d);
+            bwd_flops += 4.0 * B * cout * E;
+        }
+        return off;
+    };
+    if (train) {
+        // adjoint of the embedding MLP; registered first so it runs after every block has deposited its dTP slice
+        tape.push_back([=]() {
+            const SgemmParams* tw = at<SgemmParams>(tpw_table_off); const SgemmParams* td = at<SgemmParams>(tpd_table_off);
+            const dim3 gw((maxc + 63) / 64, (E + 63) / 64, nblocks), gd((E + 63) / 64, (B + 63) / 64, nblocks);
+            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { k_sgemm_table<<<gw, 256, 0, st>>>(tw); k_sgemm_table<<<gd, 256, 0, st>>>(td); return (int)cudaGetLastError(); });
+            float* d_e1 = at<float>(alloc((size_t)B * E * 4)); float* d_s0 = at<float>(alloc((size_t)B * E * 4)); float* d_e0 = at<float>(alloc((size_t)B * E * 4));
+            const long long nE = (long long)B * E; const int Bn = B;
+            float* gw2 = GP("embed.2.weight"); float* gb2 = GP("embed.2.bias"); float* gw0 = GP("embed.0.weight"); float* gb0 = GP("embed.0.bias");
+            const float* w2 = PP("embed.2.weight");
+            push(bwd_ops, "temb.mlp.bwd", 0, [=](cudaStream_t st) {
+                k_silu_bwd_f32<<<grid_for(nE), 256, 0, st>>>(e1, d_st, d_e1, nE);
+                SgemmParams a; memset(&a, 0, sizeof a);           // dW2[n][k] = sum_b silu(e0[b][k]) d_e1[b][n]
+                a.A = e0; a.B = d_e1; a.C = gw2; a.M = E; a.N = E; a.K = Bn; a.sa_m = 1; a.sa_k = E; a.sb_k = E; a.sb_n = 1; a.sc_m = 1; a.sc_n = E; a.alpha = 1.f; a.silu_a = 1;
+                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (E + 63) / 64, 1), 256, 0, st>>>(a);
+                k_colsum_f32<<<(E + 127) / 128, 128, 0, st>>>(d_e1, gb2, Bn, E, E);
+                SgemmParams b; memset(&b, 0, sizeof b);           // d_s0[b][k] = sum_n d_e1[b][n] W2[n][k]
+                b.A = d_e1; b.B = w2; b.C = d_s0; b.M = Bn; b.N = E; b.K = E; b.sa_m = E; b.sa_k = 1; b.sb_k = E; b.sb_n = 1; b.sc_m = E; b.sc_n = 1; b.alpha = 1.f;
+                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (Bn + 63) / 64, 1), 256, 0, st>>>(b);
+                k_silu_bwd_f32<<<grid_for(nE), 256, 0, st>>>(e0, d_s0, d_e0, nE);
+                SgemmParams c; memset(&c, 0, sizeof c);           // dW0[n][k] = sum_b emb[b][k] d_e0[b][n]
+                c.A = emb; c.B = d_e0; c.C = gw0; c.M = ch; c.N = E; c.K = Bn; c.sa_m = 1; c.sa_k = ch; c.sb_k = E; c.sb_n = 1; c.sc_m = 1; c.sc_n = ch; c.alpha = 1.f;
+                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (ch + 63) / 64, 1), 256, 0, st>>>(c);
+                k_colsum_f32<<<(E + 127) / 128, 128, 0, st>>>(d_e0, gb0, Bn, E, E);
+                return (int)cudaGetLastError(); });
+        });
+    }
+
+    // ---- in_conv (unet.py:127,210): NCHW fp32 -> NHWC bf16
+    T4 h0 = newT(B, H, W, ch);
+    {
+        const float* wi = PP("in_conv.weight"); const float* bi = PP("in_conv.bias"); bf16* o = bp(h0);
+        const size_t shm = (size_t)(ch * Cin * 9 + ch) * 4; const int n = grid_for((long long)B * H * W * (ch / 8));
+        const int Bn = B, Hn = H, Wn = W;
+        push(fwd_ops, "in_conv", 2.0 * B * H * W * ch * Cin * 9, [=](cudaStream_t st) {
+            k_in_conv<<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Cin, Hn, Wn, ch); return (int)cudaGetLastError(); });
+        fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
+        if (train) tape.push_back([=]() {
+            const T4 dY = grad_of(h0, nullptr);
+            float* gw = GP("in_conv.weight"); float* gb = GP("in_conv.bias"); const bf16* d = bp(dY);
+            const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
+            bwd_flops += 2.0 * P * ch * Cin * 9;
+            push(bwd_ops, "in_conv.wgrad", 2.0 * P * ch * Cin * 9, [=](cudaStream_t st) {
+                k_in_conv_wgrad<<<nb, 256, 0, st>>>(d, self->x_in, gw, gb, Bn, Cin, Hn, Wn, ch, ppb); return (int)cudaGetLastError(); });
+        });
+    }
+
+    // ---- down path (unet.py:210-218)
+    std::vector<T4> hs; hs.push_back(h0);
+    auto block = [&](const std::string& p, const Src& x, int cout, bool at_) -> T4 {
+        if (at_) { const int off = tp_entry(p + ".0", cout); T4 r = res_block(p + ".0", x, cout, off, tp_ld, TP, dTP); return attn_block(p + ".1", r); }
+        const int off = tp_entry(p, cout); return res_block(p, x, cout, off, tp_ld, TP, dTP);
+    };
+    for (int i = 0; i < L; ++i) {
+        const std::string p = "downsamples.level_" + std::to_string(i);
+        for (int j = 0; j < nrb; ++j) hs.push_back(block(p + "." + std::to_string(j), one(hs.back()), chs(i), cfg.attn[i] != 0));
+        if (i != L - 1) hs.push_back(down_conv(p + "." + std::to_string(nrb) + ".1", hs.back()));
+    }
+    // ---- middle (unet.py:132-136,221)
+    T4 h = hs.back();
+    { const int off = tp_entry("middle.0", chs(L - 1)); h = res_block("middle.0", one(h), chs(L - 1), off, tp_ld, TP, dTP); }
+    h = attn_block("middle.1", h);
+    { const int off = tp_entry("middle.2", chs(L - 1)); h = res_block("middle.2", one(h), chs(L - 1), off, tp_ld, TP, dTP); }
+    // ---- up path (unet.py:224-230): cat([h, hs.pop()]) is never materialised
+    for (int i = L - 1; i >= 0; --i) {
+        const std::string p = "upsamples.level_" + std::to_string(i);
+        for (int j = 0; j <= nrb; ++j) {
+            Src s; s.t0 = h; s.t1 = hs.back(); s.two = true; hs.pop_back();
+            h = block(p + "." + std::to_string(j), s, chs(i), cfg.attn[i] != 0);
+        }
+        if (i != 0) h = up_conv(p + "." + std::to_string(nrb + 1) + ".1", h);
+    }
+    if (blk != nblocks) return fail(-31, "internal: block count mismatch %d vs %d", blk, nblocks);
+    // ---- out_conv (unet.py:138-142,232): GN -> SiLU -> conv3x3 -> NCHW fp32
+    {
+        T4 a_out = newT(B, H, W, ch);
+        const GnSaved g = gn_fwd(fwd_ops, "out_conv.0", one(h), "out_conv.0", a_out, 1, 0.f);
+        const Packed wo = pack_conv("out_conv.2", Cout, ch, 3, 0, true, true, 8);
+        ConvSpec c; c.name = "out_conv.2"; c.in = one(a_out); c.wp = wo.fwd; c.ldw = wo.ld_f; c.bias = PP("out_conv.2.bias");
+        c.out_nchw = reinterpret_cast<float*>(1); c.Co = Cout; c.Ho = H; c.Wo = W;
+        conv_op(fwd_ops, c, &fwd_flops);
+        if (train) {
+            const T4 hl = h;
+            tape.push_back([=]() {
+                colsum_op("out_conv.2.bias", deps, nullptr, 0, GP("out_conv.2.bias"), nullptr, Cout);
+                T4 d_a = newT(B, H, W, ch);
+                { ConvSpec c2; c2.name = "out_conv.2.dgrad"; c2.in = one(deps); c2.wp = wo.dgr; c2.ldw = wo.ld_d; c2.out = d_a; c2.Co = ch; c2.Ho = H; c2.Wo = W;
+                  conv_op(bwd_ops, c2, &bwd_flops); }
+                wgrad_op("out_conv.2.wgrad", deps, one(a_out), 3, 1, MAP_NORMAL, GP("out_conv.2.weight"), Cout);
+                gn_bwd("out_conv.0", g, d_a, nullptr);
+                (void)hl;
+            });
+        }
+    }
+    // ---- backward list: zero accumulators + flat grads, then the tape in reverse
+    if (train) {
+        uint8_t* z = ws + zero_bwd_off; const size_t n = zero_bwd_bytes; float* Gp = G; const size_t gbytes = (size_t)flat_elems * 4;
+        push(bwd_ops, "zero.bwd", 0, [=](cudaStream_t st) {
+            if (n) { const cudaError_t e = cudaMemsetAsync(z, 0, n, st); if (e) return (int)e; }
+            return (int)cudaMemsetAsync(Gp, 0, gbytes, st); });
+        for (int i = (int)tape.size() - 1; i >= 0; --i) tape[i]();
+        tape.clear();
+    }
+    if (plan_error) return plan_error;
+    return 0;
+}
+
+inline int UnetEngine::build() {
+    // tables -> device ; plan-time zeroed arenas
+    auto up = [&](size_t off, const std::vector<SgemmParams>& v) -> int {
+        if (v.empty()) return 0;
+        return (int)cudaMemcpy(ws + off, v.data(), v.size() * sizeof(SgemmParams), cudaMemcpyHostToDevice);
+    };
+    int rc;
+    if ((rc = up(tp_table_off, tp_table_host)) || (rc = up(tpw_table_off, tpw_table_host)) || (rc = up(tpd_table_off, tpd_table_host)))
+        return fail(-2, "table upload failed: %s", cudaGetErrorString((cudaError_t)rc));
+    for (auto& r : once_list) { const cudaError_t e = cudaMemset(ws + r.first, 0, r.second); if (e) return fail(-2, "memset failed: %s", cudaGetErrorString(e)); }
+    planned = true;
+    return 0;
+}
+
+}  // namespace ddpm

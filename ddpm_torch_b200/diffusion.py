@@ -1,0 +1,299 @@
+"""Host-side mirror of ``ddpm_torch.diffusion`` (reference diffusion.py) for the accelerated path.
+
+``GaussianDiffusion`` keeps the reference's constructor, attribute names (fp64 coefficient tables) and method
+signatures.  When ``denoise_fn`` is a ``ddpm_torch_b200.UNet`` (optionally wrapped in DDP / a ``.module`` holder) and
+the configuration is the one every reference config uses (eps-prediction, fixed variance, mse loss):
+
+* ``train_losses``  -> one fused engine call: q_sample prologue, UNet forward, per-sample MSE (and the matching
+  fused backward through autograd),
+* ``p_sample`` / ``p_sample_step`` -> the engine's sampler step (UNet forward + the alpha/beta update of
+  diffusion.py:107-158 in one launch sequence, replayed from a CUDA graph once per timestep).
+
+Any other ``denoise_fn`` (toy MLPs, wrappers) takes the generic formulas below, written with plain torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .unet import UNet
+
+
+def get_beta_schedule(beta_schedule, beta_start, beta_end, timesteps, dtype=torch.float64):
+    """Same schedules and fp64 arithmetic as diffusion.py:13-29."""
+    lin = lambda a, b, n: torch.linspace(a, b, n, dtype=dtype)
+    if beta_schedule == "linear":
+        betas = lin(beta_start, beta_end, timesteps)
+    elif beta_schedule == "quad":
+        betas = lin(beta_start ** 0.5, beta_end ** 0.5, timesteps) ** 2
+    elif beta_schedule in ("warmup10", "warmup50"):
+        n = int(timesteps * (0.1 if beta_schedule == "warmup10" else 0.5))
+        betas = torch.full((timesteps,), beta_end, dtype=dtype)
+        betas[:n] = lin(beta_start, beta_end, n)
+    elif beta_schedule == "const":
+        betas = torch.full((timesteps,), beta_end, dtype=dtype)
+    elif beta_schedule == "jsd":
+        betas = 1. / lin(timesteps, 1, timesteps)
+    else:
+        raise NotImplementedError(beta_schedule)
+    assert betas.shape == (timesteps,)
+    return betas
+
+
+def _native(denoise_fn):
+    """Unwrap DDP / holders; return the engine-backed UNet or None."""
+    m = denoise_fn
+    for _ in range(3):
+        if isinstance(m, UNet):
+            return m
+        m = getattr(m, "module", None)
+        if m is None:
+            return None
+    return None
+
+
+def _flat_mean(x):
+    return x.mean(dim=list(range(1, x.ndim)))
+
+
+class GaussianDiffusion:
+    def __init__(self, betas, model_mean_type, model_var_type, loss_type, **kwargs):
+        assert isinstance(betas, torch.Tensor) and betas.dtype == torch.float64
+        assert (betas > 0).all() and (betas <= 1).all()
+        self.betas = betas
+        self.model_mean_type, self.model_var_type, self.loss_type = model_mean_type, model_var_type, loss_type
+        self.timesteps = len(betas)
+        alphas = 1 - betas
+        self.alphas_bar = torch.cumprod(alphas, dim=0)
+        ab_prev = torch.cat([torch.ones(1, dtype=torch.float64), self.alphas_bar[:-1]])
+        self.sqrt_alphas_bar = self.alphas_bar.sqrt()
+        self.sqrt_one_minus_alphas_bar = (1. - self.alphas_bar).sqrt()
+        self.sqrt_recip_alphas_bar = (1. / self.alphas_bar).sqrt()
+        self.sqrt_recip_m1_alphas_bar = (1. / self.alphas_bar - 1.).sqrt()
+        self.posterior_var = betas * (1. - ab_prev) / (1. - self.alphas_bar)
+        self.posterior_logvar_clipped = torch.log(torch.cat([self.posterior_var[[1]], self.posterior_var[1:]]))
+        self.posterior_mean_coef1 = betas * ab_prev.sqrt() / (1. - self.alphas_bar)
+        self.posterior_mean_coef2 = alphas.sqrt() * (1. - ab_prev) / (1. - self.alphas_bar)
+        self._set_fixed_var(clip=False)
+        self._dev_cache = {}
+
+    def _set_fixed_var(self, clip):
+        large = torch.cat([self.posterior_var[[1]], self.betas[1:]])
+        if clip:
+            large = large.clip(min=1e-20)
+        self.fixed_model_var, self.fixed_model_logvar = {
+            "fixed-large": (self.betas, torch.log(large)),
+            "fixed-small": (self.posterior_var, self.posterior_logvar_clipped),
+        }.get(self.model_var_type, (None, None))
+
+    # ------------------------------------------------------------------ generic (torch) formulas
+    @staticmethod
+    def _extract(arr, t, x, dtype=torch.float32, device=torch.device("cpu"), ndim=4):
+        if x is not None:
+            dtype, device, ndim = x.dtype, x.device, x.ndim
+        out = torch.as_tensor(arr, dtype=dtype, device=device).gather(0, t)
+        return out.reshape((-1,) + (1,) * (ndim - 1))
+
+    def q_mean_var(self, x_0, t):
+        return (self._extract(self.sqrt_alphas_bar, t, x_0) * x_0, self._extract(1. - self.alphas_bar, t, x_0),
+                self._extract(torch.log(1 - self.alphas_bar), t, x_0))
+
+    def q_sample(self, x_0, t, noise=None):
+        if noise is None:
+            noise = torch.randn_like(x_0)
+        return self._extract(self.sqrt_alphas_bar, t, x_0) * x_0 + \
+            self._extract(self.sqrt_one_minus_alphas_bar, t, x_0) * noise
+
+    def q_posterior_mean_var(self, x_0, x_t, t):
+        mean = self._extract(self.posterior_mean_coef1, t, x_0) * x_0 + self._extract(self.posterior_mean_coef2, t, x_0) * x_t
+        return mean, self._extract(self.posterior_var, t, x_0), self._extract(self.posterior_logvar_clipped, t, x_0)
+
+    def _pred_x_0_from_eps(self, x_t, eps, t):
+        return self._extract(self.sqrt_recip_alphas_bar, t, x_t) * x_t - self._extract(self.sqrt_recip_m1_alphas_bar, t, x_t) * eps
+
+    def _pred_x_0_from_mean(self, x_t, mean, t):
+        c1, c2 = self._extract(self.posterior_mean_coef1, t, x_t), self._extract(self.posterior_mean_coef2, t, x_t)
+        return mean / c1 - c2 / c1 * x_t
+
+    def p_mean_var(self, denoise_fn, x_t, t, clip_denoised, return_pred):
+        out = denoise_fn(x_t, t)
+        if self.model_var_type == "learned":
+            out, model_logvar = out.chunk(2, dim=1)
+            model_var = torch.exp(model_logvar)
+        elif self.model_var_type in ("fixed-small", "fixed-large"):
+            model_var, model_logvar = self._extract(self.fixed_model_var, t, x_t), self._extract(self.fixed_model_logvar, t, x_t)
+        else:
+            raise NotImplementedError(self.model_var_type)
+        clip = (lambda v: v.clamp(-1., 1.)) if clip_denoised else (lambda v: v)
+        if self.model_mean_type == "mean":
+            pred_x_0, model_mean = clip(self._pred_x_0_from_mean(x_t, out, t)), out
+        elif self.model_mean_type == "x_0":
+            pred_x_0 = clip(out)
+            model_mean = self.q_posterior_mean_var(pred_x_0, x_t, t)[0]
+        elif self.model_mean_type == "eps":
+            pred_x_0 = clip(self._pred_x_0_from_eps(x_t, out, t))
+            model_mean = self.q_posterior_mean_var(pred_x_0, x_t, t)[0]
+        else:
+            raise NotImplementedError(self.model_mean_type)
+        return (model_mean, model_var, model_logvar, pred_x_0) if return_pred else (model_mean, model_var, model_logvar)
+
+    def _fast_ok(self, denoise_fn):
+        m = _native(denoise_fn)
+        ok = m is not None and self.model_mean_type == "eps" and self.model_var_type in ("fixed-small", "fixed-large")
+        return m if ok else None
+
+    # ------------------------------------------------------------------ sampling
+    def p_sample_step(self, denoise_fn, x_t, t, clip_denoised=True, return_pred=False, generator=None):
+        model_mean, _, model_logvar, pred_x_0 = self.p_mean_var(denoise_fn, x_t, t, clip_denoised, True)
+        noise = torch.empty_like(x_t).normal_(generator=generator)
+        nonzero = (t > 0).reshape((-1,) + (1,) * (x_t.ndim - 1)).to(x_t)
+        sample = model_mean + nonzero * torch.exp(0.5 * model_logvar) * noise
+        return (sample, pred_x_0) if return_pred else sample
+
+    def _coef_rows(self):
+        """[S,6] fp32 rows {sqrt_recip_ab, sqrt_recip_m1_ab, c1, c2, exp(.5*logvar), t>0}; every entry goes through the
+        same fp64 -> fp32 cast as ``_extract`` (diffusion.py:83) and sigma is exp(0.5*fp32(logvar)) as in :157."""
+        f = lambda a: torch.as_tensor(a, dtype=torch.float32)
+        S = len(self.betas)
+        nz = (torch.arange(S) > 0).float()
+        return torch.stack([f(self.sqrt_recip_alphas_bar), f(self.sqrt_recip_m1_alphas_bar), f(self.posterior_mean_coef1),
+                            f(self.posterior_mean_coef2), torch.exp(0.5 * f(self.fixed_model_logvar)), nz], dim=1).contiguous()
+
+    def _model_timesteps(self):
+        return torch.arange(len(self.betas), dtype=torch.int64)
+
+    @torch.inference_mode()
+    def p_sample(self, denoise_fn, shape=None, device=torch.device("cpu"), noise=None, seed=None, rng="torch", use_graph=True):
+        """diffusion.py:160-174.  ``rng="torch"`` consumes a torch.Generator exactly like the reference (bit-identical
+        noise stream); ``rng="philox"`` draws the per-step noise inside the step kernel (one launch sequence per step)."""
+        model = self._fast_ok(denoise_fn)
+        B = (shape or noise.shape)[0]
+        gen = torch.Generator(device).manual_seed(seed) if seed is not None else None
+        x_t = torch.empty(shape, device=device).normal_(generator=gen) if noise is None else noise.to(device)
+        S = len(self.betas)
+        if model is None:
+            t = torch.empty((B,), dtype=torch.int64, device=device)
+            fn = self._wrap_denoise(denoise_fn, device)
+            for ti in range(S - 1, -1, -1):
+                t.fill_(ti)
+                x_t = self.p_sample_step(fn, x_t, t, generator=gen)
+            return x_t
+        return _native_sample_loop(self, model, x_t.contiguous().float().clone(), gen, rng, seed, use_graph)
+
+    def _wrap_denoise(self, denoise_fn, device):
+        return denoise_fn
+
+    @torch.inference_mode()
+    def p_sample_progressive(self, denoise_fn, shape, device=torch.device("cpu"), noise=None, pred_freq=10, seed=None):
+        B = (shape or noise.shape)[0]
+        t = torch.empty(B, dtype=torch.int64, device=device)
+        gen = torch.Generator(device).manual_seed(seed) if seed is not None else None
+        x_t = torch.empty(shape, device=device).normal_(generator=gen) if noise is None else noise.to(device)
+        n = self.timesteps // pred_freq
+        preds = torch.zeros((n, B) + tuple(shape[1:]), dtype=torch.float32)
+        idx = n
+        fn = self._wrap_denoise(denoise_fn, device)
+        for ti in range(self.timesteps - 1, -1, -1):
+            t.fill_(ti)
+            x_t, pred = self.p_sample_step(fn, x_t, t, return_pred=True, generator=gen)
+            if (ti + 1) % pred_freq == 0:
+                idx -= 1
+                preds[idx] = pred.cpu()
+        return x_t.cpu(), preds
+
+    # ------------------------------------------------------------------ training
+    def train_losses(self, denoise_fn, x_0, t, noise=None):
+        if noise is None:
+            noise = torch.randn_like(x_0)
+        model = self._fast_ok(denoise_fn)
+        if model is not None and self.loss_type == "mse" and x_0.is_cuda:
+            return _TrainLossFn.apply(self, model, denoise_fn, x_0.contiguous().float(), t.contiguous(), noise.contiguous().float(),
+                                      *model._params)
+        x_t = self.q_sample(x_0, t, noise=noise)
+        if self.loss_type != "mse":
+            raise NotImplementedError("loss_type='kl' (bits-per-dim path) is outside the accelerated scope")
+        assert self.model_var_type != "learned"
+        target = {"mean": lambda: self.q_posterior_mean_var(x_0, x_t, t)[0], "x_0": lambda: x_0, "eps": lambda: noise}[self.model_mean_type]()
+        return _flat_mean((target - denoise_fn(x_t, t)).pow(2))
+
+    def _dev_tables(self, device):
+        k = str(device)
+        if k not in self._dev_cache:
+            self._dev_cache[k] = (torch.as_tensor(self.sqrt_alphas_bar, dtype=torch.float32, device=device).contiguous(),
+                                  torch.as_tensor(self.sqrt_one_minus_alphas_bar, dtype=torch.float32, device=device).contiguous())
+        return self._dev_cache[k]
+
+
+class _TrainLossFn(torch.autograd.Function):
+    """losses[b] = mean((noise - UNet(q_sample(x0,t,noise), t))^2) through ddpm_train_forward / ddpm_train_backward."""
+
+    @staticmethod
+    def forward(ctx, diffusion, model, wrapper, x0, t, noise, *params):
+        B, _, H, W = x0.shape
+        train = torch.is_grad_enabled() or any(p.requires_grad for p in params)
+        h = model.prepare(B, H, W, training=train)
+        ta, ts = diffusion._dev_tables(x0.device)
+        losses = torch.empty(B, dtype=torch.float32, device=x0.device)
+        seed = model.next_dropout_seed() if (model.training and model.drop_rate > 0) else 0
+        _lib.check(_lib.lib().ddpm_train_forward(h, x0.data_ptr(), t.data_ptr(), noise.data_ptr(), ta.data_ptr(), ts.data_ptr(),
+                                                 losses.data_ptr(), seed, _lib.stream_ptr()), "train_forward")
+        ctx.model = model
+        ctx.keep = (x0, t, noise)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.model
+        g = g.contiguous().float()
+        _lib.check(_lib.lib().ddpm_train_backward(model._h, g.data_ptr(), _lib.stream_ptr()), "train_backward")
+        flat = model._grads.clone()
+        return (None, None, None, None, None, None, *model.grad_views(flat))
+
+
+def _native_sample_loop(diffusion, model, x, gen, rng, seed, use_graph):
+    """T sampler steps on the engine: per step {prep, UNet forward, alpha/beta tail}; captured once, replayed T times."""
+    L = _lib.lib()
+    B, _, H, W = x.shape
+    was_training = model.training
+    model.eval()
+    h = model.prepare(B, H, W, training=False)
+    coef = diffusion._coef_rows()
+    tmod = diffusion._model_timesteps().contiguous()
+    S = coef.shape[0]
+    _lib.check(L.ddpm_sampler_setup(h, S, tmod.data_ptr(), coef.data_ptr()), "sampler_setup")
+    z = torch.empty_like(x) if rng == "torch" else None
+    pseed = 0 if rng == "torch" else ((seed if seed is not None else torch.initial_seed()) | 1) & 0xFFFFFFFFFFFFFFFF
+    stream = torch.cuda.current_stream()
+    _lib.check(L.ddpm_sampler_reset(h, S - 1, C.c_void_p(stream.cuda_stream)), "sampler_reset")
+
+    def step():
+        _lib.check(L.ddpm_sampler_step(h, x.data_ptr(), z.data_ptr() if z is not None else None, pseed, _lib.stream_ptr()), "sampler_step")
+
+    graph = None
+    if use_graph:
+        # warm the allocator-free path once outside capture (step 0 of the loop), then capture one step
+        if z is not None:
+            z.normal_(generator=gen)
+        step()
+        done = 1
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        if done < S:
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            # capture does not execute: the captured step is replayed below for every remaining timestep
+            for _ in range(done, S):
+                if z is not None:
+                    z.normal_(generator=gen)
+                graph.replay()
+    else:
+        for _ in range(S):
+            if z is not None:
+                z.normal_(generator=gen)
+            step()
+    if was_training:
+        model.train()
+    return x

@@ -1,0 +1,212 @@
+"""Host-side mirror of ``ddpm_torch.models.unet.UNet`` (reference unet.py:92-233) over the sm_100a engine.
+
+Same constructor, same ``state_dict()`` keys / shapes / registration order (so reference checkpoints load with
+``load_state_dict`` and EMA / Adam / clip_grad_norm_ / DDP see ordinary ``nn.Parameter``s), same
+``forward(x, t)`` contract (x f32[B,C,H,W] NCHW, t i64[B] -> f32[B,C_out,H,W]) — but no ATen graph: the whole
+forward and backward run as the engine's launch plan through the C ABI (include/ddpm_b200.h).
+
+All parameters are views into ONE flat fp32 buffer (and gradients come back in one flat buffer), which is what the
+kernels read; the bf16 kernel layouts are re-packed from it whenever it changed.  There is no PyTorch/CPU fallback:
+calling the model without the built extension or off an sm_100 GPU raises.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class _Node(nn.Module):
+    """Plain container used only to reproduce the reference's dotted state_dict names."""
+
+
+def _xavier_uniform_(t, scale):
+    """modules.py:11-18 — xavier uniform with gain sqrt(scale or 1e-10)."""
+    return nn.init.xavier_uniform_(t, gain=math.sqrt(scale or 1e-10))
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channels, hid_channels, out_channels, ch_multipliers, num_res_blocks, apply_attn,
+                 time_embedding_dim=None, drop_rate=0., resample_with_conv=True):
+        super().__init__()
+        if not resample_with_conv:
+            raise NotImplementedError("resample_with_conv=False (AvgPool/plain Upsample) is outside the accelerated path")
+        levels = len(ch_multipliers)
+        if isinstance(apply_attn, bool):
+            apply_attn = [apply_attn] * levels
+        self.in_channels, self.hid_channels, self.out_channels = in_channels, hid_channels, out_channels
+        self.ch_multipliers, self.apply_attn = tuple(ch_multipliers), tuple(bool(a) for a in apply_attn)
+        self.num_res_blocks, self.levels = num_res_blocks, levels
+        self.time_embedding_dim = time_embedding_dim or 4 * hid_channels
+        self.drop_rate, self.resample_with_conv = drop_rate, resample_with_conv
+
+        cfg = _lib.UnetCfg()
+        cfg.in_channels, cfg.hid_channels, cfg.out_channels = in_channels, hid_channels, out_channels
+        cfg.levels, cfg.num_res_blocks = levels, num_res_blocks
+        for i in range(levels):
+            cfg.ch_mult[i] = int(ch_multipliers[i])
+            cfg.attn[i] = int(bool(apply_attn[i]))
+        cfg.temb_dim, cfg.drop_rate = self.time_embedding_dim, float(drop_rate)
+        L = _lib.lib()
+        self._h = C.c_void_p()
+        _lib.check(L.ddpm_unet_create(C.byref(cfg), C.byref(self._h)), "unet_create")
+
+        # parameter inventory from the engine (reference registration order)
+        self._meta = []
+        for i in range(L.ddpm_unet_num_params(self._h)):
+            name, nd, dims, off = C.c_char_p(), C.c_int(), (C.c_int * 4)(), C.c_longlong()
+            _lib.check(L.ddpm_unet_param_info(self._h, i, C.byref(name), C.byref(nd), C.byref(dims), C.byref(off)))
+            self._meta.append((name.value.decode(), tuple(dims[:nd.value]), int(off.value)))
+        self._flat_elems = int(L.ddpm_unet_flat_elems(self._h))
+        flat = torch.zeros(self._flat_elems, dtype=torch.float32)
+        self._params = []
+        zero_scale = (".conv2.weight", ".project_out.weight", "out_conv.2.weight")   # init_scale=0: unet.py:37,79,141
+        for name, shape, off in self._meta:
+            n = math.prod(shape)
+            p = nn.Parameter(flat[off:off + n].view(shape))
+            with torch.no_grad():
+                is_norm = ".norm" in name or name.startswith("out_conv.0")
+                if name.endswith(".weight") and not is_norm:
+                    _xavier_uniform_(p, 0. if name.endswith(zero_scale) else 1.)
+                elif name.endswith(".weight"):
+                    p.fill_(1.)
+            node = self
+            *path, leaf = name.split(".")
+            for part in path:
+                if part not in node._modules:
+                    node.add_module(part, _Node())
+                node = node._modules[part]
+            node.register_parameter(leaf, p)
+            self._params.append(p)
+        self._flat = flat
+        self._grads = None
+        self._ws = None
+        self._plan_key = None
+        self._packed_version = None
+        self._drop_calls = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().ddpm_unet_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ flat-buffer maintenance
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)     # .to()/.cuda()/.float() give every parameter its own storage ...
+        self._reflatten()                     # ... so gather them back into one flat buffer
+        return out
+
+    def _reflatten(self):
+        dev = self._params[0].device
+        flat = torch.zeros(self._flat_elems, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, (_, shape, off) in zip(self._params, self._meta):
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1).to(torch.float32))
+                p.data = flat[off:off + n].view(shape)
+        self._flat = flat
+        self._plan_key = None
+        self._packed_version = None
+
+    def _views_ok(self):
+        base = self._flat.data_ptr()
+        return all(p.data_ptr() == base + 4 * off for p, (_, _, off) in zip(self._params, self._meta))
+
+    @property
+    def flat_params(self):
+        return self._flat
+
+    @property
+    def flat_grads(self):
+        return self._grads
+
+    def grad_views(self, flat=None):
+        flat = self._grads if flat is None else flat
+        return [flat[off:off + math.prod(shape)].view(shape) for _, shape, off in self._meta]
+
+    # ------------------------------------------------------------------ planning
+    def prepare(self, B, H, W, training):
+        """Compile (or reuse) the launch plan for this batch shape and (re)pack weights if they changed."""
+        if not self._flat.is_cuda:
+            raise RuntimeError("ddpm_torch_b200.UNet runs on sm_100a CUDA devices only (no CPU / PyTorch fallback); "
+                               "move the model with .cuda() first")
+        if not self._views_ok():
+            self._reflatten()
+        L = _lib.lib()
+        key = (B, H, W, bool(training), self._flat.data_ptr())
+        if key != self._plan_key:
+            need = L.ddpm_unet_workspace_bytes(self._h, B, H, W, int(training))
+            if need < 0:
+                _lib.check(int(need), "workspace_bytes")
+            dev = self._flat.device
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = None
+                self._ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+            if training and (self._grads is None or self._grads.device != dev):
+                self._grads = torch.zeros(self._flat_elems, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.ddpm_unet_plan(self._h, B, H, W, int(training), self._flat.data_ptr(),
+                                            self._grads.data_ptr() if training else None,
+                                            self._ws.data_ptr(), self._ws.numel()), "unet_plan")
+            self._plan_key = key
+            self._packed_version = None
+        self.repack_if_needed(force=training)
+        return self._h
+
+    def repack_if_needed(self, force=False):
+        v = self._flat._version
+        if force or v != self._packed_version:
+            _lib.check(_lib.lib().ddpm_unet_repack(self._h, _lib.stream_ptr()), "unet_repack")
+            self._packed_version = v
+
+    def repack(self):
+        """Call after out-of-band weight edits (e.g. ``p.data.copy_`` as the reference EMA does, utils/train.py:307-316)."""
+        self._packed_version = None
+
+    def next_dropout_seed(self):
+        self._drop_calls += 1
+        return (torch.initial_seed() * 1000003 + self._drop_calls) & 0xFFFFFFFFFFFFFFFF
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, t):
+        B, Cc, H, W = x.shape
+        assert Cc == self.in_channels
+        x = x.contiguous().float()
+        t = t.contiguous().to(torch.int64)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._params)
+        if need_grad:
+            return _UNetFn.apply(self, x, t, *self._params)
+        return self._forward_nograd(x, t)
+
+    def _forward_nograd(self, x, t, training_plan=False):
+        B, _, H, W = x.shape
+        h = self.prepare(B, H, W, training_plan)
+        out = torch.empty(B, self.out_channels, H, W, dtype=torch.float32, device=x.device)
+        seed = self.next_dropout_seed() if (self.training and self.drop_rate > 0) else 0
+        _lib.check(_lib.lib().ddpm_unet_forward(h, x.data_ptr(), t.data_ptr(), out.data_ptr(), seed, _lib.stream_ptr()),
+                   "unet_forward")
+        return out
+
+
+class _UNetFn(torch.autograd.Function):
+    """Autograd bridge: parameter gradients come back as views of one freshly cloned flat buffer."""
+
+    @staticmethod
+    def forward(ctx, model, x, t, *params):
+        out = model._forward_nograd(x, t, training_plan=True)
+        ctx.model = model
+        ctx.save_for_backward(x, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model = ctx.model
+        g = grad_out.contiguous().float()
+        _lib.check(_lib.lib().ddpm_unet_backward(model._h, g.data_ptr(), _lib.stream_ptr()), "unet_backward")
+        flat = model._grads.clone()
+        return (None, None, None, *model.grad_views(flat))

@@ -53,6 +53,56 @@ typedef struct ddpm_gemm_desc {
 } ddpm_gemm_desc;
 int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * UNet engine.  replaces: UNet.__init__/forward (ddpm_torch/models/unet.py:96-233), its autograd backward,
+ * and the model-side half of GaussianDiffusion.train_losses / p_sample_step (diffusion.py:107-158,217-243).
+ */
+typedef struct ddpm_unet_cfg {          /* mirrors UNet(in_channels, hid_channels, out_channels, ch_multipliers,   */
+    int in_channels, hid_channels, out_channels;   /* num_res_blocks, apply_attn, time_embedding_dim, drop_rate)  unet.py:96-107 */
+    int levels; int ch_mult[8];
+    int num_res_blocks; int attn[8];
+    int temb_dim;                       /* 0 -> 4*hid_channels (unet.py:112) */
+    float drop_rate;
+} ddpm_unet_cfg;
+typedef struct ddpm_unet ddpm_unet;
+
+int  ddpm_unet_create(const ddpm_unet_cfg* cfg, ddpm_unet** out);
+void ddpm_unet_destroy(ddpm_unet* h);
+/* Parameter inventory in the reference's state_dict order (unet.py registration order). Offsets (in fp32 elements)
+ * address the FLAT parameter / gradient buffers the caller owns; each tensor is OIHW / [out,in] fp32 as in the reference. */
+int       ddpm_unet_num_params(const ddpm_unet* h);
+int       ddpm_unet_param_info(const ddpm_unet* h, int i, const char** name, int* ndim, int dims[4], long long* offset);
+long long ddpm_unet_flat_elems(const ddpm_unet* h);
+/* Workspace bytes for a (batch, H, W) plan; training != 0 also plans the backward pass. */
+long long ddpm_unet_workspace_bytes(ddpm_unet* h, int B, int H, int W, int training);
+/* Bind caller-owned device buffers and compile the launch plan. grads_flat may be NULL when training == 0. */
+int ddpm_unet_plan(ddpm_unet* h, int B, int H, int W, int training, float* params_flat, float* grads_flat,
+                   void* workspace, long long workspace_bytes);
+/* Re-pack fp32 master weights into the bf16 kernel layouts; call after every parameter update / load_state_dict. */
+int ddpm_unet_repack(ddpm_unet* h, void* stream);
+/* eps = UNet(x, t):  x f32[B,Cin,H,W] NCHW, t i64[B], eps f32[B,Cout,H,W]   (unet.py:205-233) */
+int ddpm_unet_forward(ddpm_unet* h, const float* x, const int64_t* t, float* eps, uint64_t dropout_seed, void* stream);
+/* Backward of the last forward: d_eps f32[B,Cout,H,W] -> flat grads (zeroed then written). x,t must be unchanged. */
+int ddpm_unet_backward(ddpm_unet* h, const float* d_eps, void* stream);
+/* Fused training forward (diffusion.py:217-243, mse/eps branch): x_t = q_sample(x0,t,noise) with the fp32 tables
+ * tab_sqrt_ab / tab_sqrt_1mab [T]; eps = UNet(x_t,t); losses[b] = mean((noise-eps)^2). */
+int ddpm_train_forward(ddpm_unet* h, const float* x0, const int64_t* t, const float* noise, const float* tab_sqrt_ab,
+                       const float* tab_sqrt_1mab, float* losses, uint64_t dropout_seed, void* stream);
+/* Backward of ddpm_train_forward given d(sum)/d(losses[b]) = gscale[b] (f32[B]). */
+int ddpm_train_backward(ddpm_unet* h, const float* gscale, void* stream);
+/* Sampler (diffusion.py:152-174, ddim.py:96-113).  setup uploads per-step tables: t_model[S] (timestep fed to the UNet),
+ * coef[S][6] = {sqrt_recip_ab, sqrt_recip_m1_ab, post_c1, post_c2, exp(.5*logvar), t>0}; both HOST pointers.
+ * reset(step) arms the device-side step counter; each step() call then consumes one step (counter decrements),
+ * x f32[B,C,H,W] is updated in place; z = per-step N(0,1) draw (device) or NULL (+seed != 0: built-in Philox stream).
+ * A step() is a fixed launch sequence with no host-side arguments that change -> capturable once, replayable T times. */
+int ddpm_sampler_setup(ddpm_unet* h, int S, const int64_t* t_model_host, const float* coef_host);
+int ddpm_sampler_reset(ddpm_unet* h, int first_step, void* stream);
+int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, void* stream);
+/* Introspection for tests / bench: op counts and algorithmic FLOPs of the compiled plan. */
+int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd_ops, int* n_bwd_ops, int* n_tensorcore_ops, int* n_generic_ops,
+                         double* fwd_flops, double* bwd_flops);
+int ddpm_unet_launches_per_forward(const ddpm_unet* h);
+
 #ifdef __cplusplus
 }
 #endif
