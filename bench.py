@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: UNet fwd+bwd images/sec (CIFAR-10 config, bs=128 per GPU, training
+mode, synthetic 3x32x32) on N B200s, plus p_sample-loop images/sec (bs=256) at N=1.
+
+    python bench.py [--gpus N --steps K --warmup W]           # this framework (sm_100a engine through the C ABI)
+    python bench.py --impl reference [...]                     # the reference's CPU path (oracle port, all host threads)
+
+One JSON line on stdout (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same step
+driven through the public Python API with the batch coming from pinned host memory and the loss read back.
+A "step" = weight re-pack + q_sample + UNet forward + MSE + full backward (grads of all 304 tensors)
+(+ one NCCL all-reduce (mean) of the flat gradient buffer when N > 1).  Optimiser/EMA are outside the metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CIFAR = dict(in_channels=3, hid_channels=128, out_channels=3, ch_multipliers=(1, 2, 2, 2), num_res_blocks=2,
+             apply_attn=(False, True, False, False), drop_rate=0.1)
+FWD_GFLOP_PER_IMG = 12.444          # 2*MAC of convs + linears + attention matmuls
+TRAIN_GFLOP_PER_IMG = 3 * FWD_GFLOP_PER_IMG
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def dist_setup(n):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, local, world
+
+
+def run_reference(args):
+    """The reference's own implementation of the step on the host CPU (oracle port of the unmodified reference's
+    PyTorch path — the Python reference cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import ddpm_ref as R
+    torch.set_num_threads(os.cpu_count())
+    bs = 8
+    cfg = dict(R.CIFAR10_CFG); cfg["drop_rate"] = 0.0
+    sd = {k: v.requires_grad_(True) for k, v in R.make_state_dict(cfg, 1234).items()}
+    diff = R.RefDiffusion(R.get_beta_schedule("linear", 1e-4, 0.02, 1000), "fixed-large")
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(bs, 3, 32, 32, generator=g); t = torch.randint(1000, (bs,), generator=g); noise = torch.randn(bs, 3, 32, 32, generator=g)
+
+    def step():
+        for p in sd.values():
+            p.grad = None
+        diff.train_losses(lambda x, tt: R.unet_forward(sd, cfg, x, tt), x0, t, noise).mean().backward()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = bs / dt
+    line = {"impl": "reference", "metric": "unet_train_step_images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CIFAR-10 UNet (configs/cifar10.json) q_sample+fwd+MSE+bwd, fp32 CPU, bounded sample bs=8 per step"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.steps} steps of bs={bs} (of the bs=128 workload), fp32, torch CPU, {torch.get_num_threads()} threads"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(budget_s=20.0):
+    from oracle import ddpm_ref as R
+    torch.set_num_threads(os.cpu_count())
+    bs = 8
+    cfg = dict(R.CIFAR10_CFG); cfg["drop_rate"] = 0.0
+    sd = {k: v.requires_grad_(True) for k, v in R.make_state_dict(cfg, 1234).items()}
+    diff = R.RefDiffusion(R.get_beta_schedule("linear", 1e-4, 0.02, 1000), "fixed-large")
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(bs, 3, 32, 32, generator=g); t = torch.randint(1000, (bs,), generator=g); noise = torch.randn(bs, 3, 32, 32, generator=g)
+
+    def step():
+        for p in sd.values():
+            p.grad = None
+        diff.train_losses(lambda x, tt: R.unet_forward(sd, cfg, x, tt), x0, t, noise).mean().backward()
+    step()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and n < 40:
+        step(); n += 1
+    dt = (time.perf_counter() - t0) / max(n, 1)
+    return {"value": bs / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} steps of bs={bs} fwd+bwd (oracle port of the reference path, fp32, torch CPU, {torch.get_num_threads()} threads)"}
+
+
+def dominant_kernel_roofline(pk, iters=20):
+    """Time the dominant tcgen05 launch of the step in isolation, live, with CUDA events on the launching stream:
+    3x3 conv Ci=Co=128 at 32x32, batch 128 (7 forward + 7 dgrad launches per step share this shape; 17% of FLOPs).
+    Inputs (33.5 MB in + 33.5 MB out per launch) are rotated over 8 buffer pairs (537 MB > 126 MB L2)."""
+    import ctypes as C
+    from ddpm_torch_b200 import _lib
+    B, H, W, Ci, Co = 128, 32, 32, 128, 128
+    nbuf = 8
+    xs = [torch.randn(B, H, W, Ci, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+    ys = [torch.empty(B, H, W, Co, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    w = (torch.randn(Co, 9 * Ci, device="cuda") * 0.03).to(torch.bfloat16)
+    bias = torch.zeros(Co, device="cuda")
+    descs = []
+    for i in range(nbuf):
+        d = _lib.GemmDesc()
+        d.mode = 0; d.M = B * H * W; d.N = Co; d.W = W; d.H = H; d.NB = B
+        d.a_ptr[0] = xs[i].data_ptr(); d.a_C[0] = Ci; d.a_ld[0] = Ci
+        d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = Ci // 64; d.seg_cbase[0] = 0
+        d.b_ptr = w.data_ptr(); d.b_K = 9 * Ci; d.b_rows = Co; d.b_batch = 1; d.b_ld = 9 * Ci
+        d.out = ys[i].data_ptr(); d.ldo = Co; d.bias = bias.data_ptr(); d.alpha = 1.0; d.grid_z = 1
+        descs.append(d)
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    for i in range(nbuf):
+        _lib.check(L.ddpm_gemm_run(C.byref(descs[i]), st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(iters):
+        L.ddpm_gemm_run(C.byref(descs[i % nbuf]), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * B * H * W * Co * 9 * Ci
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": None,
+            "kernel": "umma_gemm_kernel<128,KK> conv3x3 128->128 @32x32 B=128 (isolated, rotating buffers > L2)",
+            "ms_per_launch": ms, "peak_source": f"{pk['src']} bf16 burst (MEASURED_PEAKS.json)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bs", type=int, default=128, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--no-sampler", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import ddpm_torch_b200 as D
+    from ddpm_torch_b200 import _lib
+    rank, local, world = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.runtime_check()
+    pk = peaks()
+    torch.manual_seed(1234 + rank)
+    B = args.bs
+    model = D.UNet(**CIFAR).to(dev).train()
+    # non-degenerate weights (the reference init zeroes the last conv of every block -> all-zero gradients upstream)
+    with torch.no_grad():
+        gi = torch.Generator(device=dev).manual_seed(7)
+        for n_, p in model.named_parameters():
+            if p.ndim >= 2:
+                fan_in = p[0].numel()
+                p.copy_((torch.rand(p.shape, device=dev, generator=gi) * 2 - 1) * (3.0 / fan_in) ** 0.5)
+    diff = D.GaussianDiffusion(D.get_beta_schedule("linear", 1e-4, 0.02, 1000), "eps", "fixed-large", "mse")
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    # device-resident inputs for `value`: several batches so that consecutive steps do not re-read the same lines
+    nb = 4
+    x0s = [torch.rand(B, 3, 32, 32, device=dev, generator=g) * 2 - 1 for _ in range(nb)]
+    ts = [torch.randint(1000, (B,), device=dev, generator=g) for _ in range(nb)]
+    nzs = [torch.randn(B, 3, 32, 32, device=dev, generator=g) for _ in range(nb)]
+    L = _lib.lib()
+    h = model.prepare(B, 32, 32, training=True)
+    ta, tsb = diff._dev_tables(dev)
+    losses = torch.empty(B, device=dev)
+    gscale = torch.full((B,), 1.0 / B, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        sp = _lib.stream_ptr()
+        _lib.check(L.ddpm_unet_repack(h, sp))
+        k = i % nb
+        _lib.check(L.ddpm_train_forward(h, x0s[k].data_ptr(), ts[k].data_ptr(), nzs[k].data_ptr(), ta.data_ptr(), tsb.data_ptr(),
+                                        losses.data_ptr(), 1000 + i, sp))
+        _lib.check(L.ddpm_train_backward(h, gscale.data_ptr(), sp))
+        if world > 1:
+            dist.all_reduce(model.flat_grads, op=dist.ReduceOp.AVG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    with ClockSampler(local) as cs:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = cs.summary()
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = tms.item()
+    value = world * B / (ms * 1e-3)
+    assert L.ddpm_device_error_flag() == 0
+    nf, nbw, npk = (__import__("ctypes").c_int() for _ in range(3))
+    import ctypes as C
+    L.ddpm_unet_launch_counts(h, C.byref(nf), C.byref(nbw), C.byref(npk))
+    launches_per_step = nf.value + nbw.value + npk.value + 3      # + q_sample, mse, mse_grad
+
+    # ---- e2e: public API, batch from pinned host memory, loss read back (+ all-reduce through the same flat buffer)
+    host_x = [torch.empty(B, 3, 32, 32).uniform_(-1, 1).pin_memory() for _ in range(nb)]
+    gen = torch.Generator(device=dev).manual_seed(8191 + rank)
+
+    def e2e_step(i):
+        x = host_x[i % nb].to(dev, non_blocking=True)
+        t = torch.randint(1000, (B,), device=dev, generator=gen)
+        nz = torch.randn(B, 3, 32, 32, device=dev, generator=gen)
+        for p in model.parameters():
+            p.grad = None
+        loss = diff.train_losses(model, x, t, nz).mean()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(model.flat_grads, op=dist.ReduceOp.AVG)
+        return loss.item()
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_val = world * B / (ems.item() * 1e-3)
+
+    line = {"metric": "unet_train_step_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "CIFAR-10 UNet (configs/cifar10.json, 35.7M params, drop 0.1 active) training step: repack + q_sample + fwd + MSE + bwd"
+                                   + (" + NCCL all-reduce(mean) of the flat fp32 grads" if world > 1 else ""),
+                       "per_gpu_batch": B, "global_batch": B * world, "resolution": "3x32x32", "parallelism": f"dp{world}",
+                       "l2": "4 rotating input batches; activations (2.2 GB fwd) exceed the 126 MB L2"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 32 * 32 * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ems.item(), "api": "GaussianDiffusion.train_losses(model, x, t, noise).mean().backward()"},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
+            "step_tflops": world * B * TRAIN_GFLOP_PER_IMG / ms, "step_frac_of_sustained_peak": B * TRAIN_GFLOP_PER_IMG / ms / pk["sustained"]}
+
+    if rank == 0:
+        line["roofline"] = dominant_kernel_roofline(pk)
+        if not args.no_sampler and world == 1:
+            line["sampler"] = bench_sampler(D, model, dev)
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_sampler(D, model, dev, bs=256):
+    """config 3: p_sample T=1000 (fixed-large) and DDIM S=50 (eta 0) at bs=256, one CUDA-graph replay per timestep."""
+    out = {}
+    betas = D.get_beta_schedule("linear", 1e-4, 0.02, 1000)
+    model.eval()
+    base = D.GaussianDiffusion(betas, "eps", "fixed-large", "mse")
+    ddim = D.DDIM.from_ddpm(D.GaussianDiffusion(betas, "eps", "fixed-small", "mse"), eta=0.0, subsequence=D.get_selection_schedule("linear", 50, 1000))
+    for name, d, S in (("ddim50", ddim, 50), ("ancestral1000", base, 1000)):
+        d.p_sample(model, shape=(bs, 3, 32, 32), device=dev, seed=1) if name == "ddim50" else None      # warm-up (plan, graph)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        x = d.p_sample(model, shape=(bs, 3, 32, 32), device=dev, seed=2)
+        e1.record()
+        torch.cuda.synchronize()
+        s = e0.elapsed_time(e1) * 1e-3
+        assert torch.isfinite(x).all()
+        out[name] = {"images_per_s": bs / s, "seconds_per_batch": s, "ms_per_step": s / S * 1e3, "bs": bs, "steps": S, "rng": "torch generator (reference-compatible stream)"}
+    model.train()
+    return out
+
+
+if __name__ == "__main__":
+    main()

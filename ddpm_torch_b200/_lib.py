@@ -26,6 +26,10 @@ class GemmDesc(C.Structure):
         ("out_tap_stride", C.c_longlong), ("flags", C.c_int),
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int), ("rows_per_vec", C.c_int),
         ("residual", C.c_void_p), ("ldr", C.c_int), ("alpha", C.c_float),
+        ("a_estride", C.c_int), ("b_estride", C.c_int), ("b_pad", C.c_int),
+        ("seg_custom", C.c_int * 3), ("seg_cmul", C.c_int * 3),
+        ("seg_dx", (C.c_byte * 9) * 3), ("seg_dy", (C.c_byte * 9) * 3),
+        ("o_mul", C.c_int), ("o_py", C.c_int), ("o_px", C.c_int),
     ]
 
 
@@ -72,6 +76,7 @@ def lib():
             "ddpm_unet_plan_stats": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
             "ddpm_unet_launches_per_forward": ([vp], i32),
+            "ddpm_unet_launch_counts": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
         }
         for name, (args, res) in sig.items():
             fn = getattr(L, name)
@@ -86,7 +91,7 @@ EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "d
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",
            "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_unet_plan_stats",
-           "ddpm_unet_launches_per_forward"]
+           "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts"]
 
 
 def check(rc, what=""):

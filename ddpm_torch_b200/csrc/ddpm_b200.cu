@@ -113,9 +113,7 @@ int ddpm_unet_backward(ddpm_unet* h, const float* d_eps, void* stream) {
     UnetEngine& e = h->e;
     if (!e.train) return fail(-33, "plan was built without training");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int Cout = e.cfg.out_channels, HW = e.H * e.W;
-    k_nchw_f32_to_nhwc_bf16<<<grid_for((long long)e.B * HW * 8), 256, 0, st>>>(d_eps, e.at<bf16>(e.deps_off), e.B, Cout, HW, 8);
-    DDPM_CUDA_OK(cudaGetLastError());
+    e.deps_src = d_eps;
     return e.run_list(e.bwd_ops, st);
 }
 int ddpm_train_forward(ddpm_unet* h, const float* x0, const int64_t* t, const float* noise, const float* tab_a, const float* tab_s,
@@ -141,10 +139,11 @@ int ddpm_train_backward(ddpm_unet* h, const float* gscale, void* stream) {
     UnetEngine& e = h->e;
     if (!e.train || !h->train_target) return fail(-33, "ddpm_train_forward must precede ddpm_train_backward on a training plan");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int HW = e.H * e.W;
-    k_mse_grad<<<grid_for((long long)e.B * HW * 8), 256, 0, st>>>(e.at<float>(e.eps_off), h->train_target, gscale, e.at<bf16>(e.deps_off),
-                                                                 e.B, e.cfg.out_channels, HW, 8);
+    const int per_img = e.cfg.out_channels * e.H * e.W;
+    const long long total = (long long)e.B * per_img;
+    k_mse_grad<<<grid_for(total), 256, 0, st>>>(e.at<float>(e.eps_off), h->train_target, gscale, e.at<float>(e.deps_off), per_img, total);
     DDPM_CUDA_OK(cudaGetLastError());
+    e.deps_src = e.at<float>(e.deps_off);
     return e.run_list(e.bwd_ops, st);
 }
 
@@ -191,6 +190,12 @@ int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd, int* n_bwd, int* n_tc, 
     if (bf) *bf = h->e.bwd_flops;
     return 0;
 }
-int ddpm_unet_launches_per_forward(const ddpm_unet* h) { return (int)h->e.fwd_ops.size(); }
+int ddpm_unet_launches_per_forward(const ddpm_unet* h) { return UnetEngine::count_launches(h->e.fwd_ops); }
+int ddpm_unet_launch_counts(const ddpm_unet* h, int* fwd, int* bwd, int* pack) {
+    if (fwd) *fwd = UnetEngine::count_launches(h->e.fwd_ops);
+    if (bwd) *bwd = UnetEngine::count_launches(h->e.bwd_ops);
+    if (pack) *pack = UnetEngine::count_launches(h->e.pack_ops);
+    return 0;
+}
 
 }  // extern "C"

@@ -27,6 +27,9 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     p.b_k_base = d.b_k_base; p.a_z_n = d.a_z_n; p.b_z = d.b_z;
     p.taps = d.taps > 0 ? d.taps : 1; p.splits = d.splits > 0 ? d.splits : 1; p.kblocks = d.kblocks;
     p.a_c_base = d.a_c_base; p.b_c_base = d.b_c_base;
+    p.b_cmul = d.b_estride > 1 ? d.b_estride : 1; p.b_pad = d.b_estride > 1 ? d.b_pad : 1;
+    p.o_mul = d.o_mul > 1 ? d.o_mul : 1; p.o_py = d.o_py; p.o_px = d.o_px; p.oW = d.W * p.o_mul; p.oH = d.H * p.o_mul;
+    const int aes = d.a_estride > 1 ? d.a_estride : 1, bes = d.b_estride > 1 ? d.b_estride : 1;
     const int gz = d.grid_z > 0 ? d.grid_z : 1;
     const int n_tiles = (d.N + g.block_n - 1) / g.block_n;
     const int m_tiles = (d.M + 127) / 128;
@@ -38,13 +41,20 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
         if (d.nseg < 1 || d.nseg > 3) return fail(-11, "KK: nseg must be 1..3");
         int slabs = 0;
         for (int s = 0; s < d.nseg; ++s) {
-            if (d.seg_taps[s] != 1 && d.seg_taps[s] != 9) return fail(-11, "KK: taps must be 1 or 9");
-            p.seg[s] = make_seg(d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]);
+            if (d.seg_custom[s]) {
+                if (d.seg_taps[s] < 1 || d.seg_taps[s] > 9) return fail(-11, "KK: custom taps must be 1..9");
+                p.seg[s] = make_seg(d.seg_map[s], 1, d.seg_kchunks[s], d.seg_cbase[s]);
+                p.seg[s].taps = d.seg_taps[s]; p.seg[s].cmul = d.seg_cmul[s] > 0 ? d.seg_cmul[s] : 1;
+                for (int t = 0; t < d.seg_taps[s]; ++t) { p.seg[s].dx[t] = d.seg_dx[s][t]; p.seg[s].dy[t] = d.seg_dy[s][t]; }
+            } else {
+                if (d.seg_taps[s] != 1 && d.seg_taps[s] != 9) return fail(-11, "KK: taps must be 1 or 9");
+                p.seg[s] = make_seg(d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]);
+            }
             slabs += d.seg_taps[s] * d.seg_kchunks[s];
         }
         for (int i = 0; i < 3; ++i) {
             if (!d.a_ptr[i]) { g.a[i] = g.a[0]; continue; }
-            if ((rc = make_tmap_4d(&g.a[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.NB, d.a_ld[i], 64, p.w_t, p.h_t, p.n_t))) return rc;
+            if ((rc = make_tmap_4d(&g.a[i], d.a_ptr[i], d.a_C[i], d.W * aes, d.H * aes, d.NB, d.a_ld[i], 64, p.w_t, p.h_t, p.n_t, aes))) return rc;
         }
         if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n))) return rc;
         g.flops = 2.0 * d.M * d.N * 64.0 * slabs * gz;
@@ -53,7 +63,7 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
         if (d.M % 64) return fail(-11, "MNMN: M must be a multiple of 64");
         if ((rc = make_tmap_4d(&g.a[0], d.a_ptr[0], d.a_C[0], d.W, d.H, d.NB, d.a_ld[0], 64, p.wk_t, p.hk_t, p.nk_t))) return rc;
         g.a[1] = g.a[2] = g.a[0];
-        if ((rc = make_tmap_4d(&g.b, d.b_ptr, d.b_K, d.W, d.H, d.NB, d.b_ld, 64, p.wk_t, p.hk_t, p.nk_t))) return rc;
+        if ((rc = make_tmap_4d(&g.b, d.b_ptr, d.b_K, d.W * bes, d.H * bes, d.NB, d.b_ld, 64, p.wk_t, p.hk_t, p.nk_t, bes))) return rc;
         g.flops = 2.0 * d.M * d.N * 64.0 * d.kblocks * p.taps * (gz / (p.taps * p.splits));
     } else if (d.mode == GEMM_KMN) {
         if (!pick_box(d.W, d.H, 128, p.w_t, p.h_t, p.n_t)) return fail(-11, "KMN: unsupported geometry W=%d H=%d", d.W, d.H);

@@ -33,15 +33,17 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
 }
 
 // bf16 tensor viewed as (C, W, H, N) with channels contiguous, pixel stride ld elements; 128-byte swizzle.
+// estride = 2 samples every other pixel in W and H (stride-2 convolutions): the box then spans estride*box_{w,h}
+// elements and TMA loads ceil(span/estride) of them.
 inline int make_tmap_4d(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, long long ld,
-                        int box_c, int box_w, int box_h, int box_n) {
+                        int box_c, int box_w, int box_h, int box_n, int estride = 1) {
     auto fn = tmap_encode_fn();
     if (!fn) return fail(-3, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7)) return fail(-4, "tensor map: pointer/stride not 16-byte aligned");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), (cuuint32_t)box_n};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -521,13 +521,16 @@ __global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
 }
 
 // ============================================================================ in_conv: NCHW fp32 [B,Ci<=4,H,W] -> NHWC bf16 [B,H,W,Co], 3x3 pad 1
-__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, const float* __restrict__ w /*OIHW fp32*/,
+// Also used as the data-gradient of the 3-channel out_conv (x := d_eps, w := flipped/transposed weights).
+// w layout: [Co][Ci*9] fp32 (OIHW), out NHWC bf16.  Ci <= 4.
+template <int CI>
+__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, const float* __restrict__ w,
                                                 const float* __restrict__ bias, bf16* __restrict__ out,
-                                                int B, int Ci, int H, int W, int Co) {
-    extern __shared__ float sw[];                 // [Co][Ci*9] + [Co]
-    const int K = Ci * 9;
+                                                int B, int H, int W, int Co) {
+    extern __shared__ float sw[];                 // [Co][CI*9] + [Co]
+    constexpr int K = CI * 9;
     for (int i = threadIdx.x; i < Co * K; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < Co; i += blockDim.x) sw[Co * K + i] = bias[i];
+    for (int i = threadIdx.x; i < Co; i += blockDim.x) sw[Co * K + i] = bias ? bias[i] : 0.f;
     __syncthreads();
     const int oct = Co >> 3;
     const long long total = (long long)B * H * W * oct;
@@ -535,65 +538,157 @@ __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, co
         const long long pix = i / oct;
         const int c0 = (int)(i % oct) * 8;
         const int b = (int)(pix / (H * W)), r = (int)(pix % (H * W)), y = r / W, xx = r % W;
-        float in[36];
-        for (int ci = 0; ci < Ci; ++ci)
+        float in[K];
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
-                in[ci * 9 + t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)b * Ci + ci) * H + iy) * W + ix) : 0.f;
+                in[ci * 9 + t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)b * CI + ci) * H + iy) * W + ix) : 0.f;
             }
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float s = sw[Co * K + c0 + e];
+            float sacc = sw[Co * K + c0 + e];
             const float* wr = sw + (c0 + e) * K;
-            for (int k = 0; k < K; ++k) s += in[k] * wr[k];
-            o[e] = s;
+#pragma unroll
+            for (int k = 0; k < K; ++k) sacc += in[k] * wr[k];
+            o[e] = sacc;
         }
         *reinterpret_cast<uint4*>(out + pix * Co + c0) = pack8(o);
     }
 }
-// wgrad of in_conv: dW[co][ci][tap] += sum_p dy[p][co] * x[b,ci,iy,ix]  ; one block per (co-octet range), split over pixels
-__global__ void __launch_bounds__(256) k_in_conv_wgrad(const bf16* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
-                                                      float* __restrict__ dbias, int B, int Ci, int H, int W, int Co, int pix_per_block) {
-    // thread <-> output channel (Co <= 256); loops over its pixel range; accumulates K=Ci*9 partials in registers
-    const int co = threadIdx.x;
+// Correlation of a wide NHWC bf16 tensor with a narrow NCHW fp32 tensor (3x3 window):
+//   acc[C][ci][t] = sum_p wide[p][C] * narrow[b, ci, y + t/3 - 1, x + t%3 - 1]
+// = weight gradient of in_conv (wide = dY, narrow = x_t):   dW[C][ci][t]      -> dw[C*s_c + ci*s_ci + t*s_t]
+// = weight gradient of out_conv (wide = a, narrow = d_eps):  dW[ci][C][8 - t]  (flip_t = 1, strides swapped by the caller)
+// thread <-> wide channel C (blockDim.x = C <= 256); the narrow 3x3 patches of 32 pixels are staged in shared memory.
+template <int CI>
+__global__ void __launch_bounds__(256) k_corr3x3(const bf16* __restrict__ wide, const float* __restrict__ narrow, float* __restrict__ dw,
+                                                 long long s_c, long long s_ci, long long s_t, int flip_t, float* __restrict__ dbias_wide,
+                                                 int B, int H, int W, int C, int pix_per_block) {
+    constexpr int K = CI * 9, PB = 32;
+    __shared__ float sx[PB][K + 1];
+    const int c = threadIdx.x;
     const long long P = (long long)B * H * W;
     const long long p0 = (long long)blockIdx.x * pix_per_block;
     long long p1 = p0 + pix_per_block; if (p1 > P) p1 = P;
-    float acc[36]; float accb = 0.f;
-    for (int k = 0; k < 36; ++k) acc[k] = 0.f;
-    __shared__ float sx[36];
-    for (long long p = p0; p < p1; ++p) {
-        const int b = (int)(p / (H * W)), r = (int)(p % (H * W)), y = r / W, xx = r % W;
+    float acc[K]; float accb = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    for (long long pb = p0; pb < p1; pb += PB) {
         __syncthreads();
-        if (threadIdx.x < Ci * 9) {
-            const int ci = threadIdx.x / 9, t = threadIdx.x % 9;
-            const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
-            sx[threadIdx.x] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long long)b * Ci + ci) * H + iy) * W + ix] : 0.f;
+        for (int i = threadIdx.x; i < PB * K; i += blockDim.x) {
+            const int pp = i / K, k = i % K, ci = k / 9, t = k % 9;
+            const long long p = pb + pp;
+            float v = 0.f;
+            if (p < p1) {
+                const int b = (int)(p / (H * W)), r = (int)(p % (H * W)), y = r / W, xx = r % W;
+                const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = narrow[(((long long)b * CI + ci) * H + iy) * W + ix];
+            }
+            sx[pp][k] = v;
         }
         __syncthreads();
-        if (co < Co) {
-            const float d = __bfloat162float(dy[p * Co + co]);
-            accb += d;
-            for (int k = 0; k < Ci * 9; ++k) acc[k] += d * sx[k];
+        if (c < C) {
+            const int n = (int)((p1 - pb) < PB ? (p1 - pb) : PB);
+            for (int pp = 0; pp < n; ++pp) {
+                const float d = __bfloat162float(wide[(pb + pp) * C + c]);
+                accb += d;
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] += d * sx[pp][k];
+            }
         }
     }
-    if (co < Co) {
-        for (int k = 0; k < Ci * 9; ++k) atomicAdd(dw + (long long)co * Ci * 9 + k, acc[k]);
-        atomicAdd(dbias + co, accb);
+    if (c < C) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int ci = k / 9, t = k % 9;
+            atomicAdd(dw + c * s_c + ci * s_ci + (flip_t ? 8 - t : t) * s_t, acc[k]);
+        }
+        if (dbias_wide) atomicAdd(dbias_wide + c, accb);
     }
 }
-
+// out_conv forward: NHWC bf16 [B,H,W,C] -> NCHW fp32 [B,Co<=4,H,W], 3x3 pad 1.  4 lanes per pixel (C/4 channels each),
+// weights [Co][C][9] (OIHW fp32) staged in shared memory as [9][Co][C].
+template <int CO>
+__global__ void __launch_bounds__(256) k_out_conv(const bf16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                                                 float* __restrict__ out, int B, int H, int W, int C) {
+    extern __shared__ float sw[];                 // [9][CO][C]
+    for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
+        const int t = i % 9, c = (i / 9) % C, co = i / (9 * C);
+        sw[(t * CO + co) * C + c] = w[i];
+    }
+    __syncthreads();
+    const long long P = (long long)B * H * W;
+    const int lane4 = threadIdx.x & 3;
+    const int cpl = C >> 2;                       // channels per lane (multiple of 8)
+    for (long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; pix < P; pix += ((long long)gridDim.x * blockDim.x) >> 2) {
+        const int b = (int)(pix / (H * W)), r = (int)(pix % (H * W)), y = r / W, x = r % W;
+        float acc[CO];
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+            const bf16* src = a + (((long long)b * H + iy) * W + ix) * C + lane4 * cpl;
+            for (int c8 = 0; c8 < cpl; c8 += 8) {
+                float f[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(src + c8)), f);
+#pragma unroll
+                for (int co = 0; co < CO; ++co) {
+                    const float* wr = sw + (t * CO + co) * C + lane4 * cpl + c8;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[co] += f[e] * wr[e];
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
+            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
+        }
+        if (lane4 == 0) {
+#pragma unroll
+            for (int co = 0; co < CO; ++co) out[((long long)b * CO + co) * (H * W) + r] = acc[co] + bias[co];
+        }
+    }
+}
+// w'[c][co*9 + t'] = w[co][c][8 - t']  : the 3->C "in_conv" whose forward is the data-gradient of out_conv
+__global__ void k_flip_transpose_w(const float* __restrict__ w, float* __restrict__ wt, int Co, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * C * 9) return;
+    const int t = i % 9, c = (i / 9) % C, co = i / (9 * C);
+    wt[(c * Co + co) * 9 + (8 - t)] = w[i];
+}
+// sum over pixels of a narrow NCHW fp32 tensor: out[c] += sum_{b,p} x[b][c][p]   (bias gradient of out_conv)
+__global__ void __launch_bounds__(256) k_chansum_nchw(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
+    const int c = blockIdx.y;
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * HW; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / HW), r = (int)(i % HW);
+        s += x[((long long)b * C + c) * HW + r];
+    }
+    s = warp_sum(s);
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int k = 0; k < 8; ++k) t += sh[k]; atomicAdd(out + c, t); }
+}
 // ============================================================================ column sums: per image and total
 // dy [B][HW][C] bf16 -> per_img[b][ld] (+=, fp32 atomics, optional) and total[c] (+=)
 __global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, float* per_img, int ld, float* total, float* total2,
                                                int HW, int C, int C_valid, int pix_per_block) {
-    // blockDim.x = (256/oct)*oct: one channel octet per thread
+    // blockDim.x = (256/oct)*oct: one channel octet per thread; partials are merged in shared memory so that each block
+    // issues ONE atomic per channel (the first version issued one per thread and spent 14 ms/step in contention)
+    extern __shared__ float sh[];                 // [C]
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_block;
     int p1 = p0 + pix_per_block; if (p1 > HW) p1 = HW;
     const int oct = C >> 3;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
     const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = p0 + lp; p < p1; p += pstep) {
@@ -603,11 +698,13 @@ __global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, flo
         for (int e = 0; e < 8; ++e) s[e] += f[e];
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        if (o * 8 + e >= C_valid) break;
-        if (per_img) atomicAdd(per_img + (long long)b * ld + o * 8 + e, s[e]);
-        if (total) atomicAdd(total + o * 8 + e, s[e]);
-        if (total2) atomicAdd(total2 + o * 8 + e, s[e]);
+    for (int e = 0; e < 8; ++e) atomicAdd(&sh[o * 8 + e], s[e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C_valid; i += blockDim.x) {
+        const float v = sh[i];
+        if (per_img) atomicAdd(per_img + (long long)b * ld + i, v);
+        if (total) atomicAdd(total + i, v);
+        if (total2) atomicAdd(total2 + i, v);
     }
 }
 
@@ -710,18 +807,12 @@ __global__ void __launch_bounds__(256) k_mse(const float* __restrict__ eps, cons
     __syncthreads();
     if (threadIdx.x == 0) { float tsum = 0.f; for (int w = 0; w < 8; ++w) tsum += sh[w]; losses[b] = tsum / (float)per_img; }
 }
-// grad of out_conv output: d_eps[b,c,h,w] fp32 NCHW -> bf16 NHWC padded to Cp channels (zeros)
+// gradient of the per-sample MSE w.r.t. eps (fp32 NCHW): d_eps = gscale[b] * 2*(eps-target)/per_img
 __global__ void k_mse_grad(const float* __restrict__ eps, const float* __restrict__ target, const float* __restrict__ gscale,
-                           bf16* __restrict__ dout, int B, int C, int HW, int Cp) {
-    const long long total = (long long)B * HW * Cp;
+                           float* __restrict__ d_eps, int per_img, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cp); const long long pix = i / Cp; const int b = (int)(pix / HW), r = (int)(pix % HW);
-        float v = 0.f;
-        if (c < C) {
-            const long long j = ((long long)b * C + c) * HW + r;
-            v = gscale[b] * 2.f * (eps[j] - target[j]) / (float)(C * HW);
-        }
-        dout[i] = __float2bfloat16_rn(v);
+        const int b = (int)(i / per_img);
+        d_eps[i] = gscale[b] * 2.f * (eps[i] - target[i]) / (float)per_img;
     }
 }
 __global__ void k_nchw_f32_to_nhwc_bf16(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C, int HW, int Cp) {
@@ -787,6 +878,18 @@ __global__ void k_pack_conv_w_padded(const float* __restrict__ w, bf16* dgr, lon
     }
 }
 
+// data-gradient pack of a stride-2 3x3 conv: [Ci][9*Co] bf16 in four output-parity blocks
+// {(py,px)=(0,0): 4 taps @0, (0,1): 2 taps @4Co, (1,0): 2 taps @6Co, (1,1): 1 tap @8Co}; taps ordered (ky asc, kx asc).
+__global__ void k_pack_conv_w_s2dgrad(const float* __restrict__ w, bf16* __restrict__ dgr, long long ld_d, int Co, int Ci) {
+    const long long total = (long long)Co * Ci * 9;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % 9); const long long r = i / 9; const int ci = (int)(r % Ci), co = (int)(r / Ci);
+        const int ky = t / 3, kx = t % 3, py = ky & 1, px = kx & 1;
+        const int base = (py == 0 ? (px == 0 ? 0 : 4) : (px == 0 ? 6 : 8)) * Co;
+        const int j = (py ? 0 : ky / 2) * (px ? 1 : 2) + (px ? 0 : kx / 2);
+        dgr[(long long)ci * ld_d + base + (long long)j * Co + co] = __float2bfloat16_rn(w[i]);
+    }
+}
 // packed grad [tap][Co][Ci] fp32 -> OIHW fp32 (=)
 // (the scratch is cleared behind the read so the next backward starts from zeros without a memset)
 __global__ void k_unpack_conv_grad(float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps) {

@@ -37,6 +37,9 @@ struct GemmParams {
     int splits;               // MNMN: split-K factor; z = (batch*taps + tap)*splits + split
     int kblocks;              // K extent in blocks of 64 (per batch)
     int a_c_base, b_c_base;   // channel-coordinate bases
+    int b_cmul, b_pad;        // MNMN: B coordinate = origin*b_cmul + tap - b_pad (b_cmul = 2 for stride-2 convs, maps with elementStrides 2)
+    // optional output-row remap (KK): tile row (n,y,x) on the A grid -> output pixel (n, y*o_mul+o_py, x*o_mul+o_px) on an oW x oH grid
+    int o_mul, o_py, o_px, oW, oH;
     // epilogue
     void* out; int ldo; long long out_z_stride; long long out_tap_stride; int flags;
     const float* bias;        // [N] or null
@@ -148,8 +151,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             } else if (MODE == GEMM_MNMN) {
                 const int per = (p.kblocks + p.splits - 1) / p.splits;
                 const int kb0 = split * per;
-                const int dx = p.taps == 9 ? (tap % 3) - 1 : 0;
-                const int dy = p.taps == 9 ? (tap / 3) - 1 : 0;
+                const int dx = p.taps == 9 ? (tap % 3) - p.b_pad : 0;
+                const int dy = p.taps == 9 ? (tap / 3) - p.b_pad : 0;
                 for (int i = 0; i < num_slabs; ++i, ++slab) {
                     uint8_t* st = acquire(slab);
                     if (!st) break;
@@ -162,7 +165,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         tma_load_4d(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
 #pragma unroll
                     for (int b = 0; b < BLOCK_N / 64; ++b)
-                        tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, x0 + dx, y0 + dy, n0);
+                        tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
                 }
             } else {  // GEMM_KMN
                 int n0, y0, x0;
@@ -212,6 +215,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const int row = m_tile * 128 + r;
         const bool row_ok = ok && row < p.M && num_slabs > 0;
+        long long orow = row;                         // output row (pixel) index
+        if (MODE == GEMM_KK && p.o_mul > 1) {
+            int n_, y_, x_;
+            pix_decompose(row, p.W, p.H, n_, y_, x_);
+            orow = ((long long)n_ * p.oH + y_ * p.o_mul + p.o_py) * p.oW + x_ * p.o_mul + p.o_px;
+        }
         const long long zoff = (MODE == GEMM_MNMN) ? (long long)batch * p.out_z_stride + (long long)tap * p.out_tap_stride
                                                   : (long long)z * p.out_z_stride;
         const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
@@ -235,7 +244,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + col + j);
             }
             if (p.residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + col);
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const uint4 u = __ldg(rp + j4);
@@ -248,15 +257,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
             if (p.flags & EPI_ATOMIC) {
-                float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)row * p.ldo + col;
+                float* o = reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(o + j, f[j]);
+                for (int j = 0; j < 32; j += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
             } else if (p.flags & EPI_OUT_F32) {
-                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + zoff + (long long)row * p.ldo + col);
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else {
-                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + (long long)row * p.ldo + col);
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + orow * p.ldo + col);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 u;

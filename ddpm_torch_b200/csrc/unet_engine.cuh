@@ -15,7 +15,7 @@ struct ParamInfo { std::string name; int nd; int dims[4]; long long numel; long 
 struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
-struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; };
+struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; };
 struct GnSaved { Src in; float* mr; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
@@ -101,9 +101,10 @@ struct UnetEngine {
     GnSrc gsrc(const Src& s) const { GnSrc g; g.x0 = bp(s.t0); g.C0 = s.t0.C; g.x1 = s.two ? bp(s.t1) : nullptr; g.C1 = s.two ? s.t1.C : 0; return g; }
     static Src one(const T4& t) { Src s; s.t0 = t; s.two = false; return s; }
 
-    void push(std::vector<Op>& L, const std::string& name, double flops, std::function<int(cudaStream_t)> f) {
-        Op o; o.name = name; o.flops = flops; o.run = std::move(f); L.push_back(std::move(o));
+    void push(std::vector<Op>& L, const std::string& name, double flops, std::function<int(cudaStream_t)> f, int launches = 1) {
+        Op o; o.name = name; o.flops = flops; o.run = std::move(f); o.launches = launches; L.push_back(std::move(o));
     }
+    static int count_launches(const std::vector<Op>& L) { int n = 0; for (auto& o : L) n += o.launches; return n; }
     // grad tensor of a forward tensor; `first` tells the producer whether to overwrite (=) or accumulate (+=)
     T4 grad_of(const T4& t, bool* first) {
         auto it = grads.find(t.off);
@@ -130,14 +131,19 @@ struct UnetEngine {
         const long long Pout = (long long)Bn * c.Ho * c.Wo;
         double fl = 2.0 * Pout * c.Co * (double)(taps * Cin + (c.has_skip ? c.skip_in.C() : 0));
         if (flops_acc) *flops_acc += fl;
-        bool tc = c.stride == 1 && c.map == MAP_NORMAL && !c.out_nchw && !c.in.two && (i0.C % 64 == 0) && (c.Co % 64 == 0) &&
-                  c.Ho == i0.H && c.Wo == i0.W && tc_ok_geom(i0.H, i0.W) && !(c.accumulate && c.residual);
+        const bool s2 = c.stride == 2 && c.map == MAP_NORMAL && c.ksize == 3 && !c.has_skip && c.Ho * 2 == i0.H && c.Wo * 2 == i0.W;
+        bool tc = (c.stride == 1 || s2) && c.map == MAP_NORMAL && !c.out_nchw && !c.in.two && (i0.C % 64 == 0) && (c.Co % 64 == 0) &&
+                  (s2 || (c.Ho == i0.H && c.Wo == i0.W)) && tc_ok_geom(c.Ho, c.Wo) && !(c.accumulate && c.residual);
         if (c.has_skip) tc = tc && (c.skip_in.t0.C % 64 == 0) && (!c.skip_in.two || c.skip_in.t1.C % 64 == 0);
         if (tc) {
             ddpm_gemm_desc d; memset(&d, 0, sizeof d);
-            d.mode = GEMM_KK; d.M = (int)Pout; d.N = c.Co; d.W = i0.W; d.H = i0.H; d.NB = Bn;
+            d.mode = GEMM_KK; d.M = (int)Pout; d.N = c.Co; d.W = c.Wo; d.H = c.Ho; d.NB = Bn;
             d.a_ptr[0] = bp(i0); d.a_C[0] = i0.C; d.a_ld[0] = i0.C;
             d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = taps; d.seg_kchunks[0] = i0.C / 64; d.seg_cbase[0] = 0;
+            if (s2) {   // SamePad2d(3,2): pad bottom/right only -> tap offsets 0..2 on the stride-2 sampled map, OOB = zero fill
+                d.a_estride = 2; d.seg_custom[0] = 1; d.seg_cmul[0] = 2;
+                for (int t = 0; t < 9; ++t) { d.seg_dx[0][t] = (signed char)(t % 3); d.seg_dy[0][t] = (signed char)(t / 3); }
+            }
             long long K = (long long)taps * Cin;
             if (c.has_skip) {
                 d.a_ptr[1] = bp(c.skip_in.t0); d.a_C[1] = c.skip_in.t0.C; d.a_ld[1] = c.skip_in.t0.C;
@@ -179,6 +185,7 @@ struct UnetEngine {
         }
     }
     float* eps_dst = nullptr;   // run-time destination of the final conv (caller buffer or internal eps buffer)
+    const float* deps_src = nullptr;   // run-time d(loss)/d(eps), fp32 NCHW (caller buffer or internal buffer)
     int plan_error = 0;
 
     // weight gradient of a conv: dW (OIHW fp32, flat grads) from dy [B,Ho,Wo,Co] and the conv input
@@ -187,8 +194,9 @@ struct UnetEngine {
         const long long P = dy.pix();
         const double fl = 2.0 * P * Co_valid * (double)taps * Cin;
         bwd_flops += fl;
-        const bool tc = stride == 1 && map == MAP_NORMAL && Co % 64 == 0 && Co == Co_valid && in.t0.C % 64 == 0 && (!in.two || in.t1.C % 64 == 0) &&
-                        tc_ok_geom(dy.H, dy.W) && in.t0.H == dy.H;
+        const bool s2 = stride == 2 && ksize == 3 && !in.two && in.t0.H == 2 * dy.H && in.t0.W == 2 * dy.W;
+        const bool tc = (stride == 1 || s2) && map == MAP_NORMAL && Co % 64 == 0 && Co == Co_valid && in.t0.C % 64 == 0 && (!in.two || in.t1.C % 64 == 0) &&
+                        tc_ok_geom(dy.H, dy.W) && (s2 || in.t0.H == dy.H);
         if (tc) {
             float* scratch = nullptr; size_t sc_off = 0;
             if (taps == 9) { sc_off = alloc_once_zero((size_t)9 * Co * Cin * 4); scratch = at<float>(sc_off); }
@@ -198,10 +206,13 @@ struct UnetEngine {
                 d.mode = GEMM_MNMN; d.M = Co; d.N = a.C; d.W = dy.W; d.H = dy.H; d.NB = dy.B;
                 d.a_ptr[0] = bp(dy); d.a_C[0] = Co; d.a_ld[0] = Co;
                 d.b_ptr = bp(a); d.b_K = a.C; d.b_ld = a.C;
+                if (s2) { d.b_estride = 2; d.b_pad = 0; }
                 d.taps = taps; d.kblocks = (int)((P + 63) / 64);
                 const int bn = pick_block_n(a.C);
                 const int tiles = ((Co + 127) / 128) * (a.C / bn) * taps;
-                int splits = (296 + tiles - 1) / tiles; if (splits > d.kblocks) splits = d.kblocks; if (splits < 1) splits = 1;
+                // split-K so that the launch is ONE full wave (<= 148 CTAs): more splits only add epilogue atomics,
+                // and 148*k + 1 CTAs would cost a whole extra wave
+                int splits = 148 / tiles; if (splits > d.kblocks / 4) splits = d.kblocks / 4; if (splits < 1) splits = 1;
                 d.splits = splits; d.grid_z = taps * splits;
                 d.flags = EPI_OUT_F32 | EPI_ATOMIC; d.alpha = 1.f;
                 if (taps == 9) { d.out = scratch + coff; d.ldo = Cin; d.out_tap_stride = (long long)Co * Cin; }
@@ -244,7 +255,7 @@ struct UnetEngine {
 
     GnSaved gn_fwd(std::vector<Op>& L, const std::string& name, const Src& in, const std::string& pname, const T4& out, int silu, float drop_p) {
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
-        GnSaved sv; sv.in = in; sv.silu = silu; sv.drop_p = train ? drop_p : 0.f; sv.layer = ++layer_counter;
+        GnSaved sv; sv.in = in; sv.silu = silu; sv.drop_p = drop_p; sv.layer = ++layer_counter;   // dropout is armed per call by a non-zero seed
         sv.gamma = PP(pname + ".weight"); sv.beta = PP(pname + ".bias"); sv.dgamma = GP(pname + ".weight"); sv.dbeta = GP(pname + ".bias");
         double* stats = at<double>(zero_fwd((size_t)Bn * 64 * 8));
         sv.mr = at<float>(alloc((size_t)Bn * 64 * 4));
@@ -257,12 +268,12 @@ struct UnetEngine {
         push(L, name + ".stats", 0, [=](cudaStream_t st) {
             k_gn_stats<<<g1, thr, 0, st>>>(gs, stats, HW, ppb);
             k_gn_finalize<<<(Bn * 32 + 127) / 128, 128, 0, st>>>(stats, mr, Bn * 32, 1.0 / ((double)HW * (C / 32)), 1e-6f);
-            return (int)cudaGetLastError(); });
+            return (int)cudaGetLastError(); }, 2);
         GnApply a; a.s = gs; a.mr = mr; a.gamma = sv.gamma; a.beta = sv.beta; a.y = bp(out); a.HW = HW;
         a.total_oct = (long long)Bn * HW * (C / 8); a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer;
         const int n = grid_for(a.total_oct);
         UnetEngine* self = this;
-        push(L, name + ".apply", 0, [a, n, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed;
+        push(L, name + ".apply", 0, [a, n, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
             k_gn_apply<<<n, 256, 0, st>>>(aa); return (int)cudaGetLastError(); });
         return sv;
     }
@@ -285,10 +296,10 @@ struct UnetEngine {
         const int n = grid_for(a.total_oct);
         UnetEngine* self = this;
         push(bwd_ops, name + ".gn_bwd", 0, [a, g1, thr, shm, n, self](cudaStream_t st) {
-            GnBwd aa = a; aa.seed = self->drop_seed;
+            GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
             k_gn_bwd_reduce<<<g1, thr, shm, st>>>(aa);
             k_gn_bwd_apply<<<n, 256, 0, st>>>(aa);
-            return (int)cudaGetLastError(); });
+            return (int)cudaGetLastError(); }, 2);
     }
     void colsum_op(const std::string& name, const T4& dy, float* per_img, int ld, float* total, float* total2, int C_valid) {
         const int HW = dy.H * dy.W, C = dy.C, Bn = dy.B;
@@ -296,7 +307,8 @@ struct UnetEngine {
         int nblk = (592 + Bn - 1) / Bn; if (nblk > HW / 8) nblk = HW / 8; if (nblk < 1) nblk = 1;
         const int ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
         const dim3 g(nblk, Bn); const bf16* p = bp(dy);
-        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { k_colsum<<<g, thr, 0, st>>>(p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); });
+        const size_t shm = (size_t)C * 4;
+        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { k_colsum<<<g, thr, shm, st>>>(p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); });
     }
 
     // ------------------------------------------------------------------ packed weights
@@ -314,8 +326,8 @@ struct UnetEngine {
         if (co_pad) {   // dgrad pack rows are [Ci][taps*Cop]: the kernel indexes tap*Co + co, so pack with Co := Cop is wrong; use a strided variant
             push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) {
                 k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, 0, nullptr, 0, fl, Co, Ci, taps);
-                k_pack_conv_w_padded<<<n, 256, 0, st>>>(w, dg, ldd, fl, Co, Cop, Ci, taps);
-                return (int)cudaGetLastError(); });
+                if (dg) k_pack_conv_w_padded<<<n, 256, 0, st>>>(w, dg, ldd, fl, Co, Cop, Ci, taps);
+                return (int)cudaGetLastError(); }, 2);
         } else {
             push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) { k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, 0, dg, ldd, fl, Co, Ci, taps); return (int)cudaGetLastError(); });
         }
@@ -338,7 +350,12 @@ struct UnetEngine {
     int plan(int B_, int H_, int W_, bool train_, bool dry_);
     int build();
     int run_list(std::vector<Op>& L, cudaStream_t st) {
-        for (auto& o : L) { const int rc = o.run(st); if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc)); }
+        static const bool dbg = getenv("DDPM_DEBUG_SYNC") != nullptr;   // serialise + attribute faults to an op (never under graph capture)
+        for (auto& o : L) {
+            int rc = o.run(st);
+            if (!rc && dbg) rc = (int)cudaStreamSynchronize(st);
+            if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc));
+        }
         return 0;
     }
 };

@@ -160,10 +160,25 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     return out;
 }
 
-// Downsample (unet.py:163-167): SamePad2d(3,2) = zero-pad bottom/right by one, then 3x3 stride 2
+// Downsample (unet.py:163-167): SamePad2d(3,2) = zero-pad bottom/right by one, then 3x3 stride 2.
+// Tensor-core path: forward / wgrad read the input through tensor maps with elementStrides 2; the data gradient is four
+// output-parity sub-convolutions over dY (4+2+2+1 taps) whose epilogues scatter to the (2y+py, 2x+px) pixels.
 inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
     const int C = x.C, Bn = x.B, h = x.H, w = x.W;
-    const Packed pk = pack_conv(p, C, C, 3, 0, /*flip=*/false, true);
+    const bool tc = (C % 64 == 0) && tc_ok_geom(h / 2, w / 2);
+    Packed pk;
+    if (tc) {
+        pk.ld_f = 9LL * C; pk.fwd = at<bf16>(alloc((size_t)C * pk.ld_f * 2));
+        if (train) { pk.ld_d = 9LL * C; pk.dgr = at<bf16>(alloc((size_t)C * pk.ld_d * 2)); }
+        const float* wsrc = PP(p + ".weight"); bf16* f = pk.fwd; bf16* dg = pk.dgr; const long long ld = pk.ld_f;
+        const int n = grid_for((long long)C * C * 9);
+        push(pack_ops, "pack." + p, 0, [=](cudaStream_t st) {
+            k_pack_conv_w<<<n, 256, 0, st>>>(wsrc, f, ld, 0, nullptr, 0, 0, C, C, 9);
+            if (dg) k_pack_conv_w_s2dgrad<<<n, 256, 0, st>>>(wsrc, dg, ld, C, C);
+            return (int)cudaGetLastError(); }, 2);
+    } else {
+        pk = pack_conv(p, C, C, 3, 0, /*flip=*/false, true);
+    }
     T4 out = newT(Bn, h / 2, w / 2, C);
     { ConvSpec c; c.name = p; c.in = one(x); c.stride = 2; c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = h / 2; c.Wo = w / 2;
       conv_op(fwd_ops, c, &fwd_flops); }
@@ -172,8 +187,36 @@ inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
         const T4 dY = grad_of(out, nullptr);
         colsum_op(p + ".bias", dY, nullptr, 0, GP(p + ".bias"), nullptr, C);
         bool first = true; const T4 dx = grad_of(x, &first);
-        { ConvSpec c; c.name = p + ".dgrad"; c.in = one(dY); c.map = MAP_TRANSPOSED2; c.wp = pk.dgr; c.ldw = pk.ld_d; c.out = dx; c.Co = C; c.Ho = h; c.Wo = w; c.accumulate = !first;
-          conv_op(bwd_ops, c, &bwd_flops); }
+        if (tc) {
+            const double fl = 2.0 * dY.pix() * C * 9.0 * C;
+            bwd_flops += fl;
+            int q = 0;
+            for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px, ++q) {
+                ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+                d.mode = GEMM_KK; d.M = (int)dY.pix(); d.N = C; d.W = w / 2; d.H = h / 2; d.NB = Bn;
+                d.a_ptr[0] = bp(dY); d.a_C[0] = C; d.a_ld[0] = C;
+                d.nseg = 1; d.seg_map[0] = 0; d.seg_kchunks[0] = C / 64; d.seg_cbase[0] = 0; d.seg_custom[0] = 1; d.seg_cmul[0] = 1;
+                int nt = 0;
+                for (int ky = py ? 1 : 0; ky < 3; ky += 2) for (int kx = px ? 1 : 0; kx < 3; kx += 2) {
+                    d.seg_dy[0][nt] = (signed char)(-(ky / 2)); d.seg_dx[0][nt] = (signed char)(-(kx / 2)); ++nt;
+                    if (px) break;
+                }
+                // (the loops above enumerate ky in {0,2} or {1} and kx in {0,2} or {1}, kx fastest)
+                d.seg_taps[0] = nt;
+                d.b_ptr = pk.dgr; d.b_K = 9 * C; d.b_rows = C; d.b_batch = 1; d.b_ld = pk.ld_d;
+                d.b_k_base = (py == 0 ? (px == 0 ? 0 : 4) : (px == 0 ? 6 : 8)) * C;
+                d.out = bp(dx); d.ldo = C; d.alpha = 1.f; d.grid_z = 1; d.o_mul = 2; d.o_py = py; d.o_px = px;
+                if (!first) { d.residual = bp(dx); d.ldr = C; }
+                ++n_tc_gemms;
+                if (dry) { push(bwd_ops, p + ".dgrad", q ? 0 : fl, [](cudaStream_t) { return 0; }); continue; }
+                GemmLaunch g; const int rc = build_gemm(d, g);
+                if (rc) { plan_error = rc; return; }
+                push(bwd_ops, p + ".dgrad", q ? 0 : fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+            }
+        } else {
+            ConvSpec c; c.name = p + ".dgrad"; c.in = one(dY); c.map = MAP_TRANSPOSED2; c.wp = pk.dgr; c.ldw = pk.ld_d; c.out = dx; c.Co = C; c.Ho = h; c.Wo = w; c.accumulate = !first;
+            conv_op(bwd_ops, c, &bwd_flops);
+        }
         wgrad_op(p + ".wgrad", dY, one(x), 3, 2, MAP_NORMAL, GP(p + ".weight"), C);
     });
     return out;
@@ -215,7 +258,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     zero_fwd_off = alloc(dry ? 0 : zf_total); zero_bwd_off = alloc(dry ? 0 : zb_total);
     const int ch = cfg.hid_channels, L = cfg.levels, nrb = cfg.num_res_blocks, E = cfg.temb_dim, Cin = cfg.in_channels, Cout = cfg.out_channels;
     if (ch % 32) return fail(-30, "hid_channels must be a multiple of 32 (GroupNorm(32))");
-    if (Cin > 4) return fail(-30, "in_channels > 4 unsupported");
+    if (Cin > 4 || Cin < 1 || Cout > 4 || Cout < 1) return fail(-30, "in_channels / out_channels must be 1..4 (image channels)");
     if ((H >> (L - 1)) < 1 || (H % (1 << (L - 1))) || (W % (1 << (L - 1)))) return fail(-30, "resolution not divisible by 2^(levels-1)");
     UnetEngine* self = this;
 
@@ -223,11 +266,11 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     const size_t img_elems = (size_t)B * Cin * H * W;
     xt_off = alloc(img_elems * 4); eps_off = alloc((size_t)B * Cout * H * W * 4);
     tbuf_off = alloc((size_t)B * 8); coefcur_off = alloc(64); counter_off = alloc(64);
-    T4 deps = newT(B, H, W, 8); deps_off = (size_t)deps.off;
+    deps_off = alloc((size_t)B * Cout * H * W * 4);
 
     // ---- zero the per-forward accumulators
     { uint8_t* z = ws + zero_fwd_off; const size_t n = zero_fwd_bytes;
-      push(fwd_ops, "zero.fwd", 0, [z, n](cudaStream_t st) { return n ? (int)cudaMemsetAsync(z, 0, n, st) : 0; }); }
+      push(fwd_ops, "zero.fwd", 0, [z, n](cudaStream_t st) { return n ? (int)cudaMemsetAsync(z, 0, n, st) : 0; }, 0); }
 
     // ---- timestep embedding MLP (functions.py:10-26, unet.py:122-126) + all per-block projections (unet.py:77,86)
     int nblocks = L * nrb + 2 + L * (nrb + 1);
@@ -283,7 +326,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         tape.push_back([=]() {
             const SgemmParams* tw = at<SgemmParams>(tpw_table_off); const SgemmParams* td = at<SgemmParams>(tpd_table_off);
             const dim3 gw((maxc + 63) / 64, (E + 63) / 64, nblocks), gd((E + 63) / 64, (B + 63) / 64, nblocks);
-            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { k_sgemm_table<<<gw, 256, 0, st>>>(tw); k_sgemm_table<<<gd, 256, 0, st>>>(td); return (int)cudaGetLastError(); });
+            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { k_sgemm_table<<<gw, 256, 0, st>>>(tw); k_sgemm_table<<<gd, 256, 0, st>>>(td); return (int)cudaGetLastError(); }, 2);
             float* d_e1 = at<float>(alloc((size_t)B * E * 4)); float* d_s0 = at<float>(alloc((size_t)B * E * 4)); float* d_e0 = at<float>(alloc((size_t)B * E * 4));
             const long long nE = (long long)B * E; const int Bn = B;
             float* gw2 = GP("embed.2.weight"); float* gb2 = GP("embed.2.bias"); float* gw0 = GP("embed.0.weight"); float* gb0 = GP("embed.0.bias");
@@ -302,7 +345,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 c.A = emb; c.B = d_e0; c.C = gw0; c.M = ch; c.N = E; c.K = Bn; c.sa_m = 1; c.sa_k = ch; c.sb_k = E; c.sb_n = 1; c.sc_m = 1; c.sc_n = ch; c.alpha = 1.f;
                 k_sgemm<float, float, float><<<dim3((E + 63) / 64, (ch + 63) / 64, 1), 256, 0, st>>>(c);
                 k_colsum_f32<<<(E + 127) / 128, 128, 0, st>>>(d_e0, gb0, Bn, E, E);
-                return (int)cudaGetLastError(); });
+                return (int)cudaGetLastError(); }, 7);
         });
     }
 
@@ -313,15 +356,28 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         const size_t shm = (size_t)(ch * Cin * 9 + ch) * 4; const int n = grid_for((long long)B * H * W * (ch / 8));
         const int Bn = B, Hn = H, Wn = W;
         push(fwd_ops, "in_conv", 2.0 * B * H * W * ch * Cin * 9, [=](cudaStream_t st) {
-            k_in_conv<<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Cin, Hn, Wn, ch); return (int)cudaGetLastError(); });
+            switch (Cin) {
+                case 1: k_in_conv<1><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 2: k_in_conv<2><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 3: k_in_conv<3><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                default: k_in_conv<4><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+            }
+            return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
         if (train) tape.push_back([=]() {
             const T4 dY = grad_of(h0, nullptr);
             float* gw = GP("in_conv.weight"); float* gb = GP("in_conv.bias"); const bf16* d = bp(dY);
             const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
             bwd_flops += 2.0 * P * ch * Cin * 9;
+            const long long s_c = (long long)Cin * 9;
             push(bwd_ops, "in_conv.wgrad", 2.0 * P * ch * Cin * 9, [=](cudaStream_t st) {
-                k_in_conv_wgrad<<<nb, 256, 0, st>>>(d, self->x_in, gw, gb, Bn, Cin, Hn, Wn, ch, ppb); return (int)cudaGetLastError(); });
+                switch (Cin) {
+                    case 1: k_corr3x3<1><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    case 2: k_corr3x3<2><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    case 3: k_corr3x3<3><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    default: k_corr3x3<4><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                }
+                return (int)cudaGetLastError(); });
         });
     }
 
@@ -351,24 +407,51 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         if (i != 0) h = up_conv(p + "." + std::to_string(nrb + 1) + ".1", h);
     }
     if (blk != nblocks) return fail(-31, "internal: block count mismatch %d vs %d", blk, nblocks);
-    // ---- out_conv (unet.py:138-142,232): GN -> SiLU -> conv3x3 -> NCHW fp32
+    // ---- out_conv (unet.py:138-142,232): GN -> SiLU -> conv3x3 (C -> Cout<=4) -> NCHW fp32
     {
+        if (ch > 256) return fail(-30, "hid_channels > 256 unsupported by the narrow out_conv kernels");
         T4 a_out = newT(B, H, W, ch);
         const GnSaved g = gn_fwd(fwd_ops, "out_conv.0", one(h), "out_conv.0", a_out, 1, 0.f);
-        const Packed wo = pack_conv("out_conv.2", Cout, ch, 3, 0, true, true, 8);
-        ConvSpec c; c.name = "out_conv.2"; c.in = one(a_out); c.wp = wo.fwd; c.ldw = wo.ld_f; c.bias = PP("out_conv.2.bias");
-        c.out_nchw = reinterpret_cast<float*>(1); c.Co = Cout; c.Ho = H; c.Wo = W;
-        conv_op(fwd_ops, c, &fwd_flops);
+        const float* wo = PP("out_conv.2.weight"); const float* bo = PP("out_conv.2.bias"); const bf16* ap = bp(a_out);
+        const int Bn = B, Hn = H, Wn = W;
+        const size_t shm = (size_t)9 * Cout * ch * 4;
+        const int nblk = grid_for((long long)B * H * W * 4);
+        const double fl = 2.0 * B * H * W * ch * Cout * 9;
+        fwd_flops += fl;
+        push(fwd_ops, "out_conv.2", fl, [=](cudaStream_t st) {
+            switch (Cout) {
+                case 1: k_out_conv<1><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                case 2: k_out_conv<2><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                case 3: k_out_conv<3><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                default: k_out_conv<4><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+            }
+            return (int)cudaGetLastError(); });
         if (train) {
-            const T4 hl = h;
+            // data gradient = a 3x3 "in_conv" Cout -> ch over d_eps with flipped / transposed fp32 weights
+            float* wt = at<float>(alloc((size_t)ch * Cout * 9 * 4));
+            push(pack_ops, "pack.out_conv.2.T", 0, [=](cudaStream_t st) { k_flip_transpose_w<<<(Cout * ch * 9 + 255) / 256, 256, 0, st>>>(wo, wt, Cout, ch); return (int)cudaGetLastError(); });
             tape.push_back([=]() {
-                colsum_op("out_conv.2.bias", deps, nullptr, 0, GP("out_conv.2.bias"), nullptr, Cout);
+                float* gw = GP("out_conv.2.weight"); float* gb = GP("out_conv.2.bias");
                 T4 d_a = newT(B, H, W, ch);
-                { ConvSpec c2; c2.name = "out_conv.2.dgrad"; c2.in = one(deps); c2.wp = wo.dgr; c2.ldw = wo.ld_d; c2.out = d_a; c2.Co = ch; c2.Ho = H; c2.Wo = W;
-                  conv_op(bwd_ops, c2, &bwd_flops); }
-                wgrad_op("out_conv.2.wgrad", deps, one(a_out), 3, 1, MAP_NORMAL, GP("out_conv.2.weight"), Cout);
+                bf16* dap = bp(d_a);
+                const size_t shm2 = (size_t)(ch * Cout * 9 + ch) * 4; const int n2 = grid_for((long long)Bn * Hn * Wn * (ch / 8));
+                const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
+                bwd_flops += 2.0 * fl;
+                push(bwd_ops, "out_conv.2.bwd", 2.0 * fl, [=](cudaStream_t st) {
+                    const float* de = self->deps_src;
+                    k_chansum_nchw<<<dim3(64, Cout), 256, 0, st>>>(de, gb, Bn, Cout, Hn * Wn);
+                    switch (Cout) {
+                        case 1: k_in_conv<1><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                k_corr3x3<1><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        case 2: k_in_conv<2><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                k_corr3x3<2><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        case 3: k_in_conv<3><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                k_corr3x3<3><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        default: k_in_conv<4><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                k_corr3x3<4><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                    }
+                    return (int)cudaGetLastError(); }, 3);
                 gn_bwd("out_conv.0", g, d_a, nullptr);
-                (void)hl;
             });
         }
     }
@@ -377,7 +460,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         uint8_t* z = ws + zero_bwd_off; const size_t n = zero_bwd_bytes; float* Gp = G; const size_t gbytes = (size_t)flat_elems * 4;
         push(bwd_ops, "zero.bwd", 0, [=](cudaStream_t st) {
             if (n) { const cudaError_t e = cudaMemsetAsync(z, 0, n, st); if (e) return (int)e; }
-            return (int)cudaMemsetAsync(Gp, 0, gbytes, st); });
+            return (int)cudaMemsetAsync(Gp, 0, gbytes, st); }, 0);
         for (int i = (int)tape.size() - 1; i >= 0; --i) tape[i]();
         tape.clear();
     }

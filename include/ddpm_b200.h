@@ -50,6 +50,12 @@ typedef struct ddpm_gemm_desc {
     void* out; int ldo; long long out_z_stride, out_tap_stride; int flags;   /* flags: 1 = fp32 out, 2 = atomic add (fp32) */
     const float* bias; const float* rowvec; int rowvec_ld, rows_per_vec;
     const void* residual; int ldr; float alpha;
+    /* stride-2 support: a_estride/b_estride = 2 builds the A (KK) / B (MNMN) map over a (W*2, H*2) tensor sampled with
+     * elementStrides 2; seg_cmul multiplies the tile origin; seg_dx/seg_dy override the default 3x3 offsets when seg_custom != 0;
+     * o_mul/o_py/o_px scatter output rows to pixel (y*o_mul+o_py, x*o_mul+o_px) of an (W*o_mul, H*o_mul) grid. */
+    int a_estride, b_estride, b_pad;
+    int seg_custom[3], seg_cmul[3]; signed char seg_dx[3][9], seg_dy[3][9];
+    int o_mul, o_py, o_px;
 } ddpm_gemm_desc;
 int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream);
 
@@ -102,6 +108,8 @@ int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, voi
 int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd_ops, int* n_bwd_ops, int* n_tensorcore_ops, int* n_generic_ops,
                          double* fwd_flops, double* bwd_flops);
 int ddpm_unet_launches_per_forward(const ddpm_unet* h);
+/* kernel launches issued by one forward / backward / repack of the compiled plan (memsets not counted) */
+int ddpm_unet_launch_counts(const ddpm_unet* h, int* fwd, int* bwd, int* pack);
 
 #ifdef __cplusplus
 }

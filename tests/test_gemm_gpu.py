@@ -159,3 +159,98 @@ def test_kmn_pv(Cc):
     _run(d)
     ref = torch.einsum("bij,bjc->bic", P.float(), qkv[..., 2 * Cc:].float())
     assert rel(out.float(), ref) < 4e-3
+
+
+# ---------------------------------------------------------------------------- stride-2 convolution (Downsample, unet.py:163-167)
+def _s2_ref(x_nhwc, w, dy_nhwc=None):
+    """reference: SamePad2d(3,2) = pad bottom/right by one, then 3x3 stride 2 (fp32, TF32 off)."""
+    torch.backends.cudnn.allow_tf32 = False
+    x = x_nhwc.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wf = w.to(torch.bfloat16).float().clone().requires_grad_(True)
+    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), wf, stride=2)
+    if dy_nhwc is None:
+        return y
+    y.backward(dy_nhwc.float().permute(0, 3, 1, 2))
+    return y, x.grad, wf.grad
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 16, 16), (4, 8, 8), (8, 4, 4), (1, 64, 64)])
+@pytest.mark.parametrize("Co", [128, 256])
+def test_kk_conv3x3_stride2(B, h, w, Co):
+    C = 128
+    x = bf(B, 2 * h, 2 * w, C, seed=1)
+    wt = torch.randn(Co, C, 3, 3, device="cuda") * 0.05
+    out = torch.full((B, h, w, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wp = pack_w(wt)
+    d = new_desc()
+    d.mode = 0; d.M = B * h * w; d.N = Co; d.W = w; d.H = h; d.NB = B
+    d.a_ptr[0] = x.data_ptr(); d.a_C[0] = C; d.a_ld[0] = C; d.a_estride = 2
+    d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = C // 64; d.seg_cbase[0] = 0
+    d.seg_custom[0] = 1; d.seg_cmul[0] = 2
+    for t in range(9):
+        d.seg_dx[0][t] = t % 3; d.seg_dy[0][t] = t // 3
+    d.b_ptr = wp.data_ptr(); d.b_K = 9 * C; d.b_rows = Co; d.b_batch = 1; d.b_ld = 9 * C
+    d.out = out.data_ptr(); d.ldo = Co
+    _run(d)
+    ref = _s2_ref(x, wt).detach()
+    assert rel(out.float().permute(0, 3, 1, 2), ref) < 4e-3
+
+
+def pack_s2_dgrad(w):
+    """OIHW -> [Ci][9*Co] bf16, four output-parity blocks {(0,0):4 taps,(0,1):2,(1,0):2,(1,1):1}; within a block the taps are
+    ordered (ky asc, kx asc) and each tap holds Co columns.  Returns (matrix, [(k_base, [(dy,dx),...]) per parity])."""
+    Co, Ci = w.shape[:2]
+    cols, meta, base = [], [], 0
+    for py in (0, 1):
+        for px in (0, 1):
+            kys = (0, 2) if py == 0 else (1,)
+            kxs = (0, 2) if px == 0 else (1,)
+            offs = []
+            for ky in kys:
+                for kx in kxs:
+                    cols.append(w[:, :, ky, kx].t())           # [Ci][Co]
+                    offs.append((-(ky // 2), -(kx // 2)))
+            meta.append((base, offs, py, px))
+            base += len(offs) * Co
+    return torch.cat(cols, dim=1).contiguous().to(torch.bfloat16), meta
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 16, 16), (4, 8, 8), (8, 4, 4)])
+def test_kk_s2_dgrad_parity(B, h, w):
+    Co, Ci = 128, 128
+    dy = bf(B, h, w, Co, seed=1, scale=0.5)
+    wt = torch.randn(Co, Ci, 3, 3, device="cuda") * 0.05
+    x = bf(B, 2 * h, 2 * w, Ci, seed=2)
+    out = torch.full((B, 2 * h, 2 * w, Ci), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wd, meta = pack_s2_dgrad(wt)
+    for k_base, offs, py, px in meta:
+        d = new_desc()
+        d.mode = 0; d.M = B * h * w; d.N = Ci; d.W = w; d.H = h; d.NB = B
+        d.a_ptr[0] = dy.data_ptr(); d.a_C[0] = Co; d.a_ld[0] = Co
+        d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = len(offs); d.seg_kchunks[0] = Co // 64; d.seg_cbase[0] = 0
+        d.seg_custom[0] = 1; d.seg_cmul[0] = 1
+        for t, (oy, ox) in enumerate(offs):
+            d.seg_dy[0][t] = oy; d.seg_dx[0][t] = ox
+        d.b_ptr = wd.data_ptr(); d.b_K = 9 * Co; d.b_rows = Ci; d.b_batch = 1; d.b_ld = 9 * Co; d.b_k_base = k_base
+        d.out = out.data_ptr(); d.ldo = Ci; d.o_mul = 2; d.o_py = py; d.o_px = px
+        _run(d)
+    _, dx_ref, _ = _s2_ref(x, wt, dy)
+    assert rel(out.float().permute(0, 3, 1, 2), dx_ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,h,w,splits", [(2, 16, 16, 2), (4, 8, 8, 1), (16, 4, 4, 2)])
+def test_mnmn_s2_wgrad(B, h, w, splits):
+    Co, Ci = 128, 128
+    dy = bf(B, h, w, Co, seed=1, scale=0.1)
+    x = bf(B, 2 * h, 2 * w, Ci, seed=2)
+    wt = torch.zeros(Co, Ci, 3, 3, device="cuda")
+    out = torch.zeros(9, Co, Ci, device="cuda")
+    d = new_desc()
+    d.mode = 1; d.M = Co; d.N = Ci; d.W = w; d.H = h; d.NB = B
+    d.a_ptr[0] = dy.data_ptr(); d.a_C[0] = Co; d.a_ld[0] = Co
+    d.b_ptr = x.data_ptr(); d.b_K = Ci; d.b_ld = Ci; d.b_estride = 2; d.b_pad = 0
+    d.taps = 9; d.splits = splits; d.kblocks = (B * h * w + 63) // 64; d.grid_z = 9 * splits
+    d.out = out.data_ptr(); d.ldo = Ci; d.out_tap_stride = Co * Ci; d.flags = 3
+    _run(d)
+    _, _, dw_ref = _s2_ref(x, wt, dy)
+    assert rel(out, dw_ref.permute(2, 3, 0, 1).reshape(9, Co, Ci)) < 2e-5
