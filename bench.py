@@ -243,7 +243,7 @@ def main():
                                         losses.data_ptr(), 1000 + i, sp))
         _lib.check(L.ddpm_train_backward(h, gscale.data_ptr(), sp))
         if world > 1:
-            dist.all_reduce(model.flat_grads, op=dist.ReduceOp.AVG)
+            D.parallel.allreduce_mean_(model.flat_grads)
 
     def barrier():
         if world > 1:
@@ -287,7 +287,7 @@ def main():
         loss = diff.train_losses(model, x, t, nz).mean()
         loss.backward()
         if world > 1:
-            dist.all_reduce(model.flat_grads, op=dist.ReduceOp.AVG)
+            D.parallel.allreduce_mean_(model.flat_grads)
         return loss.item()
 
     for i in range(args.warmup):

@@ -6,5 +6,6 @@ from . import _lib  # noqa: F401
 from .unet import UNet
 from .diffusion import GaussianDiffusion, get_beta_schedule
 from .ddim import DDIM, get_selection_schedule
+from . import parallel
 
 __all__ = ["UNet", "GaussianDiffusion", "get_beta_schedule", "DDIM", "get_selection_schedule"]
