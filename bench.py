@@ -28,6 +28,9 @@ CIFAR = dict(in_channels=3, hid_channels=128, out_channels=3, ch_multipliers=(1,
              apply_attn=(False, True, False, False), drop_rate=0.1)
 FWD_GFLOP_PER_IMG = 12.444          # 2*MAC of convs + linears + attention matmuls
 TRAIN_GFLOP_PER_IMG = 3 * FWD_GFLOP_PER_IMG
+# torch CPU threads for the reference arm: measured on the 128-core GPU-box host (tools/cpu_threads.py, bs=32 fwd+bwd):
+# 8 -> 25, 16 -> 43.5, 32 -> 35, 64 -> 18, 128 -> 0.1 images/s; 16 is the fastest, so "all the threads it can use" = 16.
+CPU_THREADS = min(16, os.cpu_count() or 1)
 
 
 def peaks():
@@ -96,8 +99,8 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ddpm_ref as R
-    torch.set_num_threads(os.cpu_count())
-    bs = 8
+    torch.set_num_threads(CPU_THREADS)
+    bs = 32
     cfg = dict(R.CIFAR10_CFG); cfg["drop_rate"] = 0.0
     sd = {k: v.requires_grad_(True) for k, v in R.make_state_dict(cfg, 1234).items()}
     diff = R.RefDiffusion(R.get_beta_schedule("linear", 1e-4, 0.02, 1000), "fixed-large")
@@ -119,8 +122,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "unet_train_step_images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CIFAR-10 UNet (configs/cifar10.json) q_sample+fwd+MSE+bwd, fp32 CPU, bounded sample bs=8 per step"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "config": {"workload": f"CIFAR-10 UNet (configs/cifar10.json) q_sample+fwd+MSE+bwd, fp32 CPU, bounded sample bs={bs} per step"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": CPU_THREADS, "kind": "port",
                              "sample": f"{args.steps} steps of bs={bs} (of the bs=128 workload), fp32, torch CPU, {torch.get_num_threads()} threads"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -128,8 +131,8 @@ def run_reference(args):
 
 def cpu_baseline_sample(budget_s=20.0):
     from oracle import ddpm_ref as R
-    torch.set_num_threads(os.cpu_count())
-    bs = 8
+    torch.set_num_threads(CPU_THREADS)
+    bs = 32
     cfg = dict(R.CIFAR10_CFG); cfg["drop_rate"] = 0.0
     sd = {k: v.requires_grad_(True) for k, v in R.make_state_dict(cfg, 1234).items()}
     diff = R.RefDiffusion(R.get_beta_schedule("linear", 1e-4, 0.02, 1000), "fixed-large")
@@ -145,7 +148,7 @@ def cpu_baseline_sample(budget_s=20.0):
     while time.perf_counter() - t0 < budget_s and n < 40:
         step(); n += 1
     dt = (time.perf_counter() - t0) / max(n, 1)
-    return {"value": bs / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": bs / dt, "unit": "images/s", "cores": CPU_THREADS, "kind": "port",
             "sample": f"{n} steps of bs={bs} fwd+bwd (oracle port of the reference path, fp32, torch CPU, {torch.get_num_threads()} threads)"}
 
 

@@ -33,7 +33,8 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     const int gz = d.grid_z > 0 ? d.grid_z : 1;
     const int n_tiles = (d.N + g.block_n - 1) / g.block_n;
     const int m_tiles = (d.M + 127) / 128;
-    g.grid = dim3(m_tiles, n_tiles, gz);
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.grid_z = gz;
+    g.grid = dim3(m_tiles * n_tiles * gz, 1, 1);   // clipped to the SM count at launch (persistent CTAs)
     int rc;
     if (d.mode == GEMM_KK) {
         if (!pick_box(d.W, d.H, 128, p.w_t, p.h_t, p.n_t)) return fail(-11, "KK: unsupported geometry W=%d H=%d", d.W, d.H);

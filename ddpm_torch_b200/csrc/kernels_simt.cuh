@@ -17,6 +17,12 @@ __device__ __forceinline__ float silu_grad_f(float y) {
     const float s = 1.f / (1.f + __expf(-y));
     return s * (1.f + y * (1.f - s));
 }
+// one-MUFU sigmoid for the bandwidth-bound GroupNorm passes (abs error ~5e-4, below bf16 resolution of the outputs)
+__device__ __forceinline__ float sigmoid_fast(float y) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+    return fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -48,14 +54,16 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
     }
     return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask for 8 consecutive elements starting at element index e (multiple of 8)
+// keep-mask for 8 consecutive elements starting at element index e (multiple of 8): ONE Philox call, 16 random bits per
+// element (drop probability quantised to 1/65536)
 __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t layer, unsigned long long e, float p) {
-    const uint32_t thr = (uint32_t)(p * 4294967296.0);
-    const uint4 r0 = philox4x32((uint32_t)(e >> 2), (uint32_t)(e >> 34), (uint32_t)seed ^ (layer * 0x9E3779B1u), (uint32_t)(seed >> 32));
-    const uint4 r1 = philox4x32((uint32_t)((e >> 2) + 1), (uint32_t)(e >> 34), (uint32_t)seed ^ (layer * 0x9E3779B1u), (uint32_t)(seed >> 32));
+    const uint32_t thr = (uint32_t)(p * 65536.f);
+    const uint4 r = philox4x32((uint32_t)(e >> 3), (uint32_t)(e >> 35), (uint32_t)seed ^ (layer * 0x9E3779B1u), (uint32_t)(seed >> 32));
     uint32_t m = 0;
-    m |= (r0.x >= thr) << 0; m |= (r0.y >= thr) << 1; m |= (r0.z >= thr) << 2; m |= (r0.w >= thr) << 3;
-    m |= (r1.x >= thr) << 4; m |= (r1.y >= thr) << 5; m |= (r1.z >= thr) << 6; m |= (r1.w >= thr) << 7;
+    m |= ((r.x & 0xffffu) >= thr) << 0; m |= ((r.x >> 16) >= thr) << 1;
+    m |= ((r.y & 0xffffu) >= thr) << 2; m |= ((r.y >> 16) >= thr) << 3;
+    m |= ((r.z & 0xffffu) >= thr) << 4; m |= ((r.z >> 16) >= thr) << 5;
+    m |= ((r.w & 0xffffu) >= thr) << 6; m |= ((r.w >> 16) >= thr) << 7;
     return m;
 }
 
@@ -185,13 +193,19 @@ __global__ void __launch_bounds__(256) k_gn_stats(GnSrc s, double* __restrict__ 
     const int c = o * 8;
     const bool first = c < s.C0;
     float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int pp = p0 + lp; pp < p1; pp += pstep) {
-        const long long pix = (long long)b * HW + pp;
-        const bf16* src = first ? s.x0 + pix * s.C0 + c : s.x1 + pix * s.C1 + (c - s.C0);
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), f);
+    const bf16* src = first ? s.x0 + (long long)b * HW * s.C0 + c : s.x1 + (long long)b * HW * s.C1 + (c - s.C0);
+    const int sstride = first ? s.C0 : s.C1;
+    for (int pp = p0 + lp; pp < p1; pp += 4 * pstep) {
+        uint4 u[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] += f[e] * f[e]; }
+        for (int k = 0; k < 4; ++k) { const int q = pp + k * pstep; u[k] = q < p1 ? __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)) : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float f[8];
+            unpack8(u[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] += f[e] * f[e]; }
+        }
     }
     {   // flush: merge elements that share a group before touching shared memory
         int gcur = c / cg; float a1 = 0.f, a2 = 0.f;
@@ -207,143 +221,221 @@ __global__ void __launch_bounds__(256) k_gn_stats(GnSrc s, double* __restrict__ 
     for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&stats[(long long)b * 64 + i], (double)sh[i]);
 }
 
-// finalize: {sum,sumsq} -> {mean, rstd} (fp32) ; n = HW * C/32
-__global__ void k_gn_finalize(const double* __restrict__ stats, float* __restrict__ mr, int count, double inv_n, float eps) {
+// ---- GroupNorm v4: per-(image, channel) constants are materialised once by tiny "finalize" kernels, so the bandwidth-bound
+// passes start with a handful of independent 16-byte loads (no shared memory, no dependent load chains, few registers).
+// K[b][0..3][C] = { sc = rstd*gamma, sh = beta - mean*sc, r = rstd, mr = mean*rstd }   ->  y = x*sc + sh ; xh = x*r - mr
+__global__ void k_gn_finalize(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ K, int B, int C, double inv_n, float eps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const double m = stats[2 * i] * inv_n;
-    double var = stats[2 * i + 1] * inv_n - m * m;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C, g = c / (C >> 5);
+    const double m = stats[(b * 32 + g) * 2] * inv_n;
+    double var = stats[(b * 32 + g) * 2 + 1] * inv_n - m * m;
     if (var < 0) var = 0;
-    mr[2 * i] = (float)m;
-    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    const float r = (float)(1.0 / sqrt(var + (double)eps)), mf = (float)m;
+    const float sc = r * gamma[c];
+    float* Kb = K + (long long)b * 4 * C;
+    Kb[c] = sc; Kb[C + c] = beta[c] - mf * sc; Kb[2 * C + c] = r; Kb[3 * C + c] = mf * r;
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// y = act(gn(x)) [* dropout] -> bf16 NHWC [B,HW,C]
+// y = act(gn(x)) [* dropout] -> bf16 NHWC [B,HW,C] ; grid (pixel blocks, B), blockDim.x = (256/oct)*oct
 struct GnApply {
-    GnSrc s; const float* mr; const float* gamma; const float* beta; bf16* y;
-    int HW; long long total_oct; int silu; float drop_p; unsigned long long seed; uint32_t layer;
+    GnSrc s; const float* K; bf16* y;
+    int HW; int silu; float drop_p; unsigned long long seed; uint32_t layer;
 };
-__global__ void __launch_bounds__(256) k_gn_apply(const GnApply a) {
-    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
-    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total_oct; i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / oct;
-        const int c = (int)(i % oct) * 8;
-        const int b = (int)(pix / a.HW);
-        const bf16* src = c < a.s.C0 ? a.s.x0 + pix * a.s.C0 + c : a.s.x1 + pix * a.s.C1 + (c - a.s.C0);
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), f);
-        uint32_t keep = 0xffu;
-        if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)i * 8, a.drop_p);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int g = (c + e) / cg;
-            const float m = a.mr[(b * 32 + g) * 2], r = a.mr[(b * 32 + g) * 2 + 1];
-            float y = (f[e] - m) * r * __ldg(a.gamma + c + e) + __ldg(a.beta + c + e);
-            if (a.silu) y = silu_f(y);
-            f[e] = ((keep >> e) & 1u) ? y * keep_scale : 0.f;
-        }
-        *reinterpret_cast<uint4*>(a.y + pix * C + c) = pack8(f);
-    }
-}
-
-// backward of y = act(gn(x))*mask:  phase 1 reduces, phase 2 applies.
-// red[b][g][2] (fp64): S1 = sum dyh, S2 = sum dyh*xh   where dyh = dy*act'(yn)*mask*gamma ;  dgamma[c] += dy_n*xh ; dbeta[c] += dy_n
-struct GnBwd {
-    GnSrc s; const bf16* dy; const float* mr; const float* gamma; const float* beta;
-    double* red; float* dgamma; float* dbeta;
-    bf16* dx0; bf16* dx1; int acc0, acc1;                         // destinations for the two sources (accumulate flags)
-    const bf16* addend;                                           // optional [B,HW,C] term added to dx (skip-path gradient)
-    int HW; int pix_per_block; int silu; float drop_p; unsigned long long seed; uint32_t layer; long long total_oct;
-};
-__global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwd a) {   // blockDim.x = (256/oct)*oct, see k_gn_stats
-    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
+__global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_per_block) {
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3;
     const int b = blockIdx.y;
-    const int p0 = blockIdx.x * a.pix_per_block;
-    int p1 = p0 + a.pix_per_block; if (p1 > a.HW) p1 = a.HW;
-    extern __shared__ float sh[];                 // [32][2] S1,S2 ; then [C] dgamma ; [C] dbeta
-    float* sg = sh + 64; float* sb = sg + C;
-    for (int i = threadIdx.x; i < 64 + 2 * C; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
-    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const int p0 = blockIdx.x * pix_per_block;
+    int p1 = p0 + pix_per_block; if (p1 > a.HW) p1 = a.HW;
     const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
     const int c = o * 8;
     const bool first = c < a.s.C0;
-    float ga[8], be[8], m[8], r[8];
+    float sc[8], sh[8];
+    ld8(a.K + (long long)b * 4 * C + c, sc); ld8(a.K + (long long)b * 4 * C + C + c, sh);
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
+    const int sstride = first ? a.s.C0 : a.s.C1;
+    bf16* dst = a.y + (long long)b * a.HW * C + c;
+    for (int pp = p0 + lp; pp < p1; pp += 4 * pstep) {
+        uint4 u[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int g = (c + e) / cg;
-        ga[e] = __ldg(a.gamma + c + e); be[e] = __ldg(a.beta + c + e);
-        m[e] = a.mr[(b * 32 + g) * 2]; r[e] = a.mr[(b * 32 + g) * 2 + 1];
-    }
-    float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int pp = p0 + lp; pp < p1; pp += pstep) {
-        const long long pix = (long long)b * a.HW + pp;
-        const bf16* src = first ? a.s.x0 + pix * a.s.C0 + c : a.s.x1 + pix * a.s.C1 + (c - a.s.C0);
-        float x[8], d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), x);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.dy + pix * C + c)), d);
-        uint32_t keep = 0xffu;
-        if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(pix * oct + o) * 8, a.drop_p);
+        for (int k = 0; k < 4; ++k) { const int q = pp + k * pstep; if (q < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)); }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float xh = (x[e] - m[e]) * r[e];
-            float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
-            if (a.silu) dn *= silu_grad_f(xh * ga[e] + be[e]);
-            dg[e] += dn * xh; db[e] += dn;
-            const float dh = dn * ga[e];
-            s1[e] += dh; s2[e] += dh * xh;
+        for (int k = 0; k < 4; ++k) {
+            const int q = pp + k * pstep;
+            if (q >= p1) break;
+            float f[8];
+            unpack8(u[k], f);
+            uint32_t keep = 0xffu;
+            if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float y = fmaf(f[e], sc[e], sh[e]);
+                if (a.silu) y *= sigmoid_fast(y);
+                f[e] = ((keep >> e) & 1u) ? y * keep_scale : 0.f;
+            }
+            *reinterpret_cast<uint4*>(dst + (long long)q * C) = pack8(f);
         }
     }
-    {
-        int gcur = c / cg; float a1 = 0.f, a2 = 0.f;
+}
+
+// ---- backward of y = act(gn(x))*mask.  With dn = dy * mask * act'(y):
+//   pass 1 (reduce):  cs[b][c] = { sum_p dn , sum_p dn*xh }                      (per image, per channel; fp32 atomics)
+//   finalize:         S1[b,g] = sum_{c in g} gamma_c cs0 ; S2 = sum gamma_c cs1 ; dgamma_c += sum_b cs1 ; dbeta_c += sum_b cs0
+//                     PQ[b][0][c] = rstd^2*S2/n  (=: P) ;  PQ[b][1][c] = rstd*S1/n - P*mean   (=: Q)
+//   pass 2 (apply):   dx = sc*dn - P*x - Q  (+ addend) ,  sc = rstd*gamma
+struct GnBwd {
+    GnSrc s; const bf16* dy; const float* K; const float* gamma;
+    float* cs; float* PQ; float* dgamma; float* dbeta;
+    bf16* dx0; bf16* dx1; int acc0, acc1;                         // destinations for the two sources (accumulate flags)
+    const bf16* addend;                                           // optional [B,HW,C] term added to dx (skip-path gradient)
+    int B, HW; int pix_per_block; int silu; float drop_p; unsigned long long seed; uint32_t layer;
+};
+__global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {   // grid (pixel blocks, B), blockDim.x = (256/oct)*oct
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3;
+    extern __shared__ float sh2[];                // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh2[i] = 0.f;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * a.pix_per_block;
+    int p1 = p0 + a.pix_per_block; if (p1 > a.HW) p1 = a.HW;
+    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
+    const int c = o * 8;
+    const bool first = c < a.s.C0;
+    const float* Kb = a.K + (long long)b * 4 * C + c;
+    float sc[8], sh[8], r[8], mr_[8];
+    ld8(Kb, sc); ld8(Kb + C, sh); ld8(Kb + 2 * C, r); ld8(Kb + 3 * C, mr_);
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
+    const int sstride = first ? a.s.C0 : a.s.C1;
+    const bf16* dyp = a.dy + (long long)b * a.HW * C + c;
+    for (int pp = p0 + lp; pp < p1; pp += 2 * pstep) {
+        uint4 ux[2], ud[2];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            atomicAdd(&sg[c + e], dg[e]); atomicAdd(&sb[c + e], db[e]);
-            const int g = (c + e) / cg;
-            if (g != gcur) { atomicAdd(&sh[gcur * 2], a1); atomicAdd(&sh[gcur * 2 + 1], a2); a1 = a2 = 0.f; gcur = g; }
-            a1 += s1[e]; a2 += s2[e];
+        for (int k = 0; k < 2; ++k) {
+            const int q = pp + k * pstep;
+            if (q < p1) { ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)); ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C)); }
         }
-        atomicAdd(&sh[gcur * 2], a1); atomicAdd(&sh[gcur * 2 + 1], a2);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = pp + k * pstep;
+            if (q >= p1) break;
+            float x[8], d[8];
+            unpack8(ux[k], x); unpack8(ud[k], d);
+            uint32_t keep = 0xffu;
+            if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
+                if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
+                s0[e] += dn; s1[e] = fmaf(dn, fmaf(x[e], r[e], -mr_[e]), s1[e]);
+            }
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&a.red[(long long)b * 64 + i], (double)sh[i]);
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(&a.dgamma[i], sg[i]); atomicAdd(&a.dbeta[i], sb[i]); }
-}
-__global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwd a) {
-    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
-    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    const float inv_n = 1.f / ((float)a.HW * (float)cg);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total_oct; i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / oct;
-        const int c = (int)(i % oct) * 8;
-        const int b = (int)(pix / a.HW);
-        const bool first = c < a.s.C0;
-        const bf16* src = first ? a.s.x0 + pix * a.s.C0 + c : a.s.x1 + pix * a.s.C1 + (c - a.s.C0);
-        float x[8], d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(src)), x);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.dy + pix * C + c)), d);
-        uint32_t keep = 0xffu;
-        if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)i * 8, a.drop_p);
-        bf16* dst = first ? a.dx0 + pix * a.s.C0 + c : a.dx1 + pix * a.s.C1 + (c - a.s.C0);
-        const int acc = first ? a.acc0 : a.acc1;
-        float o[8], ad[8];
-        if (acc) unpack8(*reinterpret_cast<const uint4*>(dst), o);
-        if (a.addend) unpack8(__ldg(reinterpret_cast<const uint4*>(a.addend + pix * C + c)), ad);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int g = (c + e) / cg;
-            const float m = a.mr[(b * 32 + g) * 2], r = a.mr[(b * 32 + g) * 2 + 1];
-            const float ga = __ldg(a.gamma + c + e);
-            const float xh = (x[e] - m) * r;
-            float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
-            if (a.silu) dn *= silu_grad_f(xh * ga + __ldg(a.beta + c + e));
-            const float dh = dn * ga;
-            const float s1 = (float)a.red[(b * 32 + g) * 2] * inv_n, s2 = (float)a.red[(b * 32 + g) * 2 + 1] * inv_n;
-            const float v = r * (dh - s1 - xh * s2) + (a.addend ? ad[e] : 0.f);
-            o[e] = acc ? o[e] + v : v;
+    for (int e = 0; e < 8; ++e) { atomicAdd(&sh2[c + e], s0[e]); atomicAdd(&sh2[C + c + e], s1[e]); }
+    __syncthreads();
+    float* csb = a.cs + (long long)b * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(csb + i, sh2[i]);
+}
+// one block per image
+__global__ void __launch_bounds__(256) k_gn_bwd_finalize(const GnBwd a) {
+    const int C = a.s.C0 + a.s.C1, cg = C >> 5;
+    __shared__ float S[64];
+    const int b = blockIdx.x;
+    if (threadIdx.x < 64) S[threadIdx.x] = 0.f;
+    __syncthreads();
+    const float* csb = a.cs + (long long)b * 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float g = __ldg(a.gamma + c), c0 = csb[c], c1 = csb[C + c];
+        atomicAdd(&S[(c / cg) * 2], g * c0); atomicAdd(&S[(c / cg) * 2 + 1], g * c1);
+        atomicAdd(a.dbeta + c, c0); atomicAdd(a.dgamma + c, c1);
+    }
+    __syncthreads();
+    const float inv_n = 1.f / ((float)a.HW * (float)cg);
+    const float* Kb = a.K + (long long)b * 4 * C;
+    float* PQb = a.PQ + (long long)b * 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float r = Kb[2 * C + c], mr = Kb[3 * C + c];
+        const float k2 = r * S[(c / cg) * 2] * inv_n, k3 = r * S[(c / cg) * 2 + 1] * inv_n;   // dx = sc*dn - k2 - k3*xh
+        PQb[c] = k3 * r; PQb[C + c] = k2 - k3 * mr;
+    }
+}
+// grid (pixel blocks, B), blockDim.x = (256/oct)*oct.  Optionally accumulates per-image / total column sums of dx.
+__global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* cs_per_img, int cs_ld, float* cs_total, float* cs_total2) {
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3;
+    extern __shared__ float shc[];                // [C] column sums (only when requested)
+    const bool do_cs = cs_per_img || cs_total || cs_total2;
+    if (do_cs) { for (int i = threadIdx.x; i < C; i += blockDim.x) shc[i] = 0.f; }
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * a.pix_per_block;
+    int p1 = p0 + a.pix_per_block; if (p1 > a.HW) p1 = a.HW;
+    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
+    const int c = o * 8;
+    const bool first = c < a.s.C0;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const float* Kb = a.K + (long long)b * 4 * C + c;
+    const float* PQb = a.PQ + (long long)b * 2 * C + c;
+    float sc[8], sh[8], P[8], Q[8];
+    ld8(Kb, sc); ld8(Kb + C, sh); ld8(PQb, P); ld8(PQb + C, Q);
+    const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
+    const int sstride = first ? a.s.C0 : a.s.C1;
+    bf16* dst = first ? a.dx0 + (long long)b * a.HW * a.s.C0 + c : a.dx1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
+    const int acc = first ? a.acc0 : a.acc1;
+    const bf16* dyp = a.dy + (long long)b * a.HW * C + c;
+    const bf16* adp = a.addend ? a.addend + (long long)b * a.HW * C + c : nullptr;
+    float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pp = p0 + lp; pp < p1; pp += 2 * pstep) {
+        uint4 ux[2], ud[2], ua[2], uo[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = pp + k * pstep;
+            if (q < p1) {
+                ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride));
+                ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C));
+                if (adp) ua[k] = __ldg(reinterpret_cast<const uint4*>(adp + (long long)q * C));
+                if (acc) uo[k] = *reinterpret_cast<const uint4*>(dst + (long long)q * sstride);
+            }
         }
-        *reinterpret_cast<uint4*>(dst) = pack8(o);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = pp + k * pstep;
+            if (q >= p1) break;
+            float x[8], d[8], ov[8], ad[8];
+            unpack8(ux[k], x); unpack8(ud[k], d);
+            if (acc) unpack8(uo[k], ov);
+            if (adp) unpack8(ua[k], ad);
+            uint32_t keep = 0xffu;
+            if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
+                if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
+                float v = fmaf(sc[e], dn, -fmaf(P[e], x[e], Q[e]));
+                if (adp) v += ad[e];
+                if (acc) v += ov[e];
+                ov[e] = v; cs[e] += v;
+            }
+            *reinterpret_cast<uint4*>(dst + (long long)q * sstride) = pack8(ov);
+        }
+    }
+    if (do_cs) {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&shc[c + e], cs[e]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            const float v = shc[i];
+            if (cs_per_img) atomicAdd(cs_per_img + (long long)b * cs_ld + i, v);
+            if (cs_total) atomicAdd(cs_total + i, v);
+            if (cs_total2) atomicAdd(cs_total2 + i, v);
+        }
     }
 }
 

@@ -40,6 +40,7 @@ struct GemmParams {
     int b_cmul, b_pad;        // MNMN: B coordinate = origin*b_cmul + tap - b_pad (b_cmul = 2 for stride-2 convs, maps with elementStrides 2)
     // optional output-row remap (KK): tile row (n,y,x) on the A grid -> output pixel (n, y*o_mul+o_py, x*o_mul+o_px) on an oW x oH grid
     int o_mul, o_py, o_px, oW, oH;
+    int m_tiles, n_tiles, grid_z;   // tile space walked by the persistent CTAs
     // epilogue
     void* out; int ldo; long long out_z_stride; long long out_tap_stride; int flags;
     const float* bias;        // [N] or null
@@ -65,6 +66,10 @@ __device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& 
     x = r - y * W;
 }
 
+// Persistent kernel: gridDim.x CTAs walk the tile list t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   t -> (m_tile fastest, n_tile, z) so that CTAs running concurrently share the same weight (B) tile in L2.
+// TMEM holds TWO accumulator buffers (2 x BLOCK_N columns): the epilogue warps drain buffer i while the MMA warp already
+// accumulates tile i+1 into the other one; the TMA producer runs ahead across tile boundaries.
 template <int BLOCK_N, int MODE, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -73,41 +78,38 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     using SM = GemmSmem<BLOCK_N, STAGES>;
     constexpr int A_MN = (MODE == GEMM_MNMN) ? 1 : 0;
     constexpr int B_MN = (MODE == GEMM_KK) ? 0 : 1;
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y, z = blockIdx.z;
+    const int m_tiles = p.m_tiles, n_tiles = p.n_tiles;
+    const int total_tiles = m_tiles * n_tiles * p.grid_z;
 
-    // ---- number of K slabs (uniform over the CTA)
-    int num_slabs;
-    int tap = 0, split = 0, batch = z;
-    if (MODE == GEMM_KK) {
-        num_slabs = 0;
-        for (int s = 0; s < p.nseg; ++s) num_slabs += p.seg[s].taps * p.seg[s].kchunks;
-    } else if (MODE == GEMM_MNMN) {
-        split = z % p.splits;
-        tap = (z / p.splits) % p.taps;
-        batch = z / (p.splits * p.taps);
-        const int per = (p.kblocks + p.splits - 1) / p.splits;
-        const int kb0 = split * per;
-        int kb1 = kb0 + per; if (kb1 > p.kblocks) kb1 = p.kblocks;
-        num_slabs = kb1 > kb0 ? kb1 - kb0 : 0;
-    } else {
-        num_slabs = p.kblocks;
-    }
+    // K slabs of a tile (uniform across roles)
+    int kk_slabs = 0;
+    if (MODE == GEMM_KK) for (int s = 0; s < p.nseg; ++s) kk_slabs += p.seg[s].taps * p.seg[s].kchunks;
+    const int per_split = (MODE == GEMM_MNMN) ? (p.kblocks + p.splits - 1) / p.splits : 0;
+    auto slabs_of = [&](int z) -> int {
+        if (MODE == GEMM_KK) return kk_slabs;
+        if (MODE == GEMM_KMN) return p.kblocks;
+        const int split = z % p.splits;
+        const int kb0 = split * per_split;
+        int kb1 = kb0 + per_split; if (kb1 > p.kblocks) kb1 = p.kblocks;
+        return kb1 > kb0 ? kb1 - kb0 : 0;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -128,57 +130,62 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 mbar_expect_tx(&full_bar[st], SM::STAGE_BYTES);
                 return smem + st * SM::STAGE_BYTES;
             };
-            if (MODE == GEMM_KK) {
-                int n0, y0, x0;
-                pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
-                n0 += z * p.a_z_n;
-                int kcount = 0;
-                for (int s = 0; s < p.nseg && ok; ++s) {
-                    const GemmSeg sg = p.seg[s];
-                    const CUtensorMap* mA = sg.map == 0 ? &tmA0 : (sg.map == 1 ? &tmA1 : &tmA2);
-                    for (int t = 0; t < sg.taps && ok; ++t) {
-                        const int xc = x0 * sg.cmul + sg.dx[t];
-                        const int yc = y0 * sg.cmul + sg.dy[t];
-                        for (int kc = 0; kc < sg.kchunks; ++kc, ++slab, ++kcount) {
-                            uint8_t* st = acquire(slab);
-                            if (!st) break;
-                            uint64_t* fb = &full_bar[slab % STAGES];
-                            tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
-                            tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+            for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+                const int m_tile = t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
+                if (MODE == GEMM_KK) {
+                    int n0, y0, x0;
+                    pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
+                    n0 += z * p.a_z_n;
+                    int kcount = 0;
+                    for (int s = 0; s < p.nseg && ok; ++s) {
+                        const GemmSeg sg = p.seg[s];
+                        const CUtensorMap* mA = sg.map == 0 ? &tmA0 : (sg.map == 1 ? &tmA1 : &tmA2);
+                        for (int tp = 0; tp < sg.taps && ok; ++tp) {
+                            const int xc = x0 * sg.cmul + sg.dx[tp];
+                            const int yc = y0 * sg.cmul + sg.dy[tp];
+                            for (int kc = 0; kc < sg.kchunks; ++kc, ++slab, ++kcount) {
+                                uint8_t* st = acquire(slab);
+                                if (!st) break;
+                                uint64_t* fb = &full_bar[slab % STAGES];
+                                tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
+                                tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+                            }
                         }
                     }
-                }
-            } else if (MODE == GEMM_MNMN) {
-                const int per = (p.kblocks + p.splits - 1) / p.splits;
-                const int kb0 = split * per;
-                const int dx = p.taps == 9 ? (tap % 3) - p.b_pad : 0;
-                const int dy = p.taps == 9 ? (tap / 3) - p.b_pad : 0;
-                for (int i = 0; i < num_slabs; ++i, ++slab) {
-                    uint8_t* st = acquire(slab);
-                    if (!st) break;
-                    uint64_t* fb = &full_bar[slab % STAGES];
+                } else if (MODE == GEMM_MNMN) {
+                    const int split = z % p.splits, tap = (z / p.splits) % p.taps, batch = z / (p.splits * p.taps);
+                    const int kb0 = split * per_split;
+                    const int ns = slabs_of(z);
+                    const int dx = p.taps == 9 ? (tap % 3) - p.b_pad : 0;
+                    const int dy = p.taps == 9 ? (tap / 3) - p.b_pad : 0;
+                    for (int i = 0; i < ns; ++i, ++slab) {
+                        uint8_t* st = acquire(slab);
+                        if (!st) break;
+                        uint64_t* fb = &full_bar[slab % STAGES];
+                        int n0, y0, x0;
+                        pix_decompose((kb0 + i) * 64, p.W, p.H, n0, y0, x0);
+                        n0 += batch;
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+                            tma_load_4d(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
+#pragma unroll
+                        for (int b = 0; b < BLOCK_N / 64; ++b)
+                            tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64,
+                                        x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
+                    }
+                } else {  // GEMM_KMN
                     int n0, y0, x0;
-                    pix_decompose((kb0 + i) * 64, p.W, p.H, n0, y0, x0);
-                    n0 += batch;
+                    pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
+                    n0 += z * p.a_z_n;
+                    for (int i = 0; i < p.kblocks; ++i, ++slab) {
+                        uint8_t* st = acquire(slab);
+                        if (!st) break;
+                        uint64_t* fb = &full_bar[slab % STAGES];
+                        tma_load_4d(st, &tmA0, fb, p.a_c_base + i * 64, x0, y0, n0);
 #pragma unroll
-                    for (int b = 0; b < 2; ++b)
-                        tma_load_4d(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
-#pragma unroll
-                    for (int b = 0; b < BLOCK_N / 64; ++b)
-                        tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
-                }
-            } else {  // GEMM_KMN
-                int n0, y0, x0;
-                pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
-                n0 += z * p.a_z_n;
-                for (int i = 0; i < num_slabs; ++i, ++slab) {
-                    uint8_t* st = acquire(slab);
-                    if (!st) break;
-                    uint64_t* fb = &full_bar[slab % STAGES];
-                    tma_load_4d(st, &tmA0, fb, p.a_c_base + i * 64, x0, y0, n0);
-#pragma unroll
-                    for (int b = 0; b < BLOCK_N / 64; ++b)
-                        tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, i * 64, 0, z);
+                        for (int b = 0; b < BLOCK_N / 64; ++b)
+                            tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, i * 64, 0, z);
+                    }
                 }
             }
         }
@@ -186,96 +193,120 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ======================= MMA issuer =======================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, A_MN, B_MN);
-            for (int slab = 0; slab < num_slabs; ++slab) {
-                const int st = slab % STAGES;
-                const uint32_t ph = (slab / STAGES) & 1;
-                if (!mbar_wait(&full_bar[st], ph, 2)) break;
+            int slab = 0, it = 0;
+            bool ok = true;
+            for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++it) {
+                const int z = t / (m_tiles * n_tiles);
+                const int ns = slabs_of(z);
+                const int acc = it & 1;
+                const uint32_t acc_ph = (it >> 1) & 1;
+                if (!mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 4)) break;      // epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + st * SM::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + SM::A_BYTES;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int i = 0; i < ns; ++i, ++slab) {
+                    const int st = slab % STAGES;
+                    const uint32_t ph = (slab / STAGES) & 1;
+                    if (!mbar_wait(&full_bar[st], ph, 2)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + st * SM::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + SM::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // K-major: 16 elements = 32 B inside the swizzle span; MN-major: 16 K-rows of 128 B
-                    const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                             : umma_smem_desc(a_addr + k * 32, 16, 1024);
-                    const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                             : umma_smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (slab | k) != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        // K-major: 16 elements = 32 B inside the swizzle span; MN-major: 16 K-rows of 128 B
+                        const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                                 : umma_smem_desc(a_addr + k * 32, 16, 1024);
+                        const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                                 : umma_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, da, db, idesc, (i | k) != 0);
+                    }
+                    umma_commit(&empty_bar[st]);
                 }
-                umma_commit(&empty_bar[st]);
+                if (ok) umma_commit(&tmem_full[acc]);
             }
-            umma_commit(tmem_full);
         }
     } else {
         // ======================= epilogue: 4 warps <-> 4 TMEM lane quarters =======================
         const int q = warp & 3;
         const int r = q * 32 + lane;                 // accumulator row
-        bool ok = true;
-        if (num_slabs > 0) ok = mbar_wait(tmem_full, 0, 3);
-        tc_fence_after();
-        const int row = m_tile * 128 + r;
-        const bool row_ok = ok && row < p.M && num_slabs > 0;
-        long long orow = row;                         // output row (pixel) index
-        if (MODE == GEMM_KK && p.o_mul > 1) {
-            int n_, y_, x_;
-            pix_decompose(row, p.W, p.H, n_, y_, x_);
-            orow = ((long long)n_ * p.oH + y_ * p.o_mul + p.o_py) * p.oW + x_ * p.o_mul + p.o_px;
-        }
-        const long long zoff = (MODE == GEMM_MNMN) ? (long long)batch * p.out_z_stride + (long long)tap * p.out_tap_stride
-                                                  : (long long)z * p.out_z_stride;
-        const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int m_tile = t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
+            const int ns = slabs_of(z);
+            const int acc = it & 1;
+            const uint32_t acc_ph = (it >> 1) & 1;
+            if (!mbar_wait(&tmem_full[acc], acc_ph, 3)) break;
+            tc_fence_after();
+            int tap = 0, batch = z;
+            if (MODE == GEMM_MNMN) { tap = (z / p.splits) % p.taps; batch = z / (p.splits * p.taps); }
+            const int row = m_tile * 128 + r;
+            const bool row_ok = row < p.M && ns > 0;
+            long long orow = row;                         // output row (pixel) index
+            if (MODE == GEMM_KK && p.o_mul > 1) {
+                int n_, y_, x_;
+                pix_decompose(row, p.W, p.H, n_, y_, x_);
+                orow = ((long long)n_ * p.oH + y_ * p.o_mul + p.o_py) * p.oW + x_ * p.o_mul + p.o_px;
+            }
+            const long long zoff = (MODE == GEMM_MNMN) ? (long long)batch * p.out_z_stride + (long long)tap * p.out_tap_stride
+                                                      : (long long)z * p.out_z_stride;
+            const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            const int col = n_tile * BLOCK_N + c0;
-            if (col >= p.N) break;                    // uniform across the CTA
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (!row_ok) continue;
-            float f[32];
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                const int col = n_tile * BLOCK_N + c0;
+                if (col >= p.N || ns == 0) break;         // uniform across the CTA
+                uint32_t v[32];
+                tmem_ld32(t_addr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-            if (p.bias) {
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+                if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
-            }
-            if (rv) {
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
+                }
+                if (rv) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + col + j);
-            }
-            if (p.residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + col + j);
+                }
+                if (p.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const uint4 u = __ldg(rp + j4);
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const uint4 u = __ldg(rp + j4);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 t2 = __bfloat1622float2(h[e]);
-                        f[j4 * 8 + e * 2] += t2.x; f[j4 * 8 + e * 2 + 1] += t2.y;
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 t2 = __bfloat1622float2(h[e]);
+                            f[j4 * 8 + e * 2] += t2.x; f[j4 * 8 + e * 2 + 1] += t2.y;
+                        }
+                    }
+                }
+                if (p.flags & EPI_ATOMIC) {
+                    float* o = reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
+                } else if (p.flags & EPI_OUT_F32) {
+                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + orow * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                        o[j] = u;
                     }
                 }
             }
-            if (p.flags & EPI_ATOMIC) {
-                float* o = reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
-            } else if (p.flags & EPI_OUT_F32) {
-                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + orow * p.ldo + col);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 u;
-                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-                    o[j] = u;
-                }
-            }
+            // hand the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
     }
 

@@ -16,7 +16,7 @@ struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
 struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; };
-struct GnSaved { Src in; float* mr; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; };
+struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 static inline int oct_threads(int C) { const int oct = C / 8; return oct <= 256 ? (256 / oct) * oct : 0; }
@@ -253,53 +253,60 @@ struct UnetEngine {
     size_t zero_fwd(size_t bytes) { const size_t o = zf_cursor; zf_cursor += (bytes + 255) & ~size_t(255); return zero_fwd_off + o; }
     size_t zero_bwd(size_t bytes) { const size_t o = zb_cursor; zb_cursor += (bytes + 255) & ~size_t(255); return zero_bwd_off + o; }
 
+    // blocks over the pixels of one image: keep the whole launch within one wave of (148 SMs x occ) CTAs
+    static void gn_grid(int Bn, int HW, int occ, int& nblk, int& ppb) {
+        nblk = (148 * occ) / Bn; if (nblk > HW / 16) nblk = HW / 16; if (nblk < 1) nblk = 1;
+        ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
+    }
     GnSaved gn_fwd(std::vector<Op>& L, const std::string& name, const Src& in, const std::string& pname, const T4& out, int silu, float drop_p) {
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
         GnSaved sv; sv.in = in; sv.silu = silu; sv.drop_p = drop_p; sv.layer = ++layer_counter;   // dropout is armed per call by a non-zero seed
         sv.gamma = PP(pname + ".weight"); sv.beta = PP(pname + ".bias"); sv.dgamma = GP(pname + ".weight"); sv.dbeta = GP(pname + ".bias");
         double* stats = at<double>(zero_fwd((size_t)Bn * 64 * 8));
-        sv.mr = at<float>(alloc((size_t)Bn * 64 * 4));
+        sv.K = at<float>(alloc((size_t)Bn * 4 * C * 4));
         const GnSrc gs = gsrc(in);
         const int thr = oct_threads(C);
-        int nblk = (592 + Bn - 1) / Bn; if (nblk > HW / 8) nblk = HW / 8; if (nblk < 1) nblk = 1;
-        const int ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
+        int nblk, ppb; gn_grid(Bn, HW, 6, nblk, ppb);
         const dim3 g1(nblk, Bn);
-        float* mr = sv.mr;
+        float* K = sv.K; const float* ga = sv.gamma; const float* be = sv.beta;
         push(L, name + ".stats", 0, [=](cudaStream_t st) {
             k_gn_stats<<<g1, thr, 0, st>>>(gs, stats, HW, ppb);
-            k_gn_finalize<<<(Bn * 32 + 127) / 128, 128, 0, st>>>(stats, mr, Bn * 32, 1.0 / ((double)HW * (C / 32)), 1e-6f);
+            k_gn_finalize<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, ga, be, K, Bn, C, 1.0 / ((double)HW * (C / 32)), 1e-6f);
             return (int)cudaGetLastError(); }, 2);
-        GnApply a; a.s = gs; a.mr = mr; a.gamma = sv.gamma; a.beta = sv.beta; a.y = bp(out); a.HW = HW;
-        a.total_oct = (long long)Bn * HW * (C / 8); a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer;
-        const int n = grid_for(a.total_oct);
+        GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer;
+        int nb2, ppb2; gn_grid(Bn, HW, 4, nb2, ppb2);
+        const dim3 g2(nb2, Bn);
         UnetEngine* self = this;
-        push(L, name + ".apply", 0, [a, n, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
-            k_gn_apply<<<n, 256, 0, st>>>(aa); return (int)cudaGetLastError(); });
+        push(L, name + ".apply", 0, [a, g2, thr, ppb2, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
+            k_gn_apply<<<g2, thr, 0, st>>>(aa, ppb2); return (int)cudaGetLastError(); });
         return sv;
     }
     // dx(in) (=|+=) gn_bwd(dy) + addend ; dgamma/dbeta accumulate into the flat grads
-    void gn_bwd(const std::string& name, const GnSaved& sv, const T4& dy, const bf16* addend) {
+    void gn_bwd(const std::string& name, const GnSaved& sv, const T4& dy, const bf16* addend,
+                float* cs_per_img = nullptr, int cs_ld = 0, float* cs_total = nullptr, float* cs_total2 = nullptr) {
         const Src& in = sv.in;
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
         GnBwd a; memset(&a, 0, sizeof a);
-        a.s = gsrc(in); a.dy = bp(dy); a.mr = sv.mr; a.gamma = sv.gamma; a.beta = sv.beta;
-        a.red = at<double>(zero_bwd((size_t)Bn * 64 * 8)); a.dgamma = sv.dgamma; a.dbeta = sv.dbeta;
+        a.s = gsrc(in); a.dy = bp(dy); a.K = sv.K; a.gamma = sv.gamma;
+        a.cs = at<float>(zero_bwd((size_t)Bn * 2 * C * 4)); a.PQ = at<float>(alloc((size_t)Bn * 2 * C * 4));
+        a.dgamma = sv.dgamma; a.dbeta = sv.dbeta;
         bool f0 = true, f1 = true;
         const T4 g0 = grad_of(in.t0, &f0); a.dx0 = bp(g0); a.acc0 = f0 ? 0 : 1;
         if (in.two) { const T4 g1 = grad_of(in.t1, &f1); a.dx1 = bp(g1); a.acc1 = f1 ? 0 : 1; }
-        a.addend = addend; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer; a.total_oct = (long long)Bn * HW * (C / 8);
+        a.addend = addend; a.B = Bn; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer;
         const int thr = oct_threads(C);
-        int nblk = (592 + Bn - 1) / Bn; if (nblk > HW / 8) nblk = HW / 8; if (nblk < 1) nblk = 1;
-        a.pix_per_block = (HW + nblk - 1) / nblk; nblk = (HW + a.pix_per_block - 1) / a.pix_per_block;
+        int nblk, ppb; gn_grid(Bn, HW, 2, nblk, ppb);
+        a.pix_per_block = ppb;
         const dim3 g1(nblk, Bn);
-        const size_t shm = (size_t)(64 + 2 * C) * 4;
-        const int n = grid_for(a.total_oct);
+        const size_t shm = (size_t)2 * C * 4;
+        const size_t shm2 = (cs_per_img || cs_total || cs_total2) ? (size_t)C * 4 : 0;
         UnetEngine* self = this;
-        push(bwd_ops, name + ".gn_bwd", 0, [a, g1, thr, shm, n, self](cudaStream_t st) {
+        push(bwd_ops, name + ".gn_bwd", 0, [=](cudaStream_t st) {
             GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
             k_gn_bwd_reduce<<<g1, thr, shm, st>>>(aa);
-            k_gn_bwd_apply<<<n, 256, 0, st>>>(aa);
-            return (int)cudaGetLastError(); }, 2);
+            k_gn_bwd_finalize<<<Bn, 256, 0, st>>>(aa);
+            k_gn_bwd_apply<<<g1, thr, shm2, st>>>(aa, cs_per_img, cs_ld, cs_total, cs_total2);
+            return (int)cudaGetLastError(); }, 3);
     }
     void colsum_op(const std::string& name, const T4& dy, float* per_img, int ld, float* total, float* total2, int C_valid) {
         const int HW = dy.H * dy.W, C = dy.C, Bn = dy.B;

@@ -97,9 +97,10 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
             conv_op(bwd_ops, c, &bwd_flops);
             wgrad_op(p + ".skip.wgrad", dOut, x, 1, 1, MAP_NORMAL, GP(p + ".skip.weight"), cout);
         }
-        gn_bwd(p + ".norm2", g2, d_a2, nullptr);
+        // the column sums of d_h1 (bias gradients of conv1 / fc and the per-image timestep-projection gradient) are
+        // accumulated by the same kernel that produces d_h1
+        gn_bwd(p + ".norm2", g2, d_a2, nullptr, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"));
         const T4 d_h1 = grad_of(h1, nullptr);
-        colsum_op(p + ".conv1.bias", d_h1, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"), cout);
         T4 d_a1 = newT(Bn, h, w, cin);
         { ConvSpec c; c.name = p + ".conv1.dgrad"; c.in = one(d_h1); c.wp = w1.dgr; c.ldw = w1.ld_d; c.out = d_a1; c.Co = cin; c.Ho = h; c.Wo = w;
           conv_op(bwd_ops, c, &bwd_flops); }
