@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
         ("a_estride", C.c_int), ("b_estride", C.c_int), ("b_pad", C.c_int),
         ("seg_custom", C.c_int * 3), ("seg_cmul", C.c_int * 3),
         ("seg_dx", (C.c_byte * 9) * 3), ("seg_dy", (C.c_byte * 9) * 3),
-        ("o_mul", C.c_int), ("o_py", C.c_int), ("o_px", C.c_int),
+        ("o_mul", C.c_int), ("o_py", C.c_int), ("o_px", C.c_int), ("kk_splits", C.c_int),
     ]
 
 

@@ -61,6 +61,7 @@ void ddpm_unet_destroy(ddpm_unet* h) {
     if (!h) return;
     if (h->d_tmodel) cudaFree(h->d_tmodel);
     if (h->d_coef) cudaFree(h->d_coef);
+    if (h->e.side_stream) { cudaStreamDestroy(h->e.side_stream); cudaEventDestroy(h->e.ev_fork); cudaEventDestroy(h->e.ev_join); }
     delete h;
 }
 int ddpm_unet_num_params(const ddpm_unet* h) { return (int)h->e.params.size(); }

@@ -33,7 +33,8 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     const int gz = d.grid_z > 0 ? d.grid_z : 1;
     const int n_tiles = (d.N + g.block_n - 1) / g.block_n;
     const int m_tiles = (d.M + 127) / 128;
-    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.grid_z = gz;
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.grid_z = gz; p.kk_splits = d.kk_splits > 1 ? d.kk_splits : 1;
+    if (p.kk_splits > 1 && (d.mode != GEMM_KK || gz != p.kk_splits || !(d.flags & EPI_ATOMIC))) return fail(-10, "kk_splits needs mode 0, grid_z == kk_splits and the atomic fp32 epilogue");
     g.grid = dim3(m_tiles * n_tiles * gz, 1, 1);   // clipped to the SM count at launch (persistent CTAs)
     int rc;
     if (d.mode == GEMM_KK) {

@@ -96,6 +96,8 @@ struct SgemmParams {
     int M, N, K;
     long long sa_m, sa_k, sa_z, sb_k, sb_n, sb_z, sc_m, sc_n, sc_z;
     float alpha; int accumulate; int silu_a;      // accumulate: 1 = C += (read-modify-write), 2 = atomicAdd (TC = float only)
+    int ksplit;                                   // > 1: blockIdx.z = problem*ksplit + split; K is cut in ksplit ranges, the output
+                                                  // (pre-zeroed) is accumulated with atomics and the bias is added by split 0
 };
 
 template <typename TC> __device__ __forceinline__ void atomic_addf(TC* p, float v);
@@ -103,7 +105,7 @@ template <> __device__ __forceinline__ void atomic_addf<float>(float* p, float v
 template <> __device__ __forceinline__ void atomic_addf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(__bfloat162float(*p) + v); }
 
 template <typename TA, typename TB, typename TC>
-__device__ __forceinline__ void sgemm_body(const SgemmParams& p, int bz) {
+__device__ __forceinline__ void sgemm_body(const SgemmParams& p, int bz, int split = 0) {
     __shared__ float As[16][65];
     __shared__ float Bs[16][65];
     const TA* A = reinterpret_cast<const TA*>(p.A) + (long long)bz * p.sa_z;
@@ -113,14 +115,18 @@ __device__ __forceinline__ void sgemm_body(const SgemmParams& p, int bz) {
     if (m0 >= p.M || n0 >= p.N) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < p.K; k0 += 16) {
+    const int ks = p.ksplit > 1 ? p.ksplit : 1;
+    const int kper = ((p.K + ks - 1) / ks + 15) / 16 * 16;
+    const int kbeg = split * kper;
+    int kend = kbeg + kper; if (kend > p.K) kend = p.K;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
         for (int i = threadIdx.x; i < 1024; i += 256) {
             const int kk = i & 15, r = i >> 4;
             const int m = m0 + r, k = k0 + kk;
             float a = 0.f, b = 0.f;
-            if (m < p.M && k < p.K) { a = ldf<TA>(A + (long long)m * p.sa_m + (long long)k * p.sa_k); if (p.silu_a) a = silu_f(a); }
+            if (m < p.M && k < kend) { a = ldf<TA>(A + (long long)m * p.sa_m + (long long)k * p.sa_k); if (p.silu_a) a = silu_f(a); }
             const int n = n0 + r;
-            if (n < p.N && k < p.K) b = ldf<TB>(Bm + (long long)k * p.sb_k + (long long)n * p.sb_n);
+            if (n < p.N && k < kend) b = ldf<TB>(Bm + (long long)k * p.sb_k + (long long)n * p.sb_n);
             As[kk][r] = a; Bs[kk][r] = b;
         }
         __syncthreads();
@@ -145,20 +151,23 @@ __device__ __forceinline__ void sgemm_body(const SgemmParams& p, int bz) {
             const int n = n0 + tx * 4 + j;
             if (n >= p.N) continue;
             float v = acc[i][j] * p.alpha;
-            if (p.bias) v += p.bias[n];
+            if (p.bias && split == 0) v += p.bias[n];
             TC* c = C + (long long)m * p.sc_m + (long long)n * p.sc_n;
-            if (p.accumulate == 2) { atomic_addf<TC>(c, v); continue; }
+            if (p.accumulate == 2 || ks > 1) { atomic_addf<TC>(c, v); continue; }
             if (p.accumulate) v += ldf<TC>(c);
             stf<TC>(c, v);
         }
     }
 }
 template <typename TA, typename TB, typename TC>
-__global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) { sgemm_body<TA, TB, TC>(p, blockIdx.z); }
-// table-driven: blockIdx.z selects an independent problem (per-ResBlock timestep projections)
-__global__ void __launch_bounds__(256) k_sgemm_table(const SgemmParams* __restrict__ table) {
-    const SgemmParams p = table[blockIdx.z];
-    sgemm_body<float, float, float>(p, 0);
+__global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) {
+    const int ks = p.ksplit > 1 ? p.ksplit : 1;
+    sgemm_body<TA, TB, TC>(p, blockIdx.z / ks, blockIdx.z % ks);
+}
+// table-driven: blockIdx.z selects an independent problem (per-ResBlock timestep projections) and its K split
+__global__ void __launch_bounds__(256) k_sgemm_table(const SgemmParams* __restrict__ table, int ksplit) {
+    const SgemmParams p = table[blockIdx.z / ksplit];
+    sgemm_body<float, float, float>(p, 0, blockIdx.z % ksplit);
 }
 // column sums of an fp32 [M][N] matrix (bias grads of the timestep MLP): out[n] += sum_m A[m][n]
 __global__ void k_colsum_f32(const float* __restrict__ A, float* __restrict__ out, int M, int N, long long lda) {
@@ -980,6 +989,51 @@ __global__ void k_pack_conv_w_s2dgrad(const float* __restrict__ w, bf16* __restr
         const int base = (py == 0 ? (px == 0 ? 0 : 4) : (px == 0 ? 6 : 8)) * Co;
         const int j = (py ? 0 : ky / 2) * (px ? 1 : 2) + (px ? 0 : kx / 2);
         dgr[(long long)ci * ld_d + base + (long long)j * Co + co] = __float2bfloat16_rn(w[i]);
+    }
+}
+// ---- table-driven weight maintenance: ONE launch re-packs every conv weight (grid.y = table entry)
+enum PackKind { PK_CONV = 0, PK_BIAS_ADD = 1, PK_FLIP_T = 2, PK_UNPACK_GRAD = 3 };
+struct PackEntry {
+    int kind; int Co, Ci, taps; int k_off; int dkind;   // dkind: 0 none, 1 dgrad, 2 dgrad flipped taps, 3 stride-2 parity dgrad
+    const float* w; const float* w2; bf16* fwd; long long ld_f; bf16* dgr; long long ld_d; float* fout; float* scratch;
+};
+__global__ void __launch_bounds__(256) k_pack_table(const PackEntry* __restrict__ table) {
+    const PackEntry e = table[blockIdx.y];
+    const long long total = (e.kind == PK_BIAS_ADD) ? e.Co : (long long)e.Co * e.Ci * e.taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (e.kind == PK_BIAS_ADD) { e.fout[i] = e.w[i] + (e.w2 ? e.w2[i] : 0.f); continue; }
+        const int t = (int)(i % e.taps); const long long r = i / e.taps; const int ci = (int)(r % e.Ci), co = (int)(r / e.Ci);
+        if (e.kind == PK_FLIP_T) { e.fout[((long long)ci * e.Co + co) * 9 + (8 - t)] = e.w[i]; continue; }
+        if (e.kind == PK_UNPACK_GRAD) {           // packed fp32 grad [tap][Co][Ci] -> OIHW (=), scratch cleared behind the read
+            const long long j = ((long long)t * e.Co + co) * e.Ci + ci;
+            e.fout[i] = e.scratch[j]; e.scratch[j] = 0.f; continue;
+        }
+        const bf16 v = __float2bfloat16_rn(e.w[i]);
+        if (e.fwd) e.fwd[(long long)co * e.ld_f + e.k_off + (long long)t * e.Ci + ci] = v;
+        if (e.dkind == 1 || e.dkind == 2) e.dgr[(long long)ci * e.ld_d + (long long)(e.dkind == 2 ? e.taps - 1 - t : t) * e.Co + co] = v;
+        else if (e.dkind == 3) {
+            const int ky = t / 3, kx = t % 3, py = ky & 1, px = kx & 1;
+            const int base = (py == 0 ? (px == 0 ? 0 : 4) : (px == 0 ? 6 : 8)) * e.Co;
+            const int j = (py ? 0 : ky / 2) * (px ? 1 : 2) + (px ? 0 : kx / 2);
+            e.dgr[(long long)ci * e.ld_d + base + (long long)j * e.Co + co] = v;
+        }
+    }
+}
+// split-K finalize: out(bf16) = scratch(fp32) + bias + rowvec[b] + residual ; scratch is cleared behind the read
+__global__ void __launch_bounds__(256) k_splitk_finalize(float* __restrict__ scratch, const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                                        int rowvec_ld, int rows_per_vec, const bf16* __restrict__ residual, bf16* __restrict__ out,
+                                                        long long M, int N) {
+    const long long total = M * (N / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / (N / 8); const int c = (int)(i % (N / 8)) * 8;
+        float4* sp = reinterpret_cast<float4*>(scratch + row * N + c);
+        const float4 a = sp[0], b = sp[1];
+        sp[0] = make_float4(0, 0, 0, 0); sp[1] = make_float4(0, 0, 0, 0);
+        float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (bias) { for (int e = 0; e < 8; ++e) f[e] += __ldg(bias + c + e); }
+        if (rowvec) { const float* rv = rowvec + (row / rows_per_vec) * rowvec_ld + c; for (int e = 0; e < 8; ++e) f[e] += __ldg(rv + e); }
+        if (residual) { float r8[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(residual + row * N + c)), r8); for (int e = 0; e < 8; ++e) f[e] += r8[e]; }
+        *reinterpret_cast<uint4*>(out + row * N + c) = pack8(f);
     }
 }
 // packed grad [tap][Co][Ci] fp32 -> OIHW fp32 (=)

@@ -41,6 +41,7 @@ struct GemmParams {
     // optional output-row remap (KK): tile row (n,y,x) on the A grid -> output pixel (n, y*o_mul+o_py, x*o_mul+o_px) on an oW x oH grid
     int o_mul, o_py, o_px, oW, oH;
     int m_tiles, n_tiles, grid_z;   // tile space walked by the persistent CTAs
+    int kk_splits;                  // KK: > 1 -> z is a K-split index over the flattened (segment, tap, chunk) slab sequence
     // epilogue
     void* out; int ldo; long long out_z_stride; long long out_tap_stride; int flags;
     const float* bias;        // [N] or null
@@ -97,8 +98,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int kk_slabs = 0;
     if (MODE == GEMM_KK) for (int s = 0; s < p.nseg; ++s) kk_slabs += p.seg[s].taps * p.seg[s].kchunks;
     const int per_split = (MODE == GEMM_MNMN) ? (p.kblocks + p.splits - 1) / p.splits : 0;
+    const int kk_per = (MODE == GEMM_KK && p.kk_splits > 1) ? (kk_slabs + p.kk_splits - 1) / p.kk_splits : kk_slabs;
     auto slabs_of = [&](int z) -> int {
-        if (MODE == GEMM_KK) return kk_slabs;
+        if (MODE == GEMM_KK) {
+            if (p.kk_splits <= 1) return kk_slabs;
+            const int lo = z * kk_per; int hi = lo + kk_per; if (hi > kk_slabs) hi = kk_slabs;
+            return hi > lo ? hi - lo : 0;
+        }
         if (MODE == GEMM_KMN) return p.kblocks;
         const int split = z % p.splits;
         const int kb0 = split * per_split;
@@ -136,6 +142,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     int n0, y0, x0;
                     pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
                     n0 += z * p.a_z_n;
+                    const int k_lo = p.kk_splits > 1 ? z * kk_per : 0;
+                    const int k_hi = p.kk_splits > 1 ? (k_lo + kk_per < kk_slabs ? k_lo + kk_per : kk_slabs) : kk_slabs;
                     int kcount = 0;
                     for (int s = 0; s < p.nseg && ok; ++s) {
                         const GemmSeg sg = p.seg[s];
@@ -143,12 +151,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         for (int tp = 0; tp < sg.taps && ok; ++tp) {
                             const int xc = x0 * sg.cmul + sg.dx[tp];
                             const int yc = y0 * sg.cmul + sg.dy[tp];
-                            for (int kc = 0; kc < sg.kchunks; ++kc, ++slab, ++kcount) {
+                            for (int kc = 0; kc < sg.kchunks; ++kc, ++kcount) {
+                                if (kcount < k_lo || kcount >= k_hi) continue;
                                 uint8_t* st = acquire(slab);
                                 if (!st) break;
                                 uint64_t* fb = &full_bar[slab % STAGES];
                                 tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
                                 tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+                                ++slab;
                             }
                         }
                     }
@@ -247,7 +257,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 orow = ((long long)n_ * p.oH + y_ * p.o_mul + p.o_py) * p.oW + x_ * p.o_mul + p.o_px;
             }
             const long long zoff = (MODE == GEMM_MNMN) ? (long long)batch * p.out_z_stride + (long long)tap * p.out_tap_stride
-                                                      : (long long)z * p.out_z_stride;
+                                                      : ((MODE == GEMM_KK && p.kk_splits > 1) ? 0 : (long long)z * p.out_z_stride);
             const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1

@@ -15,7 +15,7 @@ struct ParamInfo { std::string name; int nd; int dims[4]; long long numel; long 
 struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
-struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; };
+struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; };
 struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
@@ -101,8 +101,8 @@ struct UnetEngine {
     GnSrc gsrc(const Src& s) const { GnSrc g; g.x0 = bp(s.t0); g.C0 = s.t0.C; g.x1 = s.two ? bp(s.t1) : nullptr; g.C1 = s.two ? s.t1.C : 0; return g; }
     static Src one(const T4& t) { Src s; s.t0 = t; s.two = false; return s; }
 
-    void push(std::vector<Op>& L, const std::string& name, double flops, std::function<int(cudaStream_t)> f, int launches = 1) {
-        Op o; o.name = name; o.flops = flops; o.run = std::move(f); o.launches = launches; L.push_back(std::move(o));
+    void push(std::vector<Op>& L, const std::string& name, double flops, std::function<int(cudaStream_t)> f, int launches = 1, bool side = false) {
+        Op o; o.name = name; o.flops = flops; o.run = std::move(f); o.launches = launches; o.side = side; L.push_back(std::move(o));
     }
     static int count_launches(const std::vector<Op>& L) { int n = 0; for (auto& o : L) n += o.launches; return n; }
     // grad tensor of a forward tensor; `first` tells the producer whether to overwrite (=) or accumulate (+=)
@@ -160,6 +160,30 @@ struct UnetEngine {
             d.bias = c.bias; d.rowvec = c.rowvec; d.rowvec_ld = c.rowvec_ld; d.rows_per_vec = c.Ho * c.Wo;
             d.residual = c.accumulate ? (const void*)bp(c.out) : (const void*)c.residual; d.ldr = c.Co;
             ++n_tc_gemms;
+            // small-M problems (8x8 / 4x4 levels) do not fill 148 SMs with output tiles: split the K loop across CTAs
+            // (fp32 atomics into a zeroed scratch) and finish bias / timestep vector / residual / bf16 in a tiny second kernel
+            const int bn = pick_block_n(c.Co);
+            const int tiles = (int)((Pout + 127) / 128) * ((c.Co + bn - 1) / bn);
+            const int slabs = (int)(K / 64);
+            int splits = 1;
+            if (tiles <= 74 && slabs >= 16) { splits = 148 / tiles; if (splits > slabs / 8) splits = slabs / 8; if (splits > 16) splits = 16; if (splits < 1) splits = 1; }
+            if (splits > 1) {
+                float* scratch = at<float>(alloc_once_zero((size_t)Pout * c.Co * 4));
+                ddpm_gemm_desc ds = d;
+                ds.kk_splits = splits; ds.grid_z = splits; ds.out = scratch; ds.flags = EPI_OUT_F32 | EPI_ATOMIC;
+                ds.bias = nullptr; ds.rowvec = nullptr; ds.residual = nullptr;
+                const float* bias = c.bias; const float* rowvec = c.rowvec; const int rvld = c.rowvec_ld, rpv = c.Ho * c.Wo;
+                const bf16* resid = reinterpret_cast<const bf16*>(d.residual); bf16* outp = bp(c.out);
+                const long long M = Pout; const int N = c.Co; const int nfin = grid_for(M * (N / 8));
+                if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }, 2); return; }
+                GemmLaunch g; int rc = build_gemm(ds, g);
+                if (rc) { plan_error = rc; return; }
+                push(L, c.name + "[splitk]", fl, [=](cudaStream_t st) {
+                    const int r2 = launch_gemm(g, st); if (r2) return r2;
+                    k_splitk_finalize<<<nfin, 256, 0, st>>>(scratch, bias, rowvec, rvld, rpv, resid, outp, M, N);
+                    return (int)cudaGetLastError(); }, 2);
+                return;
+            }
             if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return; }
             GemmLaunch g; int rc = build_gemm(d, g);
             if (rc) { plan_error = rc; return; }
@@ -223,9 +247,10 @@ struct UnetEngine {
                 if (rc) { plan_error = rc; return; }
                 push(bwd_ops, name, s ? 0 : fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
             }
-            if (taps == 9) {
-                const int n = grid_for((long long)Co * Cin * 9);
-                push(bwd_ops, name + ".unpack", 0, [=](cudaStream_t st) { k_unpack_conv_grad<<<n, 256, 0, st>>>(scratch, dw, Co, Cin, 9); return (int)cudaGetLastError(); });
+            if (taps == 9) {   // packed [tap][Co][Ci] scratch -> OIHW flat gradient: batched into ONE table-driven launch at the end of backward
+                PackEntry e; memset(&e, 0, sizeof e);
+                e.kind = PK_UNPACK_GRAD; e.Co = Co; e.Ci = Cin; e.taps = 9; e.fout = dw; e.scratch = scratch;
+                unpack_table_host.push_back(e);
             }
             return;
         }
@@ -315,36 +340,35 @@ struct UnetEngine {
         const int ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
         const dim3 g(nblk, Bn); const bf16* p = bp(dy);
         const size_t shm = (size_t)C * 4;
-        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { k_colsum<<<g, thr, shm, st>>>(p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); });
+        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { k_colsum<<<g, thr, shm, st>>>(p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); }, 1, /*side=*/true);
     }
 
-    // ------------------------------------------------------------------ packed weights
+    // ------------------------------------------------------------------ packed weights (table-driven: one launch re-packs everything)
     struct Packed { bf16* fwd = nullptr; long long ld_f = 0; bf16* dgr = nullptr; long long ld_d = 0; };
-    // fwd pack [Co][taps*Ci (+extra)], dgrad pack [Ci][taps*Co_pad]
-    Packed pack_conv(const std::string& pname, int Co, int Ci, int ksize, int extra_k, bool flip, bool want_dgrad, int co_pad = 0) {
+    std::vector<PackEntry> pack_table_host, unpack_table_host; size_t pack_table_off = 0, unpack_table_off = 0;
+    // fwd pack [Co][taps*Ci (+extra)], dgrad pack [Ci][taps*Co] (dkind 1 plain / 2 flipped taps / 3 stride-2 parity blocks)
+    Packed pack_conv(const std::string& pname, int Co, int Ci, int ksize, int extra_k, bool flip, bool want_dgrad, int dkind_override = 0) {
         const int taps = ksize * ksize;
         Packed pk; pk.ld_f = (long long)taps * Ci + extra_k;
         pk.fwd = at<bf16>(alloc((size_t)Co * pk.ld_f * 2));
-        const int Cop = co_pad ? co_pad : Co;
-        if (want_dgrad && train) { pk.ld_d = (long long)taps * Cop; pk.dgr = at<bf16>(co_pad ? alloc_once_zero((size_t)Ci * pk.ld_d * 2) : alloc((size_t)Ci * pk.ld_d * 2)); }
-        const float* w = PP(pname + ".weight");
-        const int n = grid_for((long long)Co * Ci * taps);
-        bf16* f = pk.fwd; bf16* dg = pk.dgr; const long long ldf = pk.ld_f, ldd = pk.ld_d; const int fl = flip ? 1 : 0;
-        if (co_pad) {   // dgrad pack rows are [Ci][taps*Cop]: the kernel indexes tap*Co + co, so pack with Co := Cop is wrong; use a strided variant
-            push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) {
-                k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, 0, nullptr, 0, fl, Co, Ci, taps);
-                if (dg) k_pack_conv_w_padded<<<n, 256, 0, st>>>(w, dg, ldd, fl, Co, Cop, Ci, taps);
-                return (int)cudaGetLastError(); }, 2);
-        } else {
-            push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) { k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, 0, dg, ldd, fl, Co, Ci, taps); return (int)cudaGetLastError(); });
-        }
+        if (want_dgrad && train) { pk.ld_d = (long long)taps * Co; pk.dgr = at<bf16>(alloc((size_t)Ci * pk.ld_d * 2)); }
+        PackEntry e; memset(&e, 0, sizeof e);
+        e.kind = PK_CONV; e.Co = Co; e.Ci = Ci; e.taps = taps; e.k_off = 0; e.w = PP(pname + ".weight");
+        e.fwd = pk.fwd; e.ld_f = pk.ld_f; e.dgr = pk.dgr; e.ld_d = pk.ld_d;
+        e.dkind = pk.dgr ? (dkind_override ? dkind_override : (flip ? 2 : 1)) : 0;
+        pack_table_host.push_back(e);
         return pk;
     }
     void pack_extra(const std::string& pname, const Packed& into, int k_off, int Co, int Ci, bf16* dgr, long long ld_d) {
-        const float* w = PP(pname + ".weight");
-        const int n = grid_for((long long)Co * Ci);
-        bf16* f = into.fwd; const long long ldf = into.ld_f;
-        push(pack_ops, "pack." + pname, 0, [=](cudaStream_t st) { k_pack_conv_w<<<n, 256, 0, st>>>(w, f, ldf, k_off, dgr, ld_d, 0, Co, Ci, 1); return (int)cudaGetLastError(); });
+        PackEntry e; memset(&e, 0, sizeof e);
+        e.kind = PK_CONV; e.Co = Co; e.Ci = Ci; e.taps = 1; e.k_off = k_off; e.w = PP(pname + ".weight");
+        e.fwd = into.fwd; e.ld_f = into.ld_f; e.dgr = dgr; e.ld_d = ld_d; e.dkind = dgr ? 1 : 0;
+        pack_table_host.push_back(e);
+    }
+    void pack_bias_add(float* dst, const float* a, const float* b, int n) {
+        PackEntry e; memset(&e, 0, sizeof e);
+        e.kind = PK_BIAS_ADD; e.Co = n; e.Ci = 1; e.taps = 1; e.w = a; e.w2 = b; e.fout = dst;
+        pack_table_host.push_back(e);
     }
 
     // ------------------------------------------------------------------ blocks
@@ -356,12 +380,31 @@ struct UnetEngine {
              void* C, long long ldc, long long sc, bool c_f32, int nb, int T, int Cc, float alpha, double* fl_acc);
     int plan(int B_, int H_, int W_, bool train_, bool dry_);
     int build();
+    // Ops flagged `side` (bias-gradient column sums, gradient unpacks: small, memory-bound, nothing downstream needs them
+    // before the end of the pass) are forked onto a second stream so they overlap the tensor-core kernels, and joined at
+    // the end of the list.  Fork/join are event edges, so the pattern is CUDA-graph capturable.
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int run_list(std::vector<Op>& L, cudaStream_t st) {
         static const bool dbg = getenv("DDPM_DEBUG_SYNC") != nullptr;   // serialise + attribute faults to an op (never under graph capture)
+        static const bool no_side = getenv("DDPM_NO_SIDE_STREAM") != nullptr;
+        bool forked = false;
         for (auto& o : L) {
-            int rc = o.run(st);
+            int rc;
+            if (o.side && side_stream && !dbg && !no_side) {
+                rc = (int)cudaEventRecord(ev_fork, st);
+                if (!rc) rc = (int)cudaStreamWaitEvent(side_stream, ev_fork, 0);
+                if (!rc) rc = o.run(side_stream);
+                forked = true;
+            } else {
+                rc = o.run(st);
+            }
             if (!rc && dbg) rc = (int)cudaStreamSynchronize(st);
             if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc));
+        }
+        if (forked) {
+            int rc = (int)cudaEventRecord(ev_join, side_stream);
+            if (!rc) rc = (int)cudaStreamWaitEvent(st, ev_join, 0);
+            if (rc) return fail(-20, "side-stream join failed: %s", cudaGetErrorString((cudaError_t)rc));
         }
         return 0;
     }

@@ -71,8 +71,7 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
         if (train) wsd = at<bf16>(alloc((size_t)cin * cout * 2));
         pack_extra(p + ".skip", w2, 9 * cout, cout, cin, wsd, cout);
         float* comb = at<float>(alloc((size_t)cout * 4));
-        const float* b2 = PP(p + ".conv2.bias"); const float* bs = PP(p + ".skip.bias");
-        push(pack_ops, "bias." + p, 0, [=](cudaStream_t st) { k_add_f32<<<(cout + 127) / 128, 128, 0, st>>>(comb, b2, bs, cout); return (int)cudaGetLastError(); });
+        pack_bias_add(comb, PP(p + ".conv2.bias"), PP(p + ".skip.bias"), cout);
         bias2 = comb;
     }
     T4 out = newT(Bn, h, w, cout);
@@ -167,19 +166,7 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
 inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
     const int C = x.C, Bn = x.B, h = x.H, w = x.W;
     const bool tc = (C % 64 == 0) && tc_ok_geom(h / 2, w / 2);
-    Packed pk;
-    if (tc) {
-        pk.ld_f = 9LL * C; pk.fwd = at<bf16>(alloc((size_t)C * pk.ld_f * 2));
-        if (train) { pk.ld_d = 9LL * C; pk.dgr = at<bf16>(alloc((size_t)C * pk.ld_d * 2)); }
-        const float* wsrc = PP(p + ".weight"); bf16* f = pk.fwd; bf16* dg = pk.dgr; const long long ld = pk.ld_f;
-        const int n = grid_for((long long)C * C * 9);
-        push(pack_ops, "pack." + p, 0, [=](cudaStream_t st) {
-            k_pack_conv_w<<<n, 256, 0, st>>>(wsrc, f, ld, 0, nullptr, 0, 0, C, C, 9);
-            if (dg) k_pack_conv_w_s2dgrad<<<n, 256, 0, st>>>(wsrc, dg, ld, C, C);
-            return (int)cudaGetLastError(); }, 2);
-    } else {
-        pk = pack_conv(p, C, C, 3, 0, /*flip=*/false, true);
-    }
+    const Packed pk = pack_conv(p, C, C, 3, 0, /*flip=*/false, true, tc ? 3 : 1);
     T4 out = newT(Bn, h / 2, w / 2, C);
     { ConvSpec c; c.name = p; c.in = one(x); c.stride = 2; c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = h / 2; c.Wo = w / 2;
       conv_op(fwd_ops, c, &fwd_flops); }
@@ -251,7 +238,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
 inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     B = B_; H = H_; W = W_; train = train_; dry = dry_;
     cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); grads.clear(); once_list.clear();
-    tp_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear();
+    tp_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
     layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0;
     const size_t zf_total = zf_cursor, zb_total = zb_cursor;   // sizes learned by the preceding dry pass
     zf_cursor = zb_cursor = 0;
@@ -279,8 +266,9 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     const int tp_ld = nblocks * maxc;
     float* emb = at<float>(alloc((size_t)B * ch * 4));
     float* e0 = at<float>(alloc((size_t)B * E * 4));
-    float* e1 = at<float>(alloc((size_t)B * E * 4));
-    float* TP = at<float>(alloc((size_t)B * tp_ld * 4));
+    float* e1 = at<float>(zero_fwd((size_t)B * E * 4));            // K-split GEMMs accumulate into zeroed outputs
+    float* TP = at<float>(zero_fwd((size_t)B * tp_ld * 4));
+    constexpr int KS = 4;
     float* dTP = at<float>(zero_bwd((size_t)B * tp_ld * 4));
     float* d_st = at<float>(zero_bwd((size_t)B * E * 4));
     tp_table_off = alloc(sizeof(SgemmParams) * nblocks); tpw_table_off = alloc(sizeof(SgemmParams) * nblocks); tpd_table_off = alloc(sizeof(SgemmParams) * nblocks);
@@ -292,11 +280,12 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         a.sa_m = ch; a.sa_k = 1; a.sb_k = 1; a.sb_n = ch; a.sc_m = E; a.sc_n = 1; a.alpha = 1.f;
         const dim3 g0((E + 63) / 64, (B + 63) / 64, 1);
         push(fwd_ops, "temb.fc0", 2.0 * B * E * ch, [a, g0](cudaStream_t st) { k_sgemm<float, float, float><<<g0, 256, 0, st>>>(a); return (int)cudaGetLastError(); });
-        SgemmParams b = a; b.A = e0; b.B = PP("embed.2.weight"); b.C = e1; b.bias = PP("embed.2.bias"); b.K = E; b.sa_m = E; b.sb_n = E; b.silu_a = 1;
-        push(fwd_ops, "temb.fc1", 2.0 * B * E * E, [b, g0](cudaStream_t st) { k_sgemm<float, float, float><<<g0, 256, 0, st>>>(b); return (int)cudaGetLastError(); });
+        SgemmParams b = a; b.A = e0; b.B = PP("embed.2.weight"); b.C = e1; b.bias = PP("embed.2.bias"); b.K = E; b.sa_m = E; b.sb_n = E; b.silu_a = 1; b.ksplit = KS;
+        const dim3 g0s((E + 63) / 64, (B + 63) / 64, KS);
+        push(fwd_ops, "temb.fc1", 2.0 * B * E * E, [b, g0s](cudaStream_t st) { k_sgemm<float, float, float><<<g0s, 256, 0, st>>>(b); return (int)cudaGetLastError(); });
         const SgemmParams* tab = at<SgemmParams>(tp_table_off);
-        const dim3 g1((maxc + 63) / 64, (B + 63) / 64, nblocks);
-        push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { k_sgemm_table<<<g1, 256, 0, st>>>(tab); return (int)cudaGetLastError(); });
+        const dim3 g1((maxc + 63) / 64, (B + 63) / 64, nblocks * KS);
+        push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { k_sgemm_table<<<g1, 256, 0, st>>>(tab, KS); return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * E * ch + 2.0 * B * E * E;
     }
     int blk = 0;
@@ -327,8 +316,8 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         tape.push_back([=]() {
             const SgemmParams* tw = at<SgemmParams>(tpw_table_off); const SgemmParams* td = at<SgemmParams>(tpd_table_off);
             const dim3 gw((maxc + 63) / 64, (E + 63) / 64, nblocks), gd((E + 63) / 64, (B + 63) / 64, nblocks);
-            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { k_sgemm_table<<<gw, 256, 0, st>>>(tw); k_sgemm_table<<<gd, 256, 0, st>>>(td); return (int)cudaGetLastError(); }, 2);
-            float* d_e1 = at<float>(alloc((size_t)B * E * 4)); float* d_s0 = at<float>(alloc((size_t)B * E * 4)); float* d_e0 = at<float>(alloc((size_t)B * E * 4));
+            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { k_sgemm_table<<<gw, 256, 0, st>>>(tw, 1); k_sgemm_table<<<gd, 256, 0, st>>>(td, 1); return (int)cudaGetLastError(); }, 2);
+            float* d_e1 = at<float>(alloc((size_t)B * E * 4)); float* d_s0 = at<float>(zero_bwd((size_t)B * E * 4)); float* d_e0 = at<float>(alloc((size_t)B * E * 4));
             const long long nE = (long long)B * E; const int Bn = B;
             float* gw2 = GP("embed.2.weight"); float* gb2 = GP("embed.2.bias"); float* gw0 = GP("embed.0.weight"); float* gb0 = GP("embed.0.bias");
             const float* w2 = PP("embed.2.weight");
@@ -339,8 +328,8 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 k_sgemm<float, float, float><<<dim3((E + 63) / 64, (E + 63) / 64, 1), 256, 0, st>>>(a);
                 k_colsum_f32<<<(E + 127) / 128, 128, 0, st>>>(d_e1, gb2, Bn, E, E);
                 SgemmParams b; memset(&b, 0, sizeof b);           // d_s0[b][k] = sum_n d_e1[b][n] W2[n][k]
-                b.A = d_e1; b.B = w2; b.C = d_s0; b.M = Bn; b.N = E; b.K = E; b.sa_m = E; b.sa_k = 1; b.sb_k = E; b.sb_n = 1; b.sc_m = E; b.sc_n = 1; b.alpha = 1.f;
-                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (Bn + 63) / 64, 1), 256, 0, st>>>(b);
+                b.A = d_e1; b.B = w2; b.C = d_s0; b.M = Bn; b.N = E; b.K = E; b.sa_m = E; b.sa_k = 1; b.sb_k = E; b.sb_n = 1; b.sc_m = E; b.sc_n = 1; b.alpha = 1.f; b.ksplit = 4;
+                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (Bn + 63) / 64, 4), 256, 0, st>>>(b);
                 k_silu_bwd_f32<<<grid_for(nE), 256, 0, st>>>(e0, d_s0, d_e0, nE);
                 SgemmParams c; memset(&c, 0, sizeof c);           // dW0[n][k] = sum_b emb[b][k] d_e0[b][n]
                 c.A = emb; c.B = d_e0; c.C = gw0; c.M = ch; c.N = E; c.K = Bn; c.sa_m = 1; c.sa_k = ch; c.sb_k = E; c.sb_n = 1; c.sc_m = 1; c.sc_n = ch; c.alpha = 1.f;
@@ -430,7 +419,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         if (train) {
             // data gradient = a 3x3 "in_conv" Cout -> ch over d_eps with flipped / transposed fp32 weights
             float* wt = at<float>(alloc((size_t)ch * Cout * 9 * 4));
-            push(pack_ops, "pack.out_conv.2.T", 0, [=](cudaStream_t st) { k_flip_transpose_w<<<(Cout * ch * 9 + 255) / 256, 256, 0, st>>>(wo, wt, Cout, ch); return (int)cudaGetLastError(); });
+            { PackEntry e; memset(&e, 0, sizeof e); e.kind = PK_FLIP_T; e.Co = Cout; e.Ci = ch; e.taps = 9; e.w = wo; e.fout = wt; pack_table_host.push_back(e); }
             tape.push_back([=]() {
                 float* gw = GP("out_conv.2.weight"); float* gb = GP("out_conv.2.bias");
                 T4 d_a = newT(B, H, W, ch);
@@ -464,6 +453,16 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             return (int)cudaMemsetAsync(Gp, 0, gbytes, st); }, 0);
         for (int i = (int)tape.size() - 1; i >= 0; --i) tape[i]();
         tape.clear();
+        unpack_table_off = alloc(sizeof(PackEntry) * (unpack_table_host.size() + 1));
+        if (!unpack_table_host.empty()) {
+            const PackEntry* tab = at<PackEntry>(unpack_table_off); const int n = (int)unpack_table_host.size();
+            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { k_pack_table<<<dim3(32, n), 256, 0, st>>>(tab); return (int)cudaGetLastError(); });
+        }
+    }
+    pack_table_off = alloc(sizeof(PackEntry) * (pack_table_host.size() + 1));
+    if (!pack_table_host.empty()) {
+        const PackEntry* tab = at<PackEntry>(pack_table_off); const int n = (int)pack_table_host.size();
+        push(pack_ops, "pack_all", 0, [=](cudaStream_t st) { k_pack_table<<<dim3(32, n), 256, 0, st>>>(tab); return (int)cudaGetLastError(); });
     }
     if (plan_error) return plan_error;
     return 0;
@@ -478,7 +477,15 @@ inline int UnetEngine::build() {
     int rc;
     if ((rc = up(tp_table_off, tp_table_host)) || (rc = up(tpw_table_off, tpw_table_host)) || (rc = up(tpd_table_off, tpd_table_host)))
         return fail(-2, "table upload failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (!pack_table_host.empty() && cudaMemcpy(ws + pack_table_off, pack_table_host.data(), pack_table_host.size() * sizeof(PackEntry), cudaMemcpyHostToDevice))
+        return fail(-2, "pack table upload failed");
+    if (!unpack_table_host.empty() && cudaMemcpy(ws + unpack_table_off, unpack_table_host.data(), unpack_table_host.size() * sizeof(PackEntry), cudaMemcpyHostToDevice))
+        return fail(-2, "unpack table upload failed");
     for (auto& r : once_list) { const cudaError_t e = cudaMemset(ws + r.first, 0, r.second); if (e) return fail(-2, "memset failed: %s", cudaGetErrorString(e)); }
+    if (!side_stream) {
+        if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) return fail(-2, "side stream creation failed");
+    }
     planned = true;
     return 0;
 }

@@ -56,6 +56,7 @@ typedef struct ddpm_gemm_desc {
     int a_estride, b_estride, b_pad;
     int seg_custom[3], seg_cmul[3]; signed char seg_dx[3][9], seg_dy[3][9];
     int o_mul, o_py, o_px;
+    int kk_splits;                     /* mode 0: split the K loop over grid_z = kk_splits CTAs per tile (fp32 atomic output) */
 } ddpm_gemm_desc;
 int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream);
 

@@ -254,3 +254,23 @@ def test_mnmn_s2_wgrad(B, h, w, splits):
     _run(d)
     _, _, dw_ref = _s2_ref(x, wt, dy)
     assert rel(out, dw_ref.permute(2, 3, 0, 1).reshape(9, Co, Ci)) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,splits", [(16, 4, 4, 8), (8, 8, 8, 4), (4, 4, 4, 5)])
+def test_kk_conv3x3_split_k(B, H, W, splits):
+    """small-M convolutions split their K loop over several CTAs (fp32 atomic partials into a zeroed scratch)."""
+    C, Co = 256, 256
+    x = bf(B, H, W, C, seed=1)
+    w = torch.randn(Co, C, 3, 3, device="cuda") * 0.05
+    wp = pack_w(w)
+    out = torch.zeros(B * H * W, Co, device="cuda")
+    d = new_desc()
+    d.mode = 0; d.M = B * H * W; d.N = Co; d.W = W; d.H = H; d.NB = B
+    d.a_ptr[0] = x.data_ptr(); d.a_C[0] = C; d.a_ld[0] = C
+    d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = C // 64; d.seg_cbase[0] = 0
+    d.b_ptr = wp.data_ptr(); d.b_K = 9 * C; d.b_rows = Co; d.b_batch = 1; d.b_ld = 9 * C
+    d.out = out.data_ptr(); d.ldo = Co; d.flags = 3; d.kk_splits = splits; d.grid_z = splits
+    _run(d)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1)
+    assert rel(out.view(B, H, W, Co).permute(0, 3, 1, 2), ref) < 2e-5
