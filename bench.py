@@ -152,10 +152,11 @@ def cpu_baseline_sample(budget_s=20.0):
             "sample": f"{n} steps of bs={bs} fwd+bwd (oracle port of the reference path, fp32, torch CPU, {torch.get_num_threads()} threads)"}
 
 
-def dominant_kernel_roofline(pk, iters=20):
+def dominant_kernel_roofline(pk, iters=30):
     """Time the dominant tcgen05 launch of the step in isolation, live, with CUDA events on the launching stream:
-    3x3 conv Ci=Co=128 at 32x32, batch 128 (7 forward + 7 dgrad launches per step share this shape; 17% of FLOPs).
-    Inputs (33.5 MB in + 33.5 MB out per launch) are rotated over 8 buffer pairs (537 MB > 126 MB L2)."""
+    3x3 conv Ci=Co=128 at 32x32, batch 128 (conv3x3_halo_kernel<128,2>; 7 forward + 7 dgrad launches per step share this
+    shape, 17% of the step's FLOPs).  Inputs (33.5 MB in + 33.5 MB out per launch) rotate over 8 buffer pairs
+    (537 MB > 126 MB L2).  achieved = 2*B*H*W*Co*9*Ci FLOPs / mean launch time."""
     import ctypes as C
     from ddpm_torch_b200 import _lib
     B, H, W, Ci, Co = 128, 32, 32, 128, 128
@@ -166,30 +167,29 @@ def dominant_kernel_roofline(pk, iters=20):
     bias = torch.zeros(Co, device="cuda")
     descs = []
     for i in range(nbuf):
-        d = _lib.GemmDesc()
-        d.mode = 0; d.M = B * H * W; d.N = Co; d.W = W; d.H = H; d.NB = B
+        d = _lib.HaloDesc()
+        d.NB, d.H, d.W, d.Cout = B, H, W, Co
         d.a_ptr[0] = xs[i].data_ptr(); d.a_C[0] = Ci; d.a_ld[0] = Ci
-        d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = Ci // 64; d.seg_cbase[0] = 0
-        d.b_ptr = w.data_ptr(); d.b_K = 9 * Ci; d.b_rows = Co; d.b_batch = 1; d.b_ld = 9 * Ci
-        d.out = ys[i].data_ptr(); d.ldo = Co; d.bias = bias.data_ptr(); d.alpha = 1.0; d.grid_z = 1
+        d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = Ci // 64
+        d.w = w.data_ptr(); d.ldw = 9 * Ci; d.Ktot = 9 * Ci; d.out = ys[i].data_ptr(); d.bias = bias.data_ptr()
         descs.append(d)
     L = _lib.lib()
     st = _lib.stream_ptr()
     for i in range(nbuf):
-        _lib.check(L.ddpm_gemm_run(C.byref(descs[i]), st))
+        _lib.check(L.ddpm_conv_halo_run(C.byref(descs[i]), st))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     for i in range(iters):
-        L.ddpm_gemm_run(C.byref(descs[i % nbuf]), st)
+        L.ddpm_conv_halo_run(C.byref(descs[i % nbuf]), st)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * B * H * W * Co * 9 * Ci
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": None,
-            "kernel": "umma_gemm_kernel<128,KK> conv3x3 128->128 @32x32 B=128 (isolated, rotating buffers > L2)",
-            "ms_per_launch": ms, "peak_source": f"{pk['src']} bf16 burst (MEASURED_PEAKS.json)"}
+            "kernel": "conv3x3_halo_kernel<128,2>: conv3x3 128->128 @32x32 B=128 (isolated, rotating buffers > L2)",
+            "ms_per_launch": ms, "gflop_per_launch": flops / 1e9, "peak_source": f"{pk['src']} bf16 burst (MEASURED_PEAKS.json)"}
 
 
 def main():

@@ -33,6 +33,17 @@ class GemmDesc(C.Structure):
     ]
 
 
+class HaloDesc(C.Structure):
+    _fields_ = [
+        ("NB", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int),
+        ("a_ptr", C.c_void_p * 3), ("a_C", C.c_int * 3), ("a_ld", C.c_longlong * 3),
+        ("nseg", C.c_int), ("seg_map", C.c_int * 3), ("seg_taps", C.c_int * 3), ("seg_kchunks", C.c_int * 3), ("seg_cbase", C.c_int * 3),
+        ("w", C.c_void_p), ("ldw", C.c_longlong), ("Ktot", C.c_int),
+        ("out", C.c_void_p), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int), ("residual", C.c_void_p),
+        ("base_offset_mode", C.c_int), ("force_sub", C.c_int),
+    ]
+
+
 class UnetCfg(C.Structure):
     _fields_ = [("in_channels", C.c_int), ("hid_channels", C.c_int), ("out_channels", C.c_int),
                 ("levels", C.c_int), ("ch_mult", C.c_int * 8), ("num_res_blocks", C.c_int), ("attn", C.c_int * 8),
@@ -58,6 +69,7 @@ def lib():
         L.ddpm_gemm_run.restype = C.c_int
         vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_uint64
         sig = {
+            "ddpm_conv_halo_run": ([C.POINTER(HaloDesc), vp], i32),
             "ddpm_unet_create": ([C.POINTER(UnetCfg), C.POINTER(vp)], i32),
             "ddpm_unet_destroy": ([vp], None),
             "ddpm_unet_num_params": ([vp], i32),
@@ -86,7 +98,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "ddpm_gemm_run",
+EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "ddpm_gemm_run", "ddpm_conv_halo_run",
            "ddpm_unet_create", "ddpm_unet_destroy", "ddpm_unet_num_params", "ddpm_unet_param_info",
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",

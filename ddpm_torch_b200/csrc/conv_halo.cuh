@@ -1,0 +1,309 @@
+// 3x3 stride-1 convolution with a HALOED input tile (tcgen05 + TMA), the kernel behind ResidualBlock conv1 / conv2(+skip)
+// and their data gradients at resolutions >= 16x16.
+//
+// The generic engine (umma_gemm.cuh) re-loads the 128-pixel A tile once per tap: 9x the activation traffic out of L2, which
+// (with the weight tile) saturates the L2->SM path at ~35% tensor-pipe utilisation.  Here a CTA owns a 16 x (8*SUB) pixel
+// patch of one image.  Per 64-channel chunk ONE 4-D TMA box {64 ch, P px, 18 rows} lands the patch plus its 1-pixel halo in
+// shared memory (rows = pixels, 128 B each, SWIZZLE_128B, row pitch P = 16 or 24 pixels; out-of-image pixels are zero-filled
+// by TMA = the conv's padding).  The A operand of tap (ky,kx) for sub-tile s is then just a UMMA descriptor into that
+// buffer: start row ky*P + kx + 8s, 8-row core matrices (8 consecutive x) with stride P*128 B between y rows.  The start is
+// then no longer 1024-B aligned; measured on B200 (tests/test_gemm_gpu.py::test_conv_halo_base_offset_probe): the
+// descriptor's base_offset must stay 0 — the 128-B swizzle is applied on absolute shared-memory address bits, which is
+// exactly how TMA wrote the rows (setting base_offset = (addr>>7)&7 gives garbage).  The 9 taps x SUB sub-tiles of a chunk therefore cost one A load; every
+// weight slab (one tap, 64 channels) is shared by the SUB sub-tiles.
+// Optional 1x1 segments (the ResidualBlock skip conv over the raw, possibly concatenated, input) ride in the same accumulator.
+#pragma once
+#include "../../include/ddpm_b200.h"
+#include "gemm_host.cuh"
+
+namespace ddpm {
+
+struct HaloSeg { int map; int taps; int kchunks; int c_base; };   // taps = 9 (haloed 3x3) or 1 (1x1, plain patch)
+
+struct HaloParams {
+    int H, W, NB;              // image geometry (H % 16 == 0, W % (8*SUB) == 0)
+    int tiles_x, tiles_y;      // patches per image
+    int n_tiles;               // Cout / BLOCK_N
+    int nseg; HaloSeg seg[3];
+    int N;                     // Cout
+    void* out; int ldo;        // bf16 NHWC
+    const float* bias; const float* rowvec; int rowvec_ld;   // rowvec: per-image vector [NB][rowvec_ld]
+    const __nv_bfloat16* residual; int ldr;
+    int desc_base_offset_mode; // 0 (default, correct): base_offset field = 0 ; 1: (start>>7)&7 (probe knob, wrong on B200)
+};
+
+template <int BLOCK_N, int SUB>
+struct HaloCfg {
+    static constexpr int P = (SUB == 1) ? 16 : 24;             // halo row pitch in pixels (multiple of 8)
+    static constexpr int A_ROWS = 18 * P;
+    static constexpr int A_BYTES = A_ROWS * 128;               // 36 KB / 54 KB
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int NA = 2;
+    static constexpr int NB_ST = (BLOCK_N == 256) ? ((SUB == 1) ? 4 : 3) : ((SUB == 1) ? 8 : 6);
+    static constexpr int NACC = (2 * SUB * BLOCK_N <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (NACC * SUB * BLOCK_N <= 128) ? 128 : ((NACC * SUB * BLOCK_N <= 256) ? 256 : 512);
+    static constexpr int TOTAL = NA * A_BYTES + NB_ST * B_BYTES + 1024 + 512;
+};
+
+// descriptor with explicit base offset (bits 49..51)
+__device__ __forceinline__ uint64_t umma_smem_desc_bo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
+    return umma_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)(base_off & 7) << 49);
+}
+
+template <int BLOCK_N, int SUB>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+    using CF = HaloCfg<BLOCK_N, SUB>;
+    constexpr int P = CF::P;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + CF::NA * CF::A_BYTES;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smB + CF::NB_ST * CF::B_BYTES);
+    uint64_t* empty_a = full_a + CF::NA;
+    uint64_t* full_b = empty_a + CF::NA;
+    uint64_t* empty_b = full_b + CF::NB_ST;
+    uint64_t* tmem_full = empty_b + CF::NB_ST;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int m_tiles = p.NB * tiles_per_img;
+    const int total_tiles = m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
+        for (int s = 0; s < CF::NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < CF::NB_ST; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, CF::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int ia = 0, ib = 0;
+            bool ok = true;
+            for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+                const int m_tile = t % m_tiles, n_tile = t / m_tiles;
+                const int n = m_tile / tiles_per_img, r = m_tile % tiles_per_img;
+                const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8 * SUB;
+                int kbase = 0;                       // running K coordinate of the packed weights
+                for (int s = 0; s < p.nseg && ok; ++s) {
+                    const HaloSeg sg = p.seg[s];
+                    const CUtensorMap* mA = sg.map == 0 ? &tmA0 : (sg.map == 1 ? &tmA1 : &tmA2);
+                    const int Cseg = sg.kchunks * 64;
+                    for (int kc = 0; kc < sg.kchunks && ok; ++kc) {
+                        {   // activation patch (+halo for the 3x3 segment)
+                            const int sa = ia % CF::NA; const uint32_t ph = (ia / CF::NA) & 1;
+                            if (!mbar_wait(&empty_a[sa], ph ^ 1, 5)) { ok = false; break; }
+                            const uint32_t bytes = (sg.taps == 9) ? (uint32_t)CF::A_BYTES : (uint32_t)(16 * 8 * SUB * 128);
+                            mbar_expect_tx(&full_a[sa], bytes);
+                            if (sg.taps == 9) tma_load_4d(smA + sa * CF::A_BYTES, mA, &full_a[sa], sg.c_base + kc * 64, x0 - 1, y0 - 1, n);
+                            else              tma_load_4d(smA + sa * CF::A_BYTES, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
+                            ++ia;
+                        }
+                        for (int tp = 0; tp < sg.taps; ++tp) {
+                            const int sb = ib % CF::NB_ST; const uint32_t ph = (ib / CF::NB_ST) & 1;
+                            if (!mbar_wait(&empty_b[sb], ph ^ 1, 6)) { ok = false; break; }
+                            mbar_expect_tx(&full_b[sb], CF::B_BYTES);
+                            tma_load_3d(smB + sb * CF::B_BYTES, &tmB, &full_b[sb], kbase + tp * Cseg + kc * 64, n_tile * BLOCK_N, 0);
+                            ++ib;
+                        }
+                    }
+                    kbase += sg.taps * Cseg;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, 0, 0);
+            int ia = 0, ib = 0, it = 0;
+            bool ok = true;
+            for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++it) {
+                const int acc = (CF::NACC == 2) ? (it & 1) : 0;
+                const uint32_t acc_ph = (CF::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
+                if (!mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 4)) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SUB * BLOCK_N);
+                bool first = true;
+                for (int s = 0; s < p.nseg && ok; ++s) {
+                    const HaloSeg sg = p.seg[s];
+                    for (int kc = 0; kc < sg.kchunks && ok; ++kc) {
+                        const int sa = ia % CF::NA; const uint32_t pha = (ia / CF::NA) & 1;
+                        if (!mbar_wait(&full_a[sa], pha, 7)) { ok = false; break; }
+                        const uint32_t a_base = smem_u32(smA + sa * CF::A_BYTES);
+                        for (int tp = 0; tp < sg.taps; ++tp) {
+                            const int sb = ib % CF::NB_ST; const uint32_t phb = (ib / CF::NB_ST) & 1;
+                            if (!mbar_wait(&full_b[sb], phb, 2)) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(smB + sb * CF::B_BYTES);
+                            // haloed patch: row (y+ky)*P + (x+kx+8s) ; plain 1x1 patch: row y*(8*SUB) + x + 8s
+                            const int pitch = (sg.taps == 9) ? P : 8 * SUB;
+                            const int row0 = (sg.taps == 9) ? (tp / 3) * P + (tp % 3) : 0;
+#pragma unroll
+                            for (int sub = 0; sub < SUB; ++sub) {
+                                const uint32_t a_row = a_base + (uint32_t)(row0 + 8 * sub) * 128u;
+                                const uint32_t bo = p.desc_base_offset_mode ? ((a_row >> 7) & 7u) : 0u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t da = umma_smem_desc_bo(a_row + k * 32, 16, (uint32_t)pitch * 128u, bo);
+                                    const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                                    umma_bf16(d_tmem + (uint32_t)(sub * BLOCK_N), da, db, idesc, (first && k == 0) ? 0u : 1u);
+                                }
+                            }
+                            first = false;
+                            umma_commit(&empty_b[sb]);
+                            ++ib;
+                        }
+                        umma_commit(&empty_a[sa]);
+                        ++ia;
+                    }
+                }
+                if (ok) umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ======================= epilogue =======================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // accumulator row = pixel (y = r/8, x = r%8) of the sub-tile
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int m_tile = t % m_tiles, n_tile = t / m_tiles;
+            const int n = m_tile / tiles_per_img, rr = m_tile % tiles_per_img;
+            const int y0 = (rr / p.tiles_x) * 16, x0 = (rr % p.tiles_x) * 8 * SUB;
+            const int acc = (CF::NACC == 2) ? (it & 1) : 0;
+            const uint32_t acc_ph = (CF::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
+            if (!mbar_wait(&tmem_full[acc], acc_ph, 3)) break;
+            tc_fence_after();
+            const float* rv = p.rowvec ? p.rowvec + (long long)n * p.rowvec_ld : nullptr;
+#pragma unroll 1
+            for (int sub = 0; sub < SUB; ++sub) {
+                const long long pix = ((long long)n * p.H + y0 + (r >> 3)) * p.W + x0 + 8 * sub + (r & 7);
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * SUB * BLOCK_N + sub * BLOCK_N);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    const int col = n_tile * BLOCK_N + c0;
+                    if (col >= p.N) break;
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
+                    }
+                    if (rv) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + col) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
+                    }
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + col);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const uint4 u = __ldg(rp + j4);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 t2 = __bfloat1622float2(h[e]);
+                                f[j4 * 8 + e * 2] += t2.x; f[j4 * 8 + e * 2 + 1] += t2.y;
+                            }
+                        }
+                    }
+                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                        o[j] = u;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, CF::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct HaloLaunch { CUtensorMap a[3], b; HaloParams p; int block_n, sub; int tiles; double flops; };
+
+typedef ddpm_halo_desc HaloDesc;   // the C-ABI struct doubles as the internal description
+
+inline bool halo_eligible(int H, int W, int Cout) { return H % 16 == 0 && W % 8 == 0 && Cout % 64 == 0 && H >= 16 && W >= 8; }
+
+inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
+    memset(&g, 0, sizeof g);
+    if (!halo_eligible(d.H, d.W, d.Cout)) return fail(-12, "halo conv: unsupported geometry %dx%d Cout=%d", d.H, d.W, d.Cout);
+    g.block_n = pick_block_n(d.Cout);
+    int sub = (d.W % 16 == 0 && 2 * g.block_n <= 512 && g.block_n <= 128) ? 2 : 1;   // two sub-tiles when TMEM can double-buffer them
+    if (d.W % 16 == 0 && g.block_n == 256) sub = 1;
+    if (d.force_sub == 1 || d.force_sub == 2) sub = d.force_sub;
+    if (sub == 2 && d.W % 16) return fail(-12, "halo conv: SUB=2 needs W %% 16 == 0");
+    g.sub = sub;
+    HaloParams& p = g.p;
+    p.H = d.H; p.W = d.W; p.NB = d.NB; p.tiles_x = d.W / (8 * sub); p.tiles_y = d.H / 16; p.n_tiles = (d.Cout + g.block_n - 1) / g.block_n;
+    p.N = d.Cout; p.out = d.out; p.ldo = d.Cout; p.bias = d.bias; p.rowvec = d.rowvec; p.rowvec_ld = d.rowvec_ld;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual); p.ldr = d.Cout; p.desc_base_offset_mode = d.base_offset_mode;
+    p.nseg = d.nseg;
+    const int P = sub == 1 ? 16 : 24;
+    int rc;
+    for (int s = 0; s < d.nseg; ++s) {
+        p.seg[s] = HaloSeg{d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]};
+        const int m = d.seg_map[s];
+        if (d.seg_taps[s] == 9) { if ((rc = make_tmap_4d(&g.a[m], d.a_ptr[m], d.a_C[m], d.W, d.H, d.NB, d.a_ld[m], 64, P, 18, 1))) return rc; }
+        else                    { if ((rc = make_tmap_4d(&g.a[m], d.a_ptr[m], d.a_C[m], d.W, d.H, d.NB, d.a_ld[m], 64, 8 * sub, 16, 1))) return rc; }
+    }
+    for (int i = 0; i < 3; ++i) { bool used = false; for (int s = 0; s < d.nseg; ++s) used |= d.seg_map[s] == i; if (!used) g.a[i] = g.a[d.seg_map[0]]; }
+    if ((rc = make_tmap_3d(&g.b, d.w, d.Ktot, d.Cout, 1, d.ldw, 0, 64, g.block_n))) return rc;
+    g.tiles = d.NB * p.tiles_x * p.tiles_y * p.n_tiles;
+    g.flops = 2.0 * d.NB * d.H * d.W * (double)d.Cout * d.Ktot;
+    return 0;
+}
+
+template <int BLOCK_N, int SUB>
+inline int launch_halo_inst(const HaloLaunch& g, cudaStream_t st) {
+    using CF = HaloCfg<BLOCK_N, SUB>;
+    auto kern = conv3x3_halo_kernel<BLOCK_N, SUB>;
+    static bool attr_done = false;
+    if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL)); attr_done = true; }
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int ctas = g.tiles < num_sms ? g.tiles : num_sms;
+    kern<<<ctas, 192, CF::TOTAL, st>>>(g.a[0], g.a[1], g.a[2], g.b, g.p);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+inline int launch_halo(const HaloLaunch& g, cudaStream_t st) {
+    if (g.block_n == 64 && g.sub == 1) return launch_halo_inst<64, 1>(g, st);
+    if (g.block_n == 64 && g.sub == 2) return launch_halo_inst<64, 2>(g, st);
+    if (g.block_n == 128 && g.sub == 1) return launch_halo_inst<128, 1>(g, st);
+    if (g.block_n == 128 && g.sub == 2) return launch_halo_inst<128, 2>(g, st);
+    if (g.block_n == 256 && g.sub == 1) return launch_halo_inst<256, 1>(g, st);
+    if (g.block_n == 256 && g.sub == 2) return launch_halo_inst<256, 2>(g, st);
+    return fail(-6, "unsupported halo conv variant");
+}
+
+}  // namespace ddpm

@@ -43,6 +43,13 @@ int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream) {
     return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream) {
+    HaloLaunch g;
+    int rc = build_halo(*d, g);
+    if (rc) return rc;
+    return launch_halo(g, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ UNet engine
 int ddpm_unet_create(const ddpm_unet_cfg* cfg, ddpm_unet** out) {
     if (!cfg || !out) return fail(-30, "null argument");

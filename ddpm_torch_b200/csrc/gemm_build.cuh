@@ -15,7 +15,7 @@ inline GemmSeg make_seg(int map, int taps, int kchunks, int c_base) {
 
 inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     memset(&g, 0, sizeof g);
-    g.mode = d.mode;
+    g.mode = d.mode; g.cluster = 1;
     g.block_n = d.block_n ? d.block_n : pick_block_n(d.N);
     if (g.block_n != 64 && g.block_n != 128 && g.block_n != 256) return fail(-10, "block_n must be 64/128/256");
     if (d.N % 32) return fail(-10, "N=%d must be a multiple of 32", d.N);
@@ -33,6 +33,7 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     const int gz = d.grid_z > 0 ? d.grid_z : 1;
     const int n_tiles = (d.N + g.block_n - 1) / g.block_n;
     const int m_tiles = (d.M + 127) / 128;
+    { static const int dbg = getenv("DDPM_GEMM_DBG") ? atoi(getenv("DDPM_GEMM_DBG")) : 0; p.dbg = dbg; }
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.grid_z = gz; p.kk_splits = d.kk_splits > 1 ? d.kk_splits : 1;
     if (p.kk_splits > 1 && (d.mode != GEMM_KK || gz != p.kk_splits || !(d.flags & EPI_ATOMIC))) return fail(-10, "kk_splits needs mode 0, grid_z == kk_splits and the atomic fp32 epilogue");
     g.grid = dim3(m_tiles * n_tiles * gz, 1, 1);   // clipped to the SM count at launch (persistent CTAs)
@@ -58,7 +59,11 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
             if (!d.a_ptr[i]) { g.a[i] = g.a[0]; continue; }
             if ((rc = make_tmap_4d(&g.a[i], d.a_ptr[i], d.a_C[i], d.W * aes, d.H * aes, d.NB, d.a_ld[i], 64, p.w_t, p.h_t, p.n_t, aes))) return rc;
         }
-        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n))) return rc;
+        // thread-block clusters of CTAs with consecutive m_tiles share (multicast) the weight tile
+        g.cluster = 1;
+        for (int cl = gemm_max_cluster(); cl > 1; cl >>= 1)
+            if (m_tiles % cl == 0 && (g.block_n / cl) % 8 == 0 && m_tiles * n_tiles * gz >= 2 * cl) { g.cluster = cl; break; }
+        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n / g.cluster))) return rc;
         g.flops = 2.0 * d.M * d.N * 64.0 * slabs * gz;
     } else if (d.mode == GEMM_MNMN) {
         if (!pick_box(d.W, d.H, 64, p.wk_t, p.hk_t, p.nk_t)) return fail(-11, "MNMN: unsupported geometry W=%d H=%d", d.W, d.H);

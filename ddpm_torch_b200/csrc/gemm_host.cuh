@@ -85,17 +85,20 @@ struct GemmLaunch {
     GemmParams p;
     dim3 grid;
     int mode, block_n;
+    int cluster;            // 1, 2 or 4 (KK with m_tiles % cluster == 0): the B map's box holds block_n / cluster rows
     double flops;
 };
+// multicast clusters measured no faster than unicast on B200 (L2 traffic is not the limiter) -> default off
+inline int gemm_max_cluster() { static const int v = getenv("DDPM_GEMM_CLUSTER") ? atoi(getenv("DDPM_GEMM_CLUSTER")) : 1; return v; }
 
 // Pipeline depth: "deep" = one CTA per SM with 4-8 stages; "shallow" (DDPM_GEMM_SHALLOW=1) = 2-4 stages so that two
 // CTAs are co-resident per SM and one's epilogue overlaps the other's main loop (A/B experiment knob).
 inline bool gemm_shallow() { static const bool v = getenv("DDPM_GEMM_SHALLOW") != nullptr; return v; }
 
-template <int BLOCK_N, int MODE, int STAGES>
-inline int launch_gemm_inst2(const GemmLaunch& g, cudaStream_t st) {
-    using SM = GemmSmem<BLOCK_N, STAGES>;
-    auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES>;
+template <int BLOCK_N, int MODE, int STAGES, int CLUSTER, int KSTEPS>
+inline int launch_gemm_inst3(const GemmLaunch& g, cudaStream_t st) {
+    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS>;
+    auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES, CLUSTER, KSTEPS>;
     static bool attr_done = false;
     if (!attr_done) {
         DDPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
@@ -106,17 +109,35 @@ inline int launch_gemm_inst2(const GemmLaunch& g, cudaStream_t st) {
     // persistent: one CTA per SM (two when two fit: <= 96 KB of stages and 2 x 2*BLOCK_N <= 512 TMEM columns)
     const int per_sm = (SM::TOTAL <= 110 * 1024 && 4 * BLOCK_N <= 512) ? 2 : 1;
     int ctas = (int)g.grid.x; if (ctas > num_sms * per_sm) ctas = num_sms * per_sm;
+    if (CLUSTER > 1) {
+        ctas = ctas / CLUSTER * CLUSTER;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        DDPM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.a[0], g.a[1], g.a[2], g.b, g.p));
+        return 0;
+    }
     kern<<<ctas, 192, SM::TOTAL, st>>>(g.a[0], g.a[1], g.a[2], g.b, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }
+template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
+inline int launch_gemm_inst2(const GemmLaunch& g, cudaStream_t st) {
+    if (MODE == GEMM_KK) {
+        if (g.cluster == 4) return launch_gemm_inst3<BLOCK_N, GEMM_KK, STAGES, 4, KSTEPS>(g, st);
+        if (g.cluster == 2) return launch_gemm_inst3<BLOCK_N, GEMM_KK, STAGES, 2, KSTEPS>(g, st);
+    }
+    return launch_gemm_inst3<BLOCK_N, MODE, STAGES, 1, KSTEPS>(g, st);
+}
 template <int BLOCK_N, int MODE>
 inline int launch_gemm_inst(const GemmLaunch& g, cudaStream_t st) {
-    // N=256: 4 stages x 48 KB, one CTA per SM.  N<=128: 3-4 stages (<= 96 KB) so TWO CTAs share an SM and one's epilogue
-    // overlaps the other's main loop (measured on the dominant 128x128 conv: 508 -> 696 TFLOP/s).
-    constexpr int DEEP = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    constexpr int SHALLOW = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
-    return gemm_shallow() ? launch_gemm_inst2<BLOCK_N, MODE, SHALLOW>(g, st) : launch_gemm_inst2<BLOCK_N, MODE, DEEP>(g, st);
+    // One persistent CTA per SM, ~192 KB of stages; TMEM double buffering overlaps the epilogue.
+    //   N=256: 4 stages x 1 slab (48 KB);  N=128: 3 stages x 2 slabs (64 KB);  N=64: 4 stages x 2 slabs (48 KB)
+    // DDPM_GEMM_SHALLOW=1 selects the one-slab-per-stage variants for N<=128 (A/B experiment knob).
+    if (BLOCK_N == 256) return launch_gemm_inst2<BLOCK_N, MODE, 4, 1>(g, st);
+    if (gemm_shallow()) return launch_gemm_inst2<BLOCK_N, MODE, (BLOCK_N == 128 ? 6 : 8), 1>(g, st);
+    return launch_gemm_inst2<BLOCK_N, MODE, (BLOCK_N == 128 ? 3 : 4), 2>(g, st);
 }
 
 inline int launch_gemm(const GemmLaunch& g, cudaStream_t st) {

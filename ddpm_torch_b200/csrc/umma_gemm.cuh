@@ -42,6 +42,8 @@ struct GemmParams {
     int o_mul, o_py, o_px, oW, oH;
     int m_tiles, n_tiles, grid_z;   // tile space walked by the persistent CTAs
     int kk_splits;                  // KK: > 1 -> z is a K-split index over the flattened (segment, tap, chunk) slab sequence
+    int dbg;                        // bottleneck experiments (DDPM_GEMM_DBG): 1 = epilogue drains TMEM but does no math/stores,
+                                    // 2 = MMA warp consumes stages without issuing MMAs, 4 = producer signals stages without TMA loads
     // epilogue
     void* out; int ldo; long long out_z_stride; long long out_tap_stride; int flags;
     const float* bias;        // [N] or null
@@ -51,11 +53,16 @@ struct GemmParams {
     float alpha;
 };
 
-template <int BLOCK_N, int STAGES>
+// A pipeline stage holds KSTEPS K-slabs of 64 (KSTEPS x {A 16 KB, B BLOCK_N x 128 B}).  One producer/consumer handshake costs
+// ~400 cycles of dependent mbarrier / TMA-issue / commit instructions on the single issuing threads (measured: the kernel with
+// loads, MMAs and epilogue math disabled still ran at 52% of its full time), more than the 256-cycle MMA time of one N=128
+// slab - so N <= 128 configurations move two slabs per handshake.
+template <int BLOCK_N, int STAGES, int KSTEPS = 1>
 struct GemmSmem {
     static constexpr int A_BYTES = 128 * 64 * 2;
     static constexpr int B_BYTES = BLOCK_N * 64 * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SLAB_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = KSTEPS * SLAB_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -71,12 +78,14 @@ __device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& 
 //   t -> (m_tile fastest, n_tile, z) so that CTAs running concurrently share the same weight (B) tile in L2.
 // TMEM holds TWO accumulator buffers (2 x BLOCK_N columns): the epilogue warps drain buffer i while the MMA warp already
 // accumulates tile i+1 into the other one; the TMA producer runs ahead across tile boundaries.
-template <int BLOCK_N, int MODE, int STAGES>
+// CLUSTER > 1 (KK only): CLUSTER CTAs with consecutive m_tiles (same weight tile) form a thread-block cluster; each loads
+// 1/CLUSTER of the B tile and multicasts it to all of them, so the weight traffic out of L2 drops by CLUSTER.
+template <int BLOCK_N, int MODE, int STAGES, int CLUSTER, int KSTEPS>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-    using SM = GemmSmem<BLOCK_N, STAGES>;
+    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS>;
     constexpr int A_MN = (MODE == GEMM_MNMN) ? 1 : 0;
     constexpr int B_MN = (MODE == GEMM_KK) ? 0 : 1;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
@@ -112,32 +121,48 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         return kb1 > kb0 ? kb1 - kb0 : 0;
     };
 
+    static_assert(CLUSTER == 1 || MODE == GEMM_KK, "multicast clusters are implemented for the KK mode only");
+    const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();            // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ======================= TMA producer =======================
         if (lane == 0) {
-            int slab = 0;
+            int stg = 0;                              // global stage counter
+            int sub = 0;                              // slabs already issued into the current stage
+            int left = 0;                             // slabs of the current tile not yet issued
             bool ok = true;
-            auto acquire = [&](int sl) -> uint8_t* {
-                const int st = sl % STAGES;
-                const uint32_t ph = (sl / STAGES) & 1;
-                if (!mbar_wait(&empty_bar[st], ph ^ 1, 1)) { ok = false; return nullptr; }
-                mbar_expect_tx(&full_bar[st], SM::STAGE_BYTES);
-                return smem + st * SM::STAGE_BYTES;
+            uint64_t* fb = nullptr;
+            // acquire the slot for the next slab (waits for the stage when it starts one); returns the slab's smem base
+            auto acquire = [&](int) -> uint8_t* {
+                const int st = stg % STAGES;
+                if (sub == 0) {
+                    const uint32_t ph = (stg / STAGES) & 1;
+                    if (!mbar_wait(&empty_bar[st], ph ^ 1, 1)) { ok = false; return nullptr; }
+                }
+                fb = &full_bar[st];
+                return smem + st * SM::STAGE_BYTES + sub * SM::SLAB_BYTES;
+            };
+            // after the loads of a slab were issued: arm the barrier when the stage is complete (or the tile ends)
+            auto commit_slab = [&]() {
+                ++sub; --left;
+                if (sub == KSTEPS || left == 0) { mbar_expect_tx(fb, (uint32_t)(sub * SM::SLAB_BYTES)); sub = 0; ++stg; }
             };
             for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
                 const int m_tile = t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
+                left = slabs_of(z); sub = 0;
                 if (MODE == GEMM_KK) {
                     int n0, y0, x0;
                     pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
@@ -153,12 +178,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             const int yc = y0 * sg.cmul + sg.dy[tp];
                             for (int kc = 0; kc < sg.kchunks; ++kc, ++kcount) {
                                 if (kcount < k_lo || kcount >= k_hi) continue;
-                                uint8_t* st = acquire(slab);
+                                uint8_t* st = acquire(0);
                                 if (!st) break;
-                                uint64_t* fb = &full_bar[slab % STAGES];
+                                if (p.dbg & 4) { asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(fb)), "r"((uint32_t)SM::SLAB_BYTES) : "memory"); commit_slab(); continue; }
                                 tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
-                                tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
-                                ++slab;
+                                if (CLUSTER == 1) {
+                                    tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+                                } else {
+                                    constexpr int ROWS = BLOCK_N / CLUSTER;        // this CTA's slice of the weight tile
+                                    tma_load_3d_mc(st + SM::A_BYTES + crank * ROWS * 128, &tmB, fb, p.b_k_base + kcount * 64,
+                                                   n_tile * BLOCK_N + crank * ROWS, z * p.b_z, CMASK);
+                                }
+                                commit_slab();
                             }
                         }
                     }
@@ -168,10 +199,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const int ns = slabs_of(z);
                     const int dx = p.taps == 9 ? (tap % 3) - p.b_pad : 0;
                     const int dy = p.taps == 9 ? (tap / 3) - p.b_pad : 0;
-                    for (int i = 0; i < ns; ++i, ++slab) {
-                        uint8_t* st = acquire(slab);
+                    for (int i = 0; i < ns; ++i) {
+                        uint8_t* st = acquire(0);
                         if (!st) break;
-                        uint64_t* fb = &full_bar[slab % STAGES];
                         int n0, y0, x0;
                         pix_decompose((kb0 + i) * 64, p.W, p.H, n0, y0, x0);
                         n0 += batch;
@@ -182,19 +212,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         for (int b = 0; b < BLOCK_N / 64; ++b)
                             tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64,
                                         x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
+                        commit_slab();
                     }
                 } else {  // GEMM_KMN
                     int n0, y0, x0;
                     pix_decompose(m_tile * 128, p.W, p.H, n0, y0, x0);
                     n0 += z * p.a_z_n;
-                    for (int i = 0; i < p.kblocks; ++i, ++slab) {
-                        uint8_t* st = acquire(slab);
+                    for (int i = 0; i < p.kblocks; ++i) {
+                        uint8_t* st = acquire(0);
                         if (!st) break;
-                        uint64_t* fb = &full_bar[slab % STAGES];
                         tma_load_4d(st, &tmA0, fb, p.a_c_base + i * 64, x0, y0, n0);
 #pragma unroll
                         for (int b = 0; b < BLOCK_N / 64; ++b)
                             tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64, i * 64, 0, z);
+                        commit_slab();
                     }
                 }
             }
@@ -203,7 +234,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ======================= MMA issuer =======================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, A_MN, B_MN);
-            int slab = 0, it = 0;
+            int stg = 0, it = 0;
             bool ok = true;
             for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++it) {
                 const int z = t / (m_tiles * n_tiles);
@@ -213,23 +244,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (!mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 4)) break;      // epilogue has drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int i = 0; i < ns; ++i, ++slab) {
-                    const int st = slab % STAGES;
-                    const uint32_t ph = (slab / STAGES) & 1;
+                for (int i = 0; i < ns; i += KSTEPS, ++stg) {
+                    const int st = stg % STAGES;
+                    const uint32_t ph = (stg / STAGES) & 1;
                     if (!mbar_wait(&full_bar[st], ph, 2)) { ok = false; break; }
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + st * SM::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + SM::A_BYTES;
+                    const int nsub = (ns - i) < KSTEPS ? (ns - i) : KSTEPS;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // K-major: 16 elements = 32 B inside the swizzle span; MN-major: 16 K-rows of 128 B
-                        const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                                 : umma_smem_desc(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                                 : umma_smem_desc(b_addr + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (i | k) != 0);
+                    for (int sb = 0; sb < KSTEPS; ++sb) {
+                        if (sb >= nsub) break;
+                        const uint32_t a_addr = smem_u32(smem + st * SM::STAGE_BYTES + sb * SM::SLAB_BYTES);
+                        const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // K-major: 16 elements = 32 B inside the swizzle span; MN-major: 16 K-rows of 128 B
+                            const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                                     : umma_smem_desc(a_addr + k * 32, 16, 1024);
+                            const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                                     : umma_smem_desc(b_addr + k * 32, 16, 1024);
+                            if (!(p.dbg & 2)) umma_bf16(d_tmem, da, db, idesc, (i | sb | k) != 0);
+                        }
                     }
-                    umma_commit(&empty_bar[st]);
+                    if (CLUSTER == 1) umma_commit(&empty_bar[st]); else umma_commit_mc(&empty_bar[st], CMASK);
                 }
                 if (ok) umma_commit(&tmem_full[acc]);
             }
@@ -267,17 +303,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 uint32_t v[32];
                 tmem_ld32(t_addr + (uint32_t)c0, v);
                 tmem_ld_wait();
-                if (!row_ok) continue;
+                if (!row_ok || (p.dbg & 1)) continue;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
                 if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col + j);
+                    for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+                        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
                 }
                 if (rv) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + col + j);
+                    for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + col) + j);
+                        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
                 }
                 if (p.residual) {
                     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
@@ -322,6 +360,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();            // no peer may still multicast data / arrivals into this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "gemm_build.cuh"
+#include "conv_halo.cuh"
 #include "kernels_simt.cuh"
 
 namespace ddpm {
@@ -135,6 +136,30 @@ struct UnetEngine {
         bool tc = (c.stride == 1 || s2) && c.map == MAP_NORMAL && !c.out_nchw && !c.in.two && (i0.C % 64 == 0) && (c.Co % 64 == 0) &&
                   (s2 || (c.Ho == i0.H && c.Wo == i0.W)) && tc_ok_geom(c.Ho, c.Wo) && !(c.accumulate && c.residual);
         if (c.has_skip) tc = tc && (c.skip_in.t0.C % 64 == 0) && (!c.skip_in.two || c.skip_in.t1.C % 64 == 0);
+        static const bool no_halo = getenv("DDPM_NO_HALO") != nullptr;
+        if (tc && !no_halo && c.ksize == 3 && c.stride == 1 && halo_eligible(c.Ho, c.Wo, c.Co)) {
+            ddpm_halo_desc h; memset(&h, 0, sizeof h);
+            h.NB = Bn; h.H = c.Ho; h.W = c.Wo; h.Cout = c.Co;
+            h.a_ptr[0] = bp(i0); h.a_C[0] = i0.C; h.a_ld[0] = i0.C;
+            h.nseg = 1; h.seg_map[0] = 0; h.seg_taps[0] = 9; h.seg_kchunks[0] = i0.C / 64; h.seg_cbase[0] = 0;
+            long long K = 9LL * Cin;
+            if (c.has_skip) {
+                h.a_ptr[1] = bp(c.skip_in.t0); h.a_C[1] = c.skip_in.t0.C; h.a_ld[1] = c.skip_in.t0.C;
+                h.seg_map[1] = 1; h.seg_taps[1] = 1; h.seg_kchunks[1] = c.skip_in.t0.C / 64; h.seg_cbase[1] = 0; h.nseg = 2; K += c.skip_in.t0.C;
+                if (c.skip_in.two) {
+                    h.a_ptr[2] = bp(c.skip_in.t1); h.a_C[2] = c.skip_in.t1.C; h.a_ld[2] = c.skip_in.t1.C;
+                    h.seg_map[2] = 2; h.seg_taps[2] = 1; h.seg_kchunks[2] = c.skip_in.t1.C / 64; h.seg_cbase[2] = 0; h.nseg = 3; K += c.skip_in.t1.C;
+                }
+            }
+            h.w = c.wp; h.ldw = c.ldw; h.Ktot = (int)K; h.out = bp(c.out); h.bias = c.bias; h.rowvec = c.rowvec; h.rowvec_ld = c.rowvec_ld;
+            h.residual = c.accumulate ? (const void*)bp(c.out) : (const void*)c.residual; h.base_offset_mode = 0;
+            ++n_tc_gemms;
+            if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return; }
+            HaloLaunch g; int rc = build_halo(h, g);
+            if (rc) { plan_error = rc; return; }
+            push(L, c.name + "[halo]", fl, [g](cudaStream_t st) { return launch_halo(g, st); });
+            return;
+        }
         if (tc) {
             ddpm_gemm_desc d; memset(&d, 0, sizeof d);
             d.mode = GEMM_KK; d.M = (int)Pout; d.N = c.Co; d.W = c.Wo; d.H = c.Ho; d.NB = Bn;

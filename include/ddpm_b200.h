@@ -60,6 +60,22 @@ typedef struct ddpm_gemm_desc {
 } ddpm_gemm_desc;
 int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream);
 
+/* Low-level operator: 3x3 stride-1 convolution (+ optional fused 1x1 segments) with a haloed shared-memory input tile
+ * (csrc/conv_halo.cuh) — the kernel behind ResidualBlock.conv1 / conv2(+skip) (unet.py:76,79,80) at resolutions >= 16x16.
+ * a_ptr/a_C/a_ld: up to 3 NHWC bf16 inputs; segment s reads map seg_map[s] with seg_taps[s] in {9 (3x3, pad 1), 1 (1x1)},
+ * seg_kchunks[s] chunks of 64 channels starting at channel seg_cbase[s]; w: packed bf16 [Cout][ldw], K order = segments,
+ * then tap, then channel; out: NHWC bf16 [NB,H,W,Cout] = conv + bias + rowvec[image] + residual. */
+typedef struct ddpm_halo_desc {
+    int NB, H, W, Cout;
+    const void* a_ptr[3]; int a_C[3]; long long a_ld[3];
+    int nseg; int seg_map[3], seg_taps[3], seg_kchunks[3], seg_cbase[3];
+    const void* w; long long ldw; int Ktot;
+    void* out; const float* bias; const float* rowvec; int rowvec_ld; const void* residual;
+    int base_offset_mode;              /* 0 = descriptor base_offset field left 0 (correct on B200); 1 = (addr>>7)&7 (probe) */
+    int force_sub;                     /* 0 = auto; 1 / 2 = number of 16x8 sub-tiles per CTA */
+} ddpm_halo_desc;
+int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * UNet engine.  replaces: UNet.__init__/forward (ddpm_torch/models/unet.py:96-233), its autograd backward,
  * and the model-side half of GaussianDiffusion.train_losses / p_sample_step (diffusion.py:107-158,217-243).

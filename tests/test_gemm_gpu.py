@@ -274,3 +274,66 @@ def test_kk_conv3x3_split_k(B, H, W, splits):
     torch.backends.cudnn.allow_tf32 = False
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1)
     assert rel(out.view(B, H, W, Co).permute(0, 3, 1, 2), ref) < 2e-5
+
+
+# ---------------------------------------------------------------------------- haloed 3x3 conv kernel (csrc/conv_halo.cuh)
+def _halo_run(d):
+    from ddpm_torch_b200 import _lib
+    _lib.check(_lib.lib().ddpm_conv_halo_run(C.byref(d), _lib.stream_ptr()), "conv_halo_run")
+    torch.cuda.synchronize()
+    assert _lib.lib().ddpm_device_error_flag() == 0
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 16), (1, 64, 64), (2, 16, 8)])
+@pytest.mark.parametrize("Cout,sub", [(64, 1), (64, 2), (128, 1), (128, 2), (256, 1), (256, 2)])
+def test_conv_halo_concat_skip(B, H, W, Cout, sub):
+    from ddpm_torch_b200._lib import HaloDesc
+    if sub == 2 and W % 16:
+        pytest.skip("SUB=2 needs W % 16 == 0")
+    Cin, C1, C2 = 128, 64, 128
+    a2 = bf(B, H, W, Cin, seed=1)                                        # main 3x3 input
+    x1 = bf(B, H, W, C1, seed=2); x2 = bf(B, H, W, C2, seed=3)           # raw concat sources of the fused 1x1 skip
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    ws = torch.randn(Cout, C1 + C2, 1, 1, device="cuda") * 0.1
+    wp = torch.cat([pack_w(w), pack_w(ws)], dim=1).contiguous()
+    bias = torch.randn(Cout, device="cuda"); temb = torch.randn(B, Cout, device="cuda")
+    res = bf(B, H, W, Cout, seed=4)
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = HaloDesc()
+    d.NB, d.H, d.W, d.Cout = B, H, W, Cout
+    for i, (t, c) in enumerate(((a2, Cin), (x1, C1), (x2, C2))):
+        d.a_ptr[i] = t.data_ptr(); d.a_C[i] = c; d.a_ld[i] = c
+    d.nseg = 3
+    for i, (taps, kc) in enumerate(((9, Cin // 64), (1, C1 // 64), (1, C2 // 64))):
+        d.seg_map[i] = i; d.seg_taps[i] = taps; d.seg_kchunks[i] = kc; d.seg_cbase[i] = 0
+    d.w = wp.data_ptr(); d.ldw = wp.shape[1]; d.Ktot = wp.shape[1]
+    d.out = out.data_ptr(); d.bias = bias.data_ptr(); d.rowvec = temb.data_ptr(); d.rowvec_ld = Cout; d.residual = res.data_ptr()
+    d.base_offset_mode = 0; d.force_sub = sub
+    _halo_run(d)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(a2.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1) + temb[:, :, None, None] \
+        + F.conv2d(torch.cat([x1, x2], -1).float().permute(0, 3, 1, 2), ws.to(torch.bfloat16).float()) + res.float().permute(0, 3, 1, 2)
+    assert rel(out.float().permute(0, 3, 1, 2), ref) < 4e-3
+
+
+def test_conv_halo_base_offset_probe():
+    """Documents the descriptor behaviour the kernel relies on: for start rows that are not 1024-B aligned the base_offset
+    field must stay 0 (swizzle on absolute smem address bits); base_offset=(addr>>7)&7 produces garbage on B200."""
+    from ddpm_torch_b200._lib import HaloDesc
+    B, H, W, Cin, Cout = 2, 16, 16, 64, 64
+    x = bf(B, H, W, Cin, seed=1); w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    wp = pack_w(w)
+    res = {}
+    for mode in (1, 0):
+        out = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+        d = HaloDesc()
+        d.NB, d.H, d.W, d.Cout = B, H, W, Cout
+        d.a_ptr[0] = x.data_ptr(); d.a_C[0] = Cin; d.a_ld[0] = Cin
+        d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = 1
+        d.w = wp.data_ptr(); d.ldw = 9 * Cin; d.Ktot = 9 * Cin; d.out = out.data_ptr(); d.base_offset_mode = mode; d.force_sub = 1
+        _halo_run(d)
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1)
+        res[mode] = rel(out.float().permute(0, 3, 1, 2), ref)
+    print(f"\\n[halo probe] rel-L2 with base_offset per PTX rule: {res[1]:.3e}; with base_offset = 0: {res[0]:.3e}")
+    assert min(res.values()) < 4e-3
