@@ -88,7 +88,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
     if (warp == 0) {
         // ======================= TMA producer =======================
-        if (lane == 0) {
+        // elect.sync from the converged warp (not `lane == 0`): the compiler then knows a single thread runs the
+        // uniform-datapath instructions (UTMALDG / UTCHMMA) and emits them straight-line; under a plain lane test it
+        // wraps every one of them in an ELECT/branch loop (~60-100 cycles per MMA, measured as a 2x loss at N=128).
+        if (elect_one()) {
             int ia = 0, ib = 0;
             bool ok = true;
             for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
@@ -124,7 +127,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, 0, 0);
             int ia = 0, ib = 0, it = 0;
             bool ok = true;

@@ -139,7 +139,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     if (warp == 0) {
         // ======================= TMA producer =======================
-        if (lane == 0) {
+        // elect.sync from the converged warp (not `lane == 0`): the compiler then knows a single thread runs the
+        // uniform-datapath instructions (UTMALDG / UTCHMMA) and emits them straight-line; under a plain lane test it
+        // wraps every one of them in an ELECT/branch loop (~60-100 cycles per MMA, measured as a 2x loss at N=128).
+        if (elect_one()) {
             int stg = 0;                              // global stage counter
             int sub = 0;                              // slabs already issued into the current stage
             int left = 0;                             // slabs of the current tile not yet issued
@@ -232,7 +235,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, A_MN, B_MN);
             int stg = 0, it = 0;
             bool ok = true;
