@@ -261,8 +261,7 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
     memset(&g, 0, sizeof g);
     if (!halo_eligible(d.H, d.W, d.Cout)) return fail(-12, "halo conv: unsupported geometry %dx%d Cout=%d", d.H, d.W, d.Cout);
     g.block_n = pick_block_n(d.Cout);
-    int sub = (d.W % 16 == 0 && 2 * g.block_n <= 512 && g.block_n <= 128) ? 2 : 1;   // two sub-tiles when TMEM can double-buffer them
-    if (d.W % 16 == 0 && g.block_n == 256) sub = 1;
+    int sub = 1;   // measured on B200 (tools/dbg_dominant.py): one 16x8 sub-tile per CTA beats two (1089 vs 1012 TFLOP/s at N=128)
     if (d.force_sub == 1 || d.force_sub == 2) sub = d.force_sub;
     if (sub == 2 && d.W % 16) return fail(-12, "halo conv: SUB=2 needs W %% 16 == 0");
     g.sub = sub;

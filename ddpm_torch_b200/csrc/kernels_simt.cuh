@@ -188,7 +188,7 @@ struct GnSrc { const bf16* x0; const bf16* x1; int C0, C1; };   // C = C0 + C1, 
 
 // Launch with blockDim.x = (256/oct)*oct (oct = C/8 <= 256) so that every thread owns ONE channel octet for its whole
 // pixel loop: per-channel partial sums stay in registers and are flushed once.
-__global__ void __launch_bounds__(256) k_gn_stats(GnSrc s, double* __restrict__ stats /*[B][32][2]*/, int HW, int pix_per_block) {
+__global__ void __launch_bounds__(256, 4) k_gn_stats(GnSrc s, double* __restrict__ stats /*[B][32][2]*/, int HW, int pix_per_block) {
     const int C = s.C0 + s.C1;
     const int oct = C >> 3;                       // 16-byte octets per pixel
     const int cg = C >> 5;                        // channels per group
@@ -204,16 +204,16 @@ __global__ void __launch_bounds__(256) k_gn_stats(GnSrc s, double* __restrict__ 
     float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bf16* src = first ? s.x0 + (long long)b * HW * s.C0 + c : s.x1 + (long long)b * HW * s.C1 + (c - s.C0);
     const int sstride = first ? s.C0 : s.C1;
-    for (int pp = p0 + lp; pp < p1; pp += 4 * pstep) {
-        uint4 u[4];
+    for (int pp = p0 + lp; pp < p1; pp += 8 * pstep) {
+        uint4 u[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const int q = pp + k * pstep; u[k] = q < p1 ? __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)) : make_uint4(0, 0, 0, 0); }
+        for (int k = 0; k < 8; ++k) { const int q = pp + k * pstep; u[k] = q < p1 ? __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)) : make_uint4(0, 0, 0, 0); }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
             float f[8];
             unpack8(u[k], f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] += f[e] * f[e]; }
+            for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] = fmaf(f[e], f[e], sq[e]); }
         }
     }
     {   // flush: merge elements that share a group before touching shared memory
@@ -255,6 +255,7 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
 struct GnApply {
     GnSrc s; const float* K; bf16* y;
     int HW; int silu; float drop_p; unsigned long long seed; uint32_t layer;
+    unsigned char* mask;          // [B*HW*C/8] keep bits of the dropout (written when drop_p > 0 and mask != null; read by the backward)
 };
 __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_per_block) {
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
@@ -281,7 +282,10 @@ __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_pe
             float f[8];
             unpack8(u[k], f);
             uint32_t keep = 0xffu;
-            if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
+            if (a.drop_p > 0.f) {
+                keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
+                if (a.mask) a.mask[((long long)b * a.HW + q) * oct + o] = (unsigned char)keep;
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float y = fmaf(f[e], sc[e], sh[e]);
@@ -304,8 +308,11 @@ struct GnBwd {
     bf16* dx0; bf16* dx1; int acc0, acc1;                         // destinations for the two sources (accumulate flags)
     const bf16* addend;                                           // optional [B,HW,C] term added to dx (skip-path gradient)
     int B, HW; int pix_per_block; int silu; float drop_p; unsigned long long seed; uint32_t layer;
+    const unsigned char* mask;    // keep bits saved by the forward pass (drop_p > 0)
 };
 __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {   // grid (pixel blocks, B), blockDim.x = (256/oct)*oct
+    // cs[b][0][c] = sum_p dn ; cs[b][1][c] = sum_p dn * x   (raw x: the finalize kernel converts to sum dn*xh = r*S - m*r*sum dn)
+    // Issue-bound kernel (ncu: issue-active 50% at 16 warps/SM): keep it at <= 64 registers for 4 blocks per SM.
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
     extern __shared__ float sh2[];                // [2][C]
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh2[i] = 0.f;
@@ -316,33 +323,35 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {   // 
     const int c = o * 8;
     const bool first = c < a.s.C0;
     const float* Kb = a.K + (long long)b * 4 * C + c;
-    float sc[8], sh[8], r[8], mr_[8];
-    ld8(Kb, sc); ld8(Kb + C, sh); ld8(Kb + 2 * C, r); ld8(Kb + 3 * C, mr_);
+    float sc[8], sh[8];
+    ld8(Kb, sc); ld8(Kb + C, sh);
     const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
     float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
     const int sstride = first ? a.s.C0 : a.s.C1;
     const bf16* dyp = a.dy + (long long)b * a.HW * C + c;
-    for (int pp = p0 + lp; pp < p1; pp += 2 * pstep) {
-        uint4 ux[2], ud[2];
+    const unsigned char* mk = (a.drop_p > 0.f) ? a.mask + (long long)b * a.HW * oct + o : nullptr;
+    for (int pp = p0 + lp; pp < p1; pp += 4 * pstep) {
+        uint4 ux[4], ud[4]; uint32_t kp[4] = {0xffu, 0xffu, 0xffu, 0xffu};
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const int q = pp + k * pstep;
-            if (q < p1) { ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)); ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C)); }
+            if (q < p1) {
+                ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)); ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C));
+                if (mk) kp[k] = mk[(long long)q * oct];
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const int q = pp + k * pstep;
             if (q >= p1) break;
             float x[8], d[8];
             unpack8(ux[k], x); unpack8(ud[k], d);
-            uint32_t keep = 0xffu;
-            if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
+                float dn = ((kp[k] >> e) & 1u) ? d[e] * keep_scale : 0.f;
                 if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
-                s0[e] += dn; s1[e] = fmaf(dn, fmaf(x[e], r[e], -mr_[e]), s1[e]);
+                s0[e] += dn; s1[e] = fmaf(dn, x[e], s1[e]);
             }
         }
     }
@@ -361,14 +370,15 @@ __global__ void __launch_bounds__(256) k_gn_bwd_finalize(const GnBwd a) {
     if (threadIdx.x < 64) S[threadIdx.x] = 0.f;
     __syncthreads();
     const float* csb = a.cs + (long long)b * 2 * C;
+    const float* Kb = a.K + (long long)b * 4 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float g = __ldg(a.gamma + c), c0 = csb[c], c1 = csb[C + c];
+        const float g = __ldg(a.gamma + c), c0 = csb[c];
+        const float c1 = Kb[2 * C + c] * csb[C + c] - Kb[3 * C + c] * c0;       // sum dn*xh = r*sum(dn*x) - (m*r)*sum(dn)
         atomicAdd(&S[(c / cg) * 2], g * c0); atomicAdd(&S[(c / cg) * 2 + 1], g * c1);
         atomicAdd(a.dbeta + c, c0); atomicAdd(a.dgamma + c, c1);
     }
     __syncthreads();
     const float inv_n = 1.f / ((float)a.HW * (float)cg);
-    const float* Kb = a.K + (long long)b * 4 * C;
     float* PQb = a.PQ + (long long)b * 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float r = Kb[2 * C + c], mr = Kb[3 * C + c];
@@ -377,10 +387,10 @@ __global__ void __launch_bounds__(256) k_gn_bwd_finalize(const GnBwd a) {
     }
 }
 // grid (pixel blocks, B), blockDim.x = (256/oct)*oct.  Optionally accumulates per-image / total column sums of dx.
+template <bool do_cs>
 __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* cs_per_img, int cs_ld, float* cs_total, float* cs_total2) {
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
     extern __shared__ float shc[];                // [C] column sums (only when requested)
-    const bool do_cs = cs_per_img || cs_total || cs_total2;
     if (do_cs) { for (int i = threadIdx.x; i < C; i += blockDim.x) shc[i] = 0.f; }
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * a.pix_per_block;
@@ -399,9 +409,10 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
     const int acc = first ? a.acc0 : a.acc1;
     const bf16* dyp = a.dy + (long long)b * a.HW * C + c;
     const bf16* adp = a.addend ? a.addend + (long long)b * a.HW * C + c : nullptr;
+    const unsigned char* mk = (a.drop_p > 0.f) ? a.mask + (long long)b * a.HW * oct + o : nullptr;
     float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int pp = p0 + lp; pp < p1; pp += 2 * pstep) {
-        uint4 ux[2], ud[2], ua[2], uo[2];
+        uint4 ux[2], ud[2], ua[2], uo[2]; uint32_t kp[2] = {0xffu, 0xffu};
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int q = pp + k * pstep;
@@ -410,6 +421,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
                 ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C));
                 if (adp) ua[k] = __ldg(reinterpret_cast<const uint4*>(adp + (long long)q * C));
                 if (acc) uo[k] = *reinterpret_cast<const uint4*>(dst + (long long)q * sstride);
+                if (mk) kp[k] = mk[(long long)q * oct];
             }
         }
 #pragma unroll
@@ -420,16 +432,14 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
             unpack8(ux[k], x); unpack8(ud[k], d);
             if (acc) unpack8(uo[k], ov);
             if (adp) unpack8(ua[k], ad);
-            uint32_t keep = 0xffu;
-            if (a.drop_p > 0.f) keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
+                float dn = ((kp[k] >> e) & 1u) ? d[e] * keep_scale : 0.f;
                 if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
                 float v = fmaf(sc[e], dn, -fmaf(P[e], x[e], Q[e]));
                 if (adp) v += ad[e];
                 if (acc) v += ov[e];
-                ov[e] = v; cs[e] += v;
+                ov[e] = v; if (do_cs) cs[e] += v;
             }
             *reinterpret_cast<uint4*>(dst + (long long)q * sstride) = pack8(ov);
         }
@@ -623,40 +633,66 @@ __global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
 
 // ============================================================================ in_conv: NCHW fp32 [B,Ci<=4,H,W] -> NHWC bf16 [B,H,W,Co], 3x3 pad 1
 // Also used as the data-gradient of the 3-channel out_conv (x := d_eps, w := flipped/transposed weights).
-// w layout: [Co][Ci*9] fp32 (OIHW), out NHWC bf16.  Ci <= 4.
+// w layout: [Co][CI*9] fp32 (OIHW), out NHWC bf16.  CI <= 4, Co % 32 == 0.
+// lane <-> pixel (two pixels per lane, 64 per warp); output channels are produced 32 at a time with the weights fetched as
+// warp-broadcast 16-byte shared-memory reads, so one fetch feeds 64 pixels (the per-octet version was shared-memory bound).
 template <int CI>
-__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) k_in_conv(const float* __restrict__ x, const float* __restrict__ w,
                                                 const float* __restrict__ bias, bf16* __restrict__ out,
                                                 int B, int H, int W, int Co) {
-    extern __shared__ float sw[];                 // [Co][CI*9] + [Co]
+    extern __shared__ float sw[];                 // [CI*9][Co] + [Co]
     constexpr int K = CI * 9;
-    for (int i = threadIdx.x; i < Co * K; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Co * K; i += blockDim.x) sw[(i % K) * Co + i / K] = w[i];
     for (int i = threadIdx.x; i < Co; i += blockDim.x) sw[Co * K + i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int oct = Co >> 3;
-    const long long total = (long long)B * H * W * oct;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / oct;
-        const int c0 = (int)(i % oct) * 8;
-        const int b = (int)(pix / (H * W)), r = (int)(pix % (H * W)), y = r / W, xx = r % W;
-        float in[K];
+    const long long P = (long long)B * H * W;
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp_id * 64; base < P; base += nwarps * 64) {
+        float in[2][K];
+        long long pix[2];
 #pragma unroll
-        for (int ci = 0; ci < CI; ++ci)
+        for (int u = 0; u < 2; ++u) {
+            pix[u] = base + u * 32 + lane;
+            const bool pv = pix[u] < P;
+            const int b = pv ? (int)(pix[u] / (H * W)) : 0, r = pv ? (int)(pix[u] % (H * W)) : 0, y = r / W, xx = r % W;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
-                in[ci * 9 + t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)b * CI + ci) * H + iy) * W + ix) : 0.f;
-            }
-        float o[8];
+            for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float sacc = sw[Co * K + c0 + e];
-            const float* wr = sw + (c0 + e) * K;
-#pragma unroll
-            for (int k = 0; k < K; ++k) sacc += in[k] * wr[k];
-            o[e] = sacc;
+                for (int t = 0; t < 9; ++t) {
+                    const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+                    in[u][ci * 9 + t] = (pv && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)b * CI + ci) * H + iy) * W + ix) : 0.f;
+                }
         }
-        *reinterpret_cast<uint4*>(out + pix * Co + c0) = pack8(o);
+        for (int c0 = 0; c0 < Co; c0 += 32) {
+            float acc[2][32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float bv = sw[Co * K + c0 + j]; acc[0][j] = bv; acc[1][j] = bv; }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float v0 = in[0][k], v1 = in[1][k];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(sw + k * Co + c0 + j4 * 4);     // warp-uniform address: broadcast
+                    acc[0][j4 * 4] = fmaf(v0, wv.x, acc[0][j4 * 4]); acc[0][j4 * 4 + 1] = fmaf(v0, wv.y, acc[0][j4 * 4 + 1]);
+                    acc[0][j4 * 4 + 2] = fmaf(v0, wv.z, acc[0][j4 * 4 + 2]); acc[0][j4 * 4 + 3] = fmaf(v0, wv.w, acc[0][j4 * 4 + 3]);
+                    acc[1][j4 * 4] = fmaf(v1, wv.x, acc[1][j4 * 4]); acc[1][j4 * 4 + 1] = fmaf(v1, wv.y, acc[1][j4 * 4 + 1]);
+                    acc[1][j4 * 4 + 2] = fmaf(v1, wv.z, acc[1][j4 * 4 + 2]); acc[1][j4 * 4 + 3] = fmaf(v1, wv.w, acc[1][j4 * 4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (pix[u] >= P) continue;
+                uint4* op = reinterpret_cast<uint4*>(out + pix[u] * Co + c0);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = acc[u][j8 * 8 + e];
+                    op[j8] = pack8(f);
+                }
+            }
+        }
     }
 }
 // Correlation of a wide NHWC bf16 tensor with a narrow NCHW fp32 tensor (3x3 window):
@@ -715,44 +751,69 @@ __global__ void __launch_bounds__(256) k_corr3x3(const bf16* __restrict__ wide, 
 template <int CO>
 __global__ void __launch_bounds__(256) k_out_conv(const bf16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ out, int B, int H, int W, int C) {
+    // 4 lanes per pixel group (C/4 channels each); a lane handles PX consecutive pixels of a row so that every 16-byte
+    // weight fetch from shared memory feeds PX pixels (the one-pixel version was bound by shared-memory reads)
+    constexpr int PX = 4;
     extern __shared__ float sw[];                 // [9][CO][C]
     for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
         const int t = i % 9, c = (i / 9) % C, co = i / (9 * C);
         sw[(t * CO + co) * C + c] = w[i];
     }
     __syncthreads();
-    const long long P = (long long)B * H * W;
+    const int WG = W / PX;                        // pixel groups per row (W % 4 == 0)
+    const long long G = (long long)B * H * WG;
     const int lane4 = threadIdx.x & 3;
     const int cpl = C >> 2;                       // channels per lane (multiple of 8)
-    for (long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; pix < P; pix += ((long long)gridDim.x * blockDim.x) >> 2) {
-        const int b = (int)(pix / (H * W)), r = (int)(pix % (H * W)), y = r / W, x = r % W;
-        float acc[CO];
+    for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; g < G; g += ((long long)gridDim.x * blockDim.x) >> 2) {
+        const int b = (int)(g / (H * WG)), r = (int)(g % (H * WG)), y = r / WG, x0 = (r % WG) * PX;
+        float acc[PX][CO];
 #pragma unroll
-        for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+        for (int p = 0; p < PX; ++p)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-            const bf16* src = a + (((long long)b * H + iy) * W + ix) * C + lane4 * cpl;
+            for (int co = 0; co < CO; ++co) acc[p][co] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = y + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+            const bf16* rowp = a + (((long long)b * H + iy) * W) * C + lane4 * cpl;
             for (int c8 = 0; c8 < cpl; c8 += 8) {
-                float f[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(src + c8)), f);
+                float f[PX + 2][8];               // input columns x0-1 .. x0+PX
 #pragma unroll
-                for (int co = 0; co < CO; ++co) {
-                    const float* wr = sw + (t * CO + co) * C + lane4 * cpl + c8;
+                for (int j = 0; j < PX + 2; ++j) {
+                    const int ix = x0 + j - 1;
+                    if (ix >= 0 && ix < W) unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + (long long)ix * C + c8)), f[j]);
+                    else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[co] += f[e] * wr[e];
+                        for (int e = 0; e < 8; ++e) f[j][e] = 0.f;
+                    }
                 }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) {
+                        const float* wr = sw + ((ky * 3 + kx) * CO + co) * C + lane4 * cpl + c8;
+                        const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+#pragma unroll
+                        for (int p = 0; p < PX; ++p) {
+                            const float* ff = f[p + kx];
+                            acc[p][co] += ff[0] * w0.x + ff[1] * w0.y + ff[2] * w0.z + ff[3] * w0.w + ff[4] * w1.x + ff[5] * w1.y + ff[6] * w1.z + ff[7] * w1.w;
+                        }
+                    }
             }
         }
 #pragma unroll
-        for (int co = 0; co < CO; ++co) {
-            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
-            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
-        }
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int co = 0; co < CO; ++co) {
+                acc[p][co] += __shfl_xor_sync(0xffffffffu, acc[p][co], 1);
+                acc[p][co] += __shfl_xor_sync(0xffffffffu, acc[p][co], 2);
+            }
         if (lane4 == 0) {
 #pragma unroll
-            for (int co = 0; co < CO; ++co) out[((long long)b * CO + co) * (H * W) + r] = acc[co] + bias[co];
+            for (int co = 0; co < CO; ++co) {
+                float4 o4 = make_float4(acc[0][co] + bias[co], acc[1][co] + bias[co], acc[2][co] + bias[co], acc[3][co] + bias[co]);
+                *reinterpret_cast<float4*>(out + ((long long)b * CO + co) * (H * W) + y * W + x0) = o4;
+            }
         }
     }
 }
@@ -997,25 +1058,75 @@ struct PackEntry {
     int kind; int Co, Ci, taps; int k_off; int dkind;   // dkind: 0 none, 1 dgrad, 2 dgrad flipped taps, 3 stride-2 parity dgrad
     const float* w; const float* w2; bf16* fwd; long long ld_f; bf16* dgr; long long ld_d; float* fout; float* scratch;
 };
+__device__ __forceinline__ int pack_dcol(const PackEntry& e, int t) {     // column block of tap t in the dgrad pack
+    if (e.dkind == 1) return t * e.Co;
+    if (e.dkind == 2) return (e.taps - 1 - t) * e.Co;
+    const int ky = t / 3, kx = t % 3, py = ky & 1, px = kx & 1;
+    return (py == 0 ? (px == 0 ? 0 : 4) : (px == 0 ? 6 : 8)) * e.Co + ((py ? 0 : ky / 2) * (px ? 1 : 2) + (px ? 0 : kx / 2)) * e.Co;
+}
+// grid (tiles, entries).  Conv weights / gradient unpacks go through an 8(co) x 64(ci) x taps shared-memory tile so that both
+// the fp32 side and the packed side are accessed in 16-byte-or-larger contiguous pieces (the element-wise first version spent
+// 0.6 ms/step on 2-byte scattered writes).
 __global__ void __launch_bounds__(256) k_pack_table(const PackEntry* __restrict__ table) {
     const PackEntry e = table[blockIdx.y];
-    const long long total = (e.kind == PK_BIAS_ADD) ? e.Co : (long long)e.Co * e.Ci * e.taps;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        if (e.kind == PK_BIAS_ADD) { e.fout[i] = e.w[i] + (e.w2 ? e.w2[i] : 0.f); continue; }
-        const int t = (int)(i % e.taps); const long long r = i / e.taps; const int ci = (int)(r % e.Ci), co = (int)(r / e.Ci);
-        if (e.kind == PK_FLIP_T) { e.fout[((long long)ci * e.Co + co) * 9 + (8 - t)] = e.w[i]; continue; }
-        if (e.kind == PK_UNPACK_GRAD) {           // packed fp32 grad [tap][Co][Ci] -> OIHW (=), scratch cleared behind the read
-            const long long j = ((long long)t * e.Co + co) * e.Ci + ci;
-            e.fout[i] = e.scratch[j]; e.scratch[j] = 0.f; continue;
+    if (e.kind == PK_BIAS_ADD) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.Co; i += gridDim.x * blockDim.x) e.fout[i] = e.w[i] + (e.w2 ? e.w2[i] : 0.f);
+        return;
+    }
+    if (e.kind == PK_FLIP_T) {
+        const long long total = (long long)e.Co * e.Ci * e.taps;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int t = (int)(i % e.taps); const long long r = i / e.taps; const int ci = (int)(r % e.Ci), co = (int)(r / e.Ci);
+            e.fout[((long long)ci * e.Co + co) * 9 + (8 - t)] = e.w[i];
         }
-        const bf16 v = __float2bfloat16_rn(e.w[i]);
-        if (e.fwd) e.fwd[(long long)co * e.ld_f + e.k_off + (long long)t * e.Ci + ci] = v;
-        if (e.dkind == 1 || e.dkind == 2) e.dgr[(long long)ci * e.ld_d + (long long)(e.dkind == 2 ? e.taps - 1 - t : t) * e.Co + co] = v;
-        else if (e.dkind == 3) {
-            const int ky = t / 3, kx = t % 3, py = ky & 1, px = kx & 1;
-            const int base = (py == 0 ? (px == 0 ? 0 : 4) : (px == 0 ? 6 : 8)) * e.Co;
-            const int j = (py ? 0 : ky / 2) * (px ? 1 : 2) + (px ? 0 : kx / 2);
-            e.dgr[(long long)ci * e.ld_d + base + (long long)j * e.Co + co] = v;
+        return;
+    }
+    __shared__ float sm[8][64 * 9 + 1];
+    const int T = e.taps;
+    const int tiles_ci = (e.Ci + 63) / 64, tiles = (e.Co / 8) * tiles_ci;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int co0 = (tile / tiles_ci) * 8, ci0 = (tile % tiles_ci) * 64;
+        const int nci = (e.Ci - ci0) < 64 ? (e.Ci - ci0) : 64;
+        const int row = nci * T;
+        __syncthreads();
+        if (e.kind == PK_CONV) {
+            for (int idx = threadIdx.x; idx < 8 * row; idx += blockDim.x) {
+                const int r = idx / row, j = idx % row;
+                sm[r][j] = e.w[((long long)(co0 + r) * e.Ci + ci0) * T + j];                 // sm[r][ci*T + t]
+            }
+        } else {   // PK_UNPACK_GRAD: scratch [t][Co][Ci] fp32 -> tile, cleared behind the read
+            for (int idx = threadIdx.x; idx < 8 * row; idx += blockDim.x) {
+                const int ci = idx % nci, r = (idx / nci) % 8, t = idx / (nci * 8);
+                float* sp = e.scratch + ((long long)t * e.Co + co0 + r) * e.Ci + ci0 + ci;
+                sm[r][ci * T + t] = *sp; *sp = 0.f;
+            }
+        }
+        __syncthreads();
+        if (e.kind == PK_UNPACK_GRAD) {
+            for (int idx = threadIdx.x; idx < 8 * row; idx += blockDim.x) {
+                const int r = idx / row, j = idx % row;
+                e.fout[((long long)(co0 + r) * e.Ci + ci0) * T + j] = sm[r][j];
+            }
+            continue;
+        }
+        if (e.fwd) {
+            const int octs = nci / 8;
+            for (int idx = threadIdx.x; idx < 8 * T * octs; idx += blockDim.x) {
+                const int o = idx % octs, t = (idx / octs) % T, r = idx / (octs * T);
+                float f[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = sm[r][(o * 8 + q) * T + t];
+                *reinterpret_cast<uint4*>(e.fwd + (long long)(co0 + r) * e.ld_f + e.k_off + (long long)t * e.Ci + ci0 + o * 8) = pack8(f);
+            }
+        }
+        if (e.dkind) {
+            for (int idx = threadIdx.x; idx < row; idx += blockDim.x) {
+                const int ci = idx / T, t = idx % T;
+                float f[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = sm[q][ci * T + t];
+                *reinterpret_cast<uint4*>(e.dgr + (long long)(ci0 + ci) * e.ld_d + pack_dcol(e, t) + co0) = pack8(f);
+            }
         }
     }
 }

@@ -17,7 +17,7 @@ struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
 struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; };
-struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; };
+struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; unsigned char* mask; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 static inline int oct_threads(int C) { const int oct = C / 8; return oct <= 256 ? (256 / oct) * oct : 0; }
@@ -323,7 +323,8 @@ struct UnetEngine {
             k_gn_stats<<<g1, thr, 0, st>>>(gs, stats, HW, ppb);
             k_gn_finalize<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, ga, be, K, Bn, C, 1.0 / ((double)HW * (C / 32)), 1e-6f);
             return (int)cudaGetLastError(); }, 2);
-        GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer;
+        sv.mask = (drop_p > 0.f && train) ? at<unsigned char>(alloc((size_t)Bn * HW * (C / 8))) : nullptr;
+        GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
         int nb2, ppb2; gn_grid(Bn, HW, 4, nb2, ppb2);
         const dim3 g2(nb2, Bn);
         UnetEngine* self = this;
@@ -343,7 +344,7 @@ struct UnetEngine {
         bool f0 = true, f1 = true;
         const T4 g0 = grad_of(in.t0, &f0); a.dx0 = bp(g0); a.acc0 = f0 ? 0 : 1;
         if (in.two) { const T4 g1 = grad_of(in.t1, &f1); a.dx1 = bp(g1); a.acc1 = f1 ? 0 : 1; }
-        a.addend = addend; a.B = Bn; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer;
+        a.addend = addend; a.B = Bn; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer; a.mask = sv.mask;
         const int thr = oct_threads(C);
         int nblk, ppb; gn_grid(Bn, HW, 2, nblk, ppb);
         a.pix_per_block = ppb;
@@ -355,7 +356,8 @@ struct UnetEngine {
             GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
             k_gn_bwd_reduce<<<g1, thr, shm, st>>>(aa);
             k_gn_bwd_finalize<<<Bn, 256, 0, st>>>(aa);
-            k_gn_bwd_apply<<<g1, thr, shm2, st>>>(aa, cs_per_img, cs_ld, cs_total, cs_total2);
+            if (shm2) k_gn_bwd_apply<true><<<g1, thr, shm2, st>>>(aa, cs_per_img, cs_ld, cs_total, cs_total2);
+            else      k_gn_bwd_apply<false><<<g1, thr, 0, st>>>(aa, cs_per_img, cs_ld, cs_total, cs_total2);
             return (int)cudaGetLastError(); }, 3);
     }
     void colsum_op(const std::string& name, const T4& dy, float* per_img, int ld, float* total, float* total2, int C_valid) {

@@ -343,14 +343,14 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     T4 h0 = newT(B, H, W, ch);
     {
         const float* wi = PP("in_conv.weight"); const float* bi = PP("in_conv.bias"); bf16* o = bp(h0);
-        const size_t shm = (size_t)(ch * Cin * 9 + ch) * 4; const int n = grid_for((long long)B * H * W * (ch / 8));
+        const size_t shm = (size_t)(ch * Cin * 9 + ch) * 4; const int n = grid_for((long long)B * H * W / 2, 128);
         const int Bn = B, Hn = H, Wn = W;
         push(fwd_ops, "in_conv", 2.0 * B * H * W * ch * Cin * 9, [=](cudaStream_t st) {
             switch (Cin) {
-                case 1: k_in_conv<1><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                case 2: k_in_conv<2><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                case 3: k_in_conv<3><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                default: k_in_conv<4><<<n, 256, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 1: k_in_conv<1><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 2: k_in_conv<2><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 3: k_in_conv<3><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                default: k_in_conv<4><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
             }
             return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
@@ -405,7 +405,8 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         const float* wo = PP("out_conv.2.weight"); const float* bo = PP("out_conv.2.bias"); const bf16* ap = bp(a_out);
         const int Bn = B, Hn = H, Wn = W;
         const size_t shm = (size_t)9 * Cout * ch * 4;
-        const int nblk = grid_for((long long)B * H * W * 4);
+        if (W % 4) return fail(-30, "image width must be a multiple of 4");
+        const int nblk = grid_for((long long)B * H * W);
         const double fl = 2.0 * B * H * W * ch * Cout * 9;
         fwd_flops += fl;
         push(fwd_ops, "out_conv.2", fl, [=](cudaStream_t st) {
@@ -424,20 +425,20 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 float* gw = GP("out_conv.2.weight"); float* gb = GP("out_conv.2.bias");
                 T4 d_a = newT(B, H, W, ch);
                 bf16* dap = bp(d_a);
-                const size_t shm2 = (size_t)(ch * Cout * 9 + ch) * 4; const int n2 = grid_for((long long)Bn * Hn * Wn * (ch / 8));
+                const size_t shm2 = (size_t)(ch * Cout * 9 + ch) * 4; const int n2 = grid_for((long long)Bn * Hn * Wn / 2, 128);
                 const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
                 bwd_flops += 2.0 * fl;
                 push(bwd_ops, "out_conv.2.bwd", 2.0 * fl, [=](cudaStream_t st) {
                     const float* de = self->deps_src;
                     k_chansum_nchw<<<dim3(64, Cout), 256, 0, st>>>(de, gb, Bn, Cout, Hn * Wn);
                     switch (Cout) {
-                        case 1: k_in_conv<1><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        case 1: k_in_conv<1><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
                                 k_corr3x3<1><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        case 2: k_in_conv<2><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        case 2: k_in_conv<2><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
                                 k_corr3x3<2><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        case 3: k_in_conv<3><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        case 3: k_in_conv<3><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
                                 k_corr3x3<3><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        default: k_in_conv<4><<<n2, 256, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        default: k_in_conv<4><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
                                 k_corr3x3<4><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
                     }
                     return (int)cudaGetLastError(); }, 3);

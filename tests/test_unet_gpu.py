@@ -223,3 +223,40 @@ def test_celebahq_forward_golden(golden):
     print(f"\n[celebahq bs1 256x256] eps rel-L2 vs reference golden {r:.3e}")
     assert r < 3e-2
     check_device_flag()
+
+
+def test_dropout_gradient_directional_derivative():
+    """Train mode with dropout (the engine's own Philox masks, saved by the forward and re-used by the backward): the
+    masks cannot be compared with torch's, so check the gradient by a directional derivative under the SAME seed:
+    L(w - eps*g) ~= L(w) - eps*|g|^2."""
+    import ddpm_torch_b200 as D
+    cfg = dict(R.SMALL64_CFG); cfg["drop_rate"] = 0.1
+    c = R.normalize_cfg(cfg)
+    m = D.UNet(3, 64, 3, c["ch_multipliers"], c["num_res_blocks"], c["apply_attn"], drop_rate=0.1)
+    m.load_state_dict(R.make_state_dict(cfg, 7))
+    m = m.to(DEV).train()
+    diff = D.GaussianDiffusion(D.get_beta_schedule("linear", 1e-4, 0.02, 1000), "eps", "fixed-large", "mse")
+    g = torch.Generator(DEV).manual_seed(3)
+    x0 = torch.randn(8, 3, 32, 32, device=DEV, generator=g); t = torch.randint(1000, (8,), device=DEV, generator=g)
+    nz = torch.randn(8, 3, 32, 32, device=DEV, generator=g)
+
+    def loss_with_seed():
+        m._drop_calls = 41                        # same dropout seed on every evaluation
+        return diff.train_losses(m, x0, t, nz).mean()
+
+    l0 = loss_with_seed()
+    l0.backward()
+    grads = [p.grad.clone() for p in m.parameters()]
+    g2 = sum((gg.double() ** 2).sum() for gg in grads).item()
+    with torch.no_grad():
+        l0b = loss_with_seed().item()
+    assert abs(l0b - l0.item()) < 2e-3 * abs(l0.item())          # same seed -> same masks (up to reduction-order noise)
+    eps = 0.05 * l0.item() / g2                                  # aim at a 5 % first-order decrease
+    with torch.no_grad():
+        for p, gg in zip(m.parameters(), grads):
+            p.sub_(eps * gg)
+        l1 = loss_with_seed().item()
+    pred, got = eps * g2, l0.item() - l1
+    print(f"\n[dropout grad] L0 {l0.item():.5f} predicted decrease {pred:.5f} measured {got:.5f}")
+    assert 0.7 * pred < got < 1.3 * pred
+    check_device_flag()
