@@ -308,6 +308,30 @@ struct UnetEngine {
         nblk = (148 * occ) / Bn; if (nblk > HW / 16) nblk = HW / 16; if (nblk < 1) nblk = 1;
         ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
     }
+    // fused single-kernel GroupNorm (one thread-block cluster per image, tile kept in shared memory, statistics exchanged
+    // through DSMEM): cluster size such that the image's tile(s) fit; 0 = use the multi-kernel path.
+    // MEASURED SLOWER on B200 (CIFAR bs=128 step 14.3 ms vs 12.6 ms): at 1-2 CTAs per SM the load -> cluster barrier -> apply
+    // phases serialise, while the multi-kernel path overlaps 4-8 blocks per SM.  Kept as an opt-in experiment (DDPM_FUSED_GN=1).
+    static int gn_cluster(int HW, int C, int ntiles, size_t extra) {
+        static const bool on = getenv("DDPM_FUSED_GN") != nullptr;
+        if (!on) return 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const size_t budget = pass == 0 ? 100 * 1024 : 200 * 1024;
+            for (int cl = 1; cl <= 8; cl <<= 1) {
+                if (HW % cl) continue;
+                if ((size_t)(HW / cl) * C * 2 * ntiles + extra <= budget) return cl;
+            }
+        }
+        return 0;
+    }
+    template <class Kern, class... Args>
+    static int launch_cluster(Kern kern, dim3 grid, int threads, size_t shm, int cl, cudaStream_t st, Args... args) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = shm; cfg.stream = st;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, kern, args...);
+    }
     GnSaved gn_fwd(std::vector<Op>& L, const std::string& name, const Src& in, const std::string& pname, const T4& out, int silu, float drop_p) {
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
         GnSaved sv; sv.in = in; sv.silu = silu; sv.drop_p = drop_p; sv.layer = ++layer_counter;   // dropout is armed per call by a non-zero seed
@@ -316,14 +340,27 @@ struct UnetEngine {
         sv.K = at<float>(alloc((size_t)Bn * 4 * C * 4));
         const GnSrc gs = gsrc(in);
         const int thr = oct_threads(C);
+        float* K = sv.K; const float* ga = sv.gamma; const float* be = sv.beta;
+        sv.mask = (drop_p > 0.f && train) ? at<unsigned char>(alloc((size_t)Bn * HW * (C / 8))) : nullptr;
+        const int cl = gn_cluster(HW, C, 1, 1024);
+        if (cl) {
+            GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
+            const int ppc = HW / cl; const size_t shm = 512 + (size_t)ppc * C * 2;
+            const int thr5 = (512 / (C / 8)) * (C / 8);
+            const dim3 gf(cl, Bn);
+            UnetEngine* self = this;
+            static bool attr_done = false;
+            if (!attr_done && !dry) { cudaFuncSetAttribute(k_gn_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }
+            push(L, name + ".fused", 0, [=](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
+                return launch_cluster(k_gn_fused_fwd, gf, thr5, shm, cl, st, aa, K, ga, be, ppc, 1e-6f); });
+            return sv;
+        }
         int nblk, ppb; gn_grid(Bn, HW, 6, nblk, ppb);
         const dim3 g1(nblk, Bn);
-        float* K = sv.K; const float* ga = sv.gamma; const float* be = sv.beta;
         push(L, name + ".stats", 0, [=](cudaStream_t st) {
             k_gn_stats<<<g1, thr, 0, st>>>(gs, stats, HW, ppb);
             k_gn_finalize<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, ga, be, K, Bn, C, 1.0 / ((double)HW * (C / 32)), 1e-6f);
             return (int)cudaGetLastError(); }, 2);
-        sv.mask = (drop_p > 0.f && train) ? at<unsigned char>(alloc((size_t)Bn * HW * (C / 8))) : nullptr;
         GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
         int nb2, ppb2; gn_grid(Bn, HW, 4, nb2, ppb2);
         const dim3 g2(nb2, Bn);
@@ -346,6 +383,26 @@ struct UnetEngine {
         if (in.two) { const T4 g1 = grad_of(in.t1, &f1); a.dx1 = bp(g1); a.acc1 = f1 ? 0 : 1; }
         a.addend = addend; a.B = Bn; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer; a.mask = sv.mask;
         const int thr = oct_threads(C);
+        {
+            const size_t extra = (size_t)(5 * C + 64) * 4 + 64;
+            const int cl = gn_cluster(HW, C, 2, extra);
+            if (cl) {
+                const int ppc = HW / cl; const size_t shm = (((size_t)(5 * C + 64) * 4 + 15) / 16) * 16 + (size_t)2 * ppc * C * 2;
+                const int thr5 = (512 / (C / 8)) * (C / 8);
+                const dim3 gf(cl, Bn);
+                const bool cs = cs_per_img || cs_total || cs_total2;
+                UnetEngine* self = this;
+                static bool attr_done = false;
+                if (!attr_done && !dry) {
+                    cudaFuncSetAttribute(k_gn_fused_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                    cudaFuncSetAttribute(k_gn_fused_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }
+                push(bwd_ops, name + ".gn_bwd.fused", 0, [=](cudaStream_t st) {
+                    GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
+                    if (cs) return launch_cluster(k_gn_fused_bwd<true>, gf, thr5, shm, cl, st, aa, ppc, cs_per_img, cs_ld, cs_total, cs_total2);
+                    return launch_cluster(k_gn_fused_bwd<false>, gf, thr5, shm, cl, st, aa, ppc, cs_per_img, cs_ld, cs_total, cs_total2); });
+                return;
+            }
+        }
         int nblk, ppb; gn_grid(Bn, HW, 2, nblk, ppb);
         a.pix_per_block = ppb;
         const dim3 g1(nblk, Bn);
