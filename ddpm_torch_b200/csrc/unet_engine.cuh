@@ -267,10 +267,13 @@ struct UnetEngine {
                 if (taps == 9) { d.out = scratch + coff; d.ldo = Cin; d.out_tap_stride = (long long)Co * Cin; }
                 else { d.out = dw + coff; d.ldo = Cin; }
                 ++n_tc_gemms;
-                if (dry) { push(bwd_ops, name, s ? 0 : fl, [](cudaStream_t) { return 0; }); continue; }
+                // weight gradients are leaves of the backward graph: run them on the side stream, where the tensor-bound GEMMs
+                // overlap the memory-bound GroupNorm kernels of the main chain (DDPM_WGRAD_MAIN=1 keeps them in line)
+                static const bool wg_side = getenv("DDPM_WGRAD_MAIN") == nullptr;
+                if (dry) { push(bwd_ops, name, s ? 0 : fl, [](cudaStream_t) { return 0; }, 1, wg_side); continue; }
                 GemmLaunch g; int rc = build_gemm(d, g);
                 if (rc) { plan_error = rc; return; }
-                push(bwd_ops, name, s ? 0 : fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+                push(bwd_ops, name, s ? 0 : fl, [g](cudaStream_t st) { return launch_gemm(g, st); }, 1, wg_side);
             }
             if (taps == 9) {   // packed [tap][Co][Ci] scratch -> OIHW flat gradient: batched into ONE table-driven launch at the end of backward
                 PackEntry e; memset(&e, 0, sizeof e);
@@ -289,7 +292,7 @@ struct UnetEngine {
         w.pix_per_split = (int)(((P + splits - 1) / splits + 15) / 16 * 16);
         splits = (int)((P + w.pix_per_split - 1) / w.pix_per_split);
         const dim3 grid((Cin + 63) / 64, (Co + 63) / 64, taps * splits);
-        push(bwd_ops, name + "[simt]", fl, [w, grid](cudaStream_t st) { k_wgrad_generic<<<grid, 256, 0, st>>>(w); return (int)cudaGetLastError(); });
+        push(bwd_ops, name + "[simt]", fl, [w, grid](cudaStream_t st) { k_wgrad_generic<<<grid, 256, 0, st>>>(w); return (int)cudaGetLastError(); }, 1, true);
     }
     size_t alloc_once_zero(size_t bytes) {   // carve from the plan-time-zeroed arena (contiguous region grown on demand)
         const size_t o = alloc(bytes);

@@ -457,7 +457,8 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         unpack_table_off = alloc(sizeof(PackEntry) * (unpack_table_host.size() + 1));
         if (!unpack_table_host.empty()) {
             const PackEntry* tab = at<PackEntry>(unpack_table_off); const int n = (int)unpack_table_host.size();
-            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { k_pack_table<<<dim3(32, n), 256, 0, st>>>(tab); return (int)cudaGetLastError(); });
+            // on the side stream too: ordered after every wgrad GEMM there; the list's final join publishes the flat gradients
+            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { k_pack_table<<<dim3(32, n), 256, 0, st>>>(tab); return (int)cudaGetLastError(); }, 1, true);
         }
     }
     pack_table_off = alloc(sizeof(PackEntry) * (pack_table_host.size() + 1));
