@@ -54,6 +54,7 @@ template <int BLOCK_N, int SUB>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+    pdl_trigger();
     using CF = HaloCfg<BLOCK_N, SUB>;
     constexpr int P = CF::P;
     extern __shared__ uint8_t smem_raw[];
@@ -84,6 +85,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -294,7 +296,7 @@ inline int launch_halo_inst(const HaloLaunch& g, cudaStream_t st) {
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     const int ctas = g.tiles < num_sms ? g.tiles : num_sms;
-    kern<<<ctas, 192, CF::TOTAL, st>>>(g.a[0], g.a[1], g.a[2], g.b, g.p);
+    launch_k(kern, ctas, 192, CF::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

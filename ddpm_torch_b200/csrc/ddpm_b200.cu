@@ -12,7 +12,8 @@ struct ddpm_unet {
     const float* train_target = nullptr;
 };
 
-__global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_set_int(int* p, int v) {
+    pdl_entry(); *p = v; }
 
 extern "C" {
 
@@ -69,6 +70,7 @@ void ddpm_unet_destroy(ddpm_unet* h) {
     if (h->d_tmodel) cudaFree(h->d_tmodel);
     if (h->d_coef) cudaFree(h->d_coef);
     if (h->e.side_stream) { cudaStreamDestroy(h->e.side_stream); cudaEventDestroy(h->e.ev_fork); cudaEventDestroy(h->e.ev_join); }
+    if (h->e.hp_stream) { cudaStreamDestroy(h->e.hp_stream); cudaEventDestroy(h->e.ev_hp_fork); cudaEventDestroy(h->e.ev_hp_join); }
     delete h;
 }
 int ddpm_unet_num_params(const ddpm_unet* h) { return (int)h->e.params.size(); }
@@ -132,13 +134,13 @@ int ddpm_train_forward(ddpm_unet* h, const float* x0, const int64_t* t, const fl
     const int per_img = e.cfg.in_channels * e.H * e.W;
     const long long total = (long long)e.B * per_img;
     float* xt = e.at<float>(e.xt_off); float* eps = e.at<float>(e.eps_off);
-    k_qsample<<<grid_for(total), 256, 0, st>>>(x0, noise, reinterpret_cast<const long long*>(t), tab_a, tab_s, xt, per_img, total);
+    launch_k(k_qsample, grid_for(total), 256, 0, st, x0, noise, reinterpret_cast<const long long*>(t), tab_a, tab_s, xt, per_img, total);
     DDPM_CUDA_OK(cudaGetLastError());
     e.x_in = xt; e.t_in = reinterpret_cast<const long long*>(t); e.eps_dst = eps; e.drop_seed = dropout_seed;
     const int rc = e.run_list(e.fwd_ops, st);
     if (rc) return rc;
     h->train_target = noise;
-    k_mse<<<e.B, 256, 0, st>>>(eps, noise, losses, e.cfg.out_channels * e.H * e.W);
+    launch_k(k_mse, e.B, 256, 0, st, eps, noise, losses, e.cfg.out_channels * e.H * e.W);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -149,7 +151,7 @@ int ddpm_train_backward(ddpm_unet* h, const float* gscale, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int per_img = e.cfg.out_channels * e.H * e.W;
     const long long total = (long long)e.B * per_img;
-    k_mse_grad<<<grid_for(total), 256, 0, st>>>(e.at<float>(e.eps_off), h->train_target, gscale, e.at<float>(e.deps_off), per_img, total);
+    launch_k(k_mse_grad, grid_for(total), 256, 0, st, e.at<float>(e.eps_off), h->train_target, gscale, e.at<float>(e.deps_off), per_img, total);
     DDPM_CUDA_OK(cudaGetLastError());
     e.deps_src = e.at<float>(e.deps_off);
     return e.run_list(e.bwd_ops, st);
@@ -169,7 +171,7 @@ int ddpm_sampler_setup(ddpm_unet* h, int S, const int64_t* t_model_host, const f
 int ddpm_sampler_reset(ddpm_unet* h, int first_step, void* stream) {
     NEED_PLAN(h);
     if (first_step < 0 || first_step >= h->S) return fail(-30, "first_step out of range");
-    k_set_int<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(h->e.at<int>(h->e.counter_off), first_step);
+    launch_k(k_set_int, 1, 1, 0, static_cast<cudaStream_t>(stream), h->e.at<int>(h->e.counter_off), first_step);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -179,13 +181,13 @@ int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, voi
     UnetEngine& e = h->e;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     long long* tbuf = e.at<long long>(e.tbuf_off); float* cc = e.at<float>(e.coefcur_off); float* eps = e.at<float>(e.eps_off);
-    k_sampler_prep<<<1, 256, 0, st>>>(e.at<int>(e.counter_off), h->d_tmodel, h->d_coef, tbuf, cc, e.B);
+    launch_k(k_sampler_prep, 1, 256, 0, st, e.at<int>(e.counter_off), h->d_tmodel, h->d_coef, tbuf, cc, e.B);
     DDPM_CUDA_OK(cudaGetLastError());
     e.x_in = x; e.t_in = tbuf; e.eps_dst = eps; e.drop_seed = 0;
     const int rc = e.run_list(e.fwd_ops, st);
     if (rc) return rc;
     const long long total = (long long)e.B * e.cfg.out_channels * e.H * e.W;
-    k_psample_tail<<<grid_for(total), 256, 0, st>>>(eps, x, z, cc, (unsigned long long)seed, total);
+    launch_k(k_psample_tail, grid_for(total), 256, 0, st, eps, x, z, cc, (unsigned long long)seed, total);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

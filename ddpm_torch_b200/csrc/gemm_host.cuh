@@ -118,7 +118,7 @@ inline int launch_gemm_inst3(const GemmLaunch& g, cudaStream_t st) {
         DDPM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.a[0], g.a[1], g.a[2], g.b, g.p));
         return 0;
     }
-    kern<<<ctas, 192, SM::TOTAL, st>>>(g.a[0], g.a[1], g.a[2], g.b, g.p);
+    launch_k(kern, ctas, 192, SM::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

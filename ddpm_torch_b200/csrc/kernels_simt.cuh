@@ -69,6 +69,7 @@ __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint3
 
 // ============================================================================ timestep embedding (functions.py:10-26)
 __global__ void k_timestep_embedding(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim / 2;
     if (i >= B * half) return;
@@ -161,16 +162,19 @@ __device__ __forceinline__ void sgemm_body(const SgemmParams& p, int bz, int spl
 }
 template <typename TA, typename TB, typename TC>
 __global__ void __launch_bounds__(256) k_sgemm(const SgemmParams p) {
+    pdl_entry();
     const int ks = p.ksplit > 1 ? p.ksplit : 1;
     sgemm_body<TA, TB, TC>(p, blockIdx.z / ks, blockIdx.z % ks);
 }
 // table-driven: blockIdx.z selects an independent problem (per-ResBlock timestep projections) and its K split
 __global__ void __launch_bounds__(256) k_sgemm_table(const SgemmParams* __restrict__ table, int ksplit) {
+    pdl_entry();
     const SgemmParams p = table[blockIdx.z / ksplit];
     sgemm_body<float, float, float>(p, 0, blockIdx.z % ksplit);
 }
 // column sums of an fp32 [M][N] matrix (bias grads of the timestep MLP): out[n] += sum_m A[m][n]
 __global__ void k_colsum_f32(const float* __restrict__ A, float* __restrict__ out, int M, int N, long long lda) {
+    pdl_entry();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
@@ -178,6 +182,7 @@ __global__ void k_colsum_f32(const float* __restrict__ A, float* __restrict__ ou
     atomicAdd(out + n, s);
 }
 __global__ void k_add_f32(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
 }
@@ -188,7 +193,9 @@ struct GnSrc { const bf16* x0; const bf16* x1; int C0, C1; };   // C = C0 + C1, 
 
 // Launch with blockDim.x = (256/oct)*oct (oct = C/8 <= 256) so that every thread owns ONE channel octet for its whole
 // pixel loop: per-channel partial sums stay in registers and are flushed once.
-__global__ void __launch_bounds__(256, 4) k_gn_stats(GnSrc s, double* __restrict__ stats /*[B][32][2]*/, int HW, int pix_per_block) {
+struct GnFin { const float* gamma; const float* beta; float* K; int* ticket; float eps; };   // fused finalize (last block per image)
+__global__ void __launch_bounds__(256, 4) k_gn_stats(GnSrc s, double* __restrict__ stats /*[B][32][2]*/, int HW, int pix_per_block, GnFin fin) {
+    pdl_entry();
     const int C = s.C0 + s.C1;
     const int oct = C >> 3;                       // 16-byte octets per pixel
     const int cg = C >> 5;                        // channels per group
@@ -228,6 +235,25 @@ __global__ void __launch_bounds__(256, 4) k_gn_stats(GnSrc s, double* __restrict
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&stats[(long long)b * 64 + i], (double)sh[i]);
+    // the block that arrives last for this image turns {sum, sumsq} into the per-channel constants K (saves a launch per norm)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(fin.ticket + b, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double inv_n = 1.0 / ((double)HW * cg);
+    float* Kb = fin.K + (long long)b * 4 * C;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        const int g = ch / cg;
+        const double m = __ldcg(&stats[(long long)b * 64 + g * 2]) * inv_n;
+        double var = __ldcg(&stats[(long long)b * 64 + g * 2 + 1]) * inv_n - m * m;
+        if (var < 0) var = 0;
+        const float r = (float)(1.0 / sqrt(var + (double)fin.eps)), mf = (float)m;
+        const float scv = r * fin.gamma[ch];
+        Kb[ch] = scv; Kb[C + ch] = fin.beta[ch] - mf * scv; Kb[2 * C + ch] = r; Kb[3 * C + ch] = mf * r;
+    }
 }
 
 // ---- GroupNorm v4: per-(image, channel) constants are materialised once by tiny "finalize" kernels, so the bandwidth-bound
@@ -235,6 +261,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_stats(GnSrc s, double* __restrict
 // K[b][0..3][C] = { sc = rstd*gamma, sh = beta - mean*sc, r = rstd, mr = mean*rstd }   ->  y = x*sc + sh ; xh = x*r - mr
 __global__ void k_gn_finalize(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                               float* __restrict__ K, int B, int C, double inv_n, float eps) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
     const int b = i / C, c = i % C, g = c / (C >> 5);
@@ -258,6 +285,7 @@ struct GnApply {
     unsigned char* mask;          // [B*HW*C/8] keep bits of the dropout (written when drop_p > 0 and mask != null; read by the backward)
 };
 __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_per_block) {
+    pdl_entry();
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_block;
@@ -309,8 +337,11 @@ struct GnBwd {
     const bf16* addend;                                           // optional [B,HW,C] term added to dx (skip-path gradient)
     int B, HW; int pix_per_block; int silu; float drop_p; unsigned long long seed; uint32_t layer;
     const unsigned char* mask;    // keep bits saved by the forward pass (drop_p > 0)
+    int* ticket;                  // [B] arrival counters (zeroed per pass): the last reduce block of an image runs the finalize
+    int dn_inplace;               // reduce pass overwrites dy with dn = mask*dy*silu'(y); apply pass reads it back as-is
 };
-__global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {   // grid (pixel blocks, B), blockDim.x = (256/oct)*oct
+__global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {
+    pdl_entry();   // grid (pixel blocks, B), blockDim.x = (256/oct)*oct
     // cs[b][0][c] = sum_p dn ; cs[b][1][c] = sum_p dn * x   (raw x: the finalize kernel converts to sum dn*xh = r*S - m*r*sum dn)
     // Issue-bound kernel (ncu: issue-active 50% at 16 warps/SM): keep it at <= 64 registers for 4 blocks per SM.
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
@@ -352,7 +383,10 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {   // 
                 float dn = ((kp[k] >> e) & 1u) ? d[e] * keep_scale : 0.f;
                 if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
                 s0[e] += dn; s1[e] = fmaf(dn, x[e], s1[e]);
+                d[e] = dn;
             }
+            // dn (gradient at the normalised pre-activation) replaces dy in place: the apply pass then needs no SiLU / mask math
+            if (a.dn_inplace) *reinterpret_cast<uint4*>(const_cast<bf16*>(dyp) + (long long)q * C) = pack8(d);
         }
     }
     __syncthreads();
@@ -361,9 +395,35 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {   // 
     __syncthreads();
     float* csb = a.cs + (long long)b * 2 * C;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(csb + i, sh2[i]);
+    // last block of this image: group sums, dgamma/dbeta, and the per-channel P,Q of the apply pass (was k_gn_bwd_finalize)
+    __shared__ int s_last; __shared__ float S[64];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket + b, 1) == (int)gridDim.x - 1);
+    if (threadIdx.x < 64) S[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int cg = C >> 5;
+    const float* Kc = a.K + (long long)b * 4 * C;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        const float g = __ldg(a.gamma + ch), c0 = __ldcg(csb + ch);
+        const float c1 = Kc[2 * C + ch] * __ldcg(csb + C + ch) - Kc[3 * C + ch] * c0;
+        atomicAdd(&S[(ch / cg) * 2], g * c0); atomicAdd(&S[(ch / cg) * 2 + 1], g * c1);
+        atomicAdd(a.dbeta + ch, c0); atomicAdd(a.dgamma + ch, c1);
+    }
+    __syncthreads();
+    const float inv_n = 1.f / ((float)a.HW * (float)cg);
+    float* PQb = a.PQ + (long long)b * 2 * C;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        const float r = Kc[2 * C + ch], mr = Kc[3 * C + ch];
+        const float k2 = r * S[(ch / cg) * 2] * inv_n, k3 = r * S[(ch / cg) * 2 + 1] * inv_n;
+        PQb[ch] = k3 * r; PQb[C + ch] = k2 - k3 * mr;
+    }
 }
 // one block per image
 __global__ void __launch_bounds__(256) k_gn_bwd_finalize(const GnBwd a) {
+    pdl_entry();
     const int C = a.s.C0 + a.s.C1, cg = C >> 5;
     __shared__ float S[64];
     const int b = blockIdx.x;
@@ -389,6 +449,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_finalize(const GnBwd a) {
 // grid (pixel blocks, B), blockDim.x = (256/oct)*oct.  Optionally accumulates per-image / total column sums of dx.
 template <bool do_cs>
 __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* cs_per_img, int cs_ld, float* cs_total, float* cs_total2) {
+    pdl_entry();
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
     extern __shared__ float shc[];                // [C] column sums (only when requested)
     if (do_cs) { for (int i = threadIdx.x; i < C; i += blockDim.x) shc[i] = 0.f; }
@@ -421,7 +482,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
                 ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C));
                 if (adp) ua[k] = __ldg(reinterpret_cast<const uint4*>(adp + (long long)q * C));
                 if (acc) uo[k] = *reinterpret_cast<const uint4*>(dst + (long long)q * sstride);
-                if (mk) kp[k] = mk[(long long)q * oct];
+                if (mk && !a.dn_inplace) kp[k] = mk[(long long)q * oct];
             }
         }
 #pragma unroll
@@ -434,8 +495,11 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
             if (adp) unpack8(ua[k], ad);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float dn = ((kp[k] >> e) & 1u) ? d[e] * keep_scale : 0.f;
-                if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
+                float dn = d[e];
+                if (!a.dn_inplace) {
+                    dn = ((kp[k] >> e) & 1u) ? d[e] * keep_scale : 0.f;
+                    if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
+                }
                 float v = fmaf(sc[e], dn, -fmaf(P[e], x[e], Q[e]));
                 if (adp) v += ad[e];
                 if (acc) v += ov[e];
@@ -479,6 +543,7 @@ __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("m
 // grid (CL, B), cluster (CL,1,1), blockDim.x = 512-ish multiple of oct.  dynamic smem: [ppc][C] bf16 tile + [64] floats
 __global__ void __launch_bounds__(512, 1) k_gn_fused_fwd(const GnApply a, float* __restrict__ Kout, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int ppc, float eps) {
+    pdl_entry();
     const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* part = reinterpret_cast<float*>(smraw);                 // [32][2] this CTA's group partials
@@ -566,6 +631,7 @@ __global__ void __launch_bounds__(512, 1) k_gn_fused_fwd(const GnApply a, float*
 // [2][C] floats partial + [2][C] floats P,Q + 2 x [ppc][oct] uint4
 template <bool do_cs>
 __global__ void __launch_bounds__(512, 1) k_gn_fused_bwd(const GnBwd a, int ppc, float* cs_per_img, int cs_ld, float* cs_total, float* cs_total2) {
+    pdl_entry();
     const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
     extern __shared__ __align__(16) unsigned char smraw[];
     float* part = reinterpret_cast<float*>(smraw);                 // [2][C]: sum dn, sum dn*x  (this CTA)
@@ -598,7 +664,7 @@ __global__ void __launch_bounds__(512, 1) k_gn_fused_bwd(const GnBwd a, int ppc,
             const int q = pp + k * pstep;
             if (q < ppc) {
                 ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)); ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C));
-                if (mk) kp[k] = mk[(long long)q * oct];
+                if (mk && !a.dn_inplace) kp[k] = mk[(long long)q * oct];
             }
         }
 #pragma unroll
@@ -698,6 +764,7 @@ __device__ __forceinline__ bool conv_map_coord(int map, int o, int k, int stride
     const int u = o + k - 1; i = u >> 1; return u >= 0 && i < n_in;
 }
 __global__ void __launch_bounds__(256) k_conv_generic(const ConvG c) {
+    pdl_entry();
     __shared__ float As[16][65];
     __shared__ float Bs[16][65];
     const int Cin = c.in.C0 + c.in.C1;
@@ -791,6 +858,7 @@ struct WgradG {
     int Co_valid;                                 // rows of dW actually written (dy may be channel-padded)
 };
 __global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
+    pdl_entry();
     __shared__ float As[16][65];   // [pixel][co]
     __shared__ float Bs[16][65];   // [pixel][ci]
     const int Cin = c.in.C0 + c.in.C1;
@@ -862,6 +930,7 @@ template <int CI>
 __global__ void __launch_bounds__(128) k_in_conv(const float* __restrict__ x, const float* __restrict__ w,
                                                 const float* __restrict__ bias, bf16* __restrict__ out,
                                                 int B, int H, int W, int Co) {
+    pdl_entry();
     extern __shared__ float sw[];                 // [CI*9][Co] + [Co]
     constexpr int K = CI * 9;
     for (int i = threadIdx.x; i < Co * K; i += blockDim.x) sw[(i % K) * Co + i / K] = w[i];
@@ -926,6 +995,7 @@ template <int CI>
 __global__ void __launch_bounds__(256) k_corr3x3(const bf16* __restrict__ wide, const float* __restrict__ narrow, float* __restrict__ dw,
                                                  long long s_c, long long s_ci, long long s_t, int flip_t, float* __restrict__ dbias_wide,
                                                  int B, int H, int W, int C, int pix_per_block) {
+    pdl_entry();
     constexpr int K = CI * 9, PB = 32;
     __shared__ float sx[PB][K + 1];
     const int c = threadIdx.x;
@@ -973,6 +1043,7 @@ __global__ void __launch_bounds__(256) k_corr3x3(const bf16* __restrict__ wide, 
 template <int CO>
 __global__ void __launch_bounds__(256) k_out_conv(const bf16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ out, int B, int H, int W, int C) {
+    pdl_entry();
     // 4 lanes per pixel group (C/4 channels each); a lane handles PX consecutive pixels of a row so that every 16-byte
     // weight fetch from shared memory feeds PX pixels (the one-pixel version was bound by shared-memory reads)
     constexpr int PX = 4;
@@ -1041,6 +1112,7 @@ __global__ void __launch_bounds__(256) k_out_conv(const bf16* __restrict__ a, co
 }
 // w'[c][co*9 + t'] = w[co][c][8 - t']  : the 3->C "in_conv" whose forward is the data-gradient of out_conv
 __global__ void k_flip_transpose_w(const float* __restrict__ w, float* __restrict__ wt, int Co, int C) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Co * C * 9) return;
     const int t = i % 9, c = (i / 9) % C, co = i / (9 * C);
@@ -1048,6 +1120,7 @@ __global__ void k_flip_transpose_w(const float* __restrict__ w, float* __restric
 }
 // sum over pixels of a narrow NCHW fp32 tensor: out[c] += sum_{b,p} x[b][c][p]   (bias gradient of out_conv)
 __global__ void __launch_bounds__(256) k_chansum_nchw(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
+    pdl_entry();
     const int c = blockIdx.y;
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * HW; i += (long long)gridDim.x * blockDim.x) {
@@ -1064,6 +1137,7 @@ __global__ void __launch_bounds__(256) k_chansum_nchw(const float* __restrict__ 
 // dy [B][HW][C] bf16 -> per_img[b][ld] (+=, fp32 atomics, optional) and total[c] (+=)
 __global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, float* per_img, int ld, float* total, float* total2,
                                                int HW, int C, int C_valid, int pix_per_block) {
+    pdl_entry();
     // blockDim.x = (256/oct)*oct: one channel octet per thread; partials are merged in shared memory so that each block
     // issues ONE atomic per channel (the first version issued one per thread and spent 14 ms/step in contention)
     extern __shared__ float sh[];                 // [C]
@@ -1094,6 +1168,7 @@ __global__ void __launch_bounds__(256) k_colsum(const bf16* __restrict__ dy, flo
 
 // ============================================================================ softmax over rows of S fp32 [rows][T] -> P bf16
 __global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int T) {
+    pdl_entry();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + warp;
     if (row >= rows) return;
@@ -1111,6 +1186,7 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ 
 // dS = P * (dP - rowsum(dP*P)) * scale  -> bf16
 __global__ void __launch_bounds__(256) k_softmax_bwd(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
                                                     long long rows, int T, float scale) {
+    pdl_entry();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + warp;
     if (row >= rows) return;
@@ -1123,6 +1199,7 @@ __global__ void __launch_bounds__(256) k_softmax_bwd(const bf16* __restrict__ P,
 
 // ============================================================================ nearest 2x upsample (unet.py:199) and its adjoint
 __global__ void k_upsample2x(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+    pdl_entry();
     const int oct = C >> 3;
     const long long total = (long long)B * 4 * H * W * oct;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1132,6 +1209,7 @@ __global__ void k_upsample2x(const bf16* __restrict__ in, bf16* __restrict__ out
     }
 }
 __global__ void k_upsample2x_bwd(const bf16* __restrict__ dout, bf16* __restrict__ din, int B, int H, int W, int C, int accumulate) {
+    pdl_entry();
     const int oct = C >> 3;
     const long long total = (long long)B * H * W * oct;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1156,6 +1234,7 @@ __global__ void k_upsample2x_bwd(const bf16* __restrict__ dout, bf16* __restrict
 }
 // dst (+)= src  (bf16, 8 at a time)
 __global__ void k_add_bf16(bf16* __restrict__ dst, const bf16* __restrict__ src, long long n_oct, int accumulate) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_oct; i += (long long)gridDim.x * blockDim.x) {
         if (!accumulate) { reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i); continue; }
         float a[8], b[8];
@@ -1171,6 +1250,7 @@ __global__ void k_add_bf16(bf16* __restrict__ dst, const bf16* __restrict__ src,
 // q_sample (diffusion.py:92-97): x_t = sqrt_ab[t]*x0 + sqrt_1m_ab[t]*noise, fp32 NCHW, same op order as the reference
 __global__ void k_qsample(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
                           const float* __restrict__ tab_a, const float* __restrict__ tab_s, float* __restrict__ xt, int per_img, long long total) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / per_img);
         const float a = tab_a[t[b]], s = tab_s[t[b]];
@@ -1179,6 +1259,7 @@ __global__ void k_qsample(const float* __restrict__ x0, const float* __restrict_
 }
 // per-sample MSE (diffusion.py:239, functions.py:99-101) and d(loss)/d(eps) = gscale[b] * 2*(eps-target)/per_img as NHWC bf16
 __global__ void __launch_bounds__(256) k_mse(const float* __restrict__ eps, const float* __restrict__ target, float* __restrict__ losses, int per_img) {
+    pdl_entry();
     const int b = blockIdx.x;
     float s = 0.f;
     for (int i = threadIdx.x; i < per_img; i += blockDim.x) {
@@ -1194,12 +1275,14 @@ __global__ void __launch_bounds__(256) k_mse(const float* __restrict__ eps, cons
 // gradient of the per-sample MSE w.r.t. eps (fp32 NCHW): d_eps = gscale[b] * 2*(eps-target)/per_img
 __global__ void k_mse_grad(const float* __restrict__ eps, const float* __restrict__ target, const float* __restrict__ gscale,
                            float* __restrict__ d_eps, int per_img, long long total) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / per_img);
         d_eps[i] = gscale[b] * 2.f * (eps[i] - target[i]) / (float)per_img;
     }
 }
 __global__ void k_nchw_f32_to_nhwc_bf16(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C, int HW, int Cp) {
+    pdl_entry();
     const long long total = (long long)B * HW * Cp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % Cp); const long long pix = i / Cp; const int b = (int)(pix / HW), r = (int)(pix % HW);
@@ -1212,6 +1295,7 @@ __global__ void k_nchw_f32_to_nhwc_bf16(const float* __restrict__ src, bf16* __r
 //   z == nullptr and seed != 0: the noise is drawn in-kernel (Philox4x32-10 + Box-Muller; NOT torch's stream)
 __global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict__ x /*in: x_t, out: x_{t-1}*/, const float* __restrict__ z,
                                const float* __restrict__ coef, unsigned long long seed, long long total) {
+    pdl_entry();
     const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], sg = coef[4], nz = coef[5];
     const uint32_t step = (uint32_t)coef[6];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1232,6 +1316,7 @@ __global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict_
 // one block: fetch step i = *counter, broadcast t_model[i] to t_buf[B], copy the coefficient row, then advance the counter
 __global__ void k_sampler_prep(int* __restrict__ counter, const long long* __restrict__ t_model, const float* __restrict__ coef_table /*[S][6]*/,
                                long long* __restrict__ t_buf, float* __restrict__ coef_cur /*[7]*/, int B) {
+    pdl_entry();
     const int i = *counter;
     for (int b = threadIdx.x; b < B; b += blockDim.x) t_buf[b] = t_model[i];
     if (threadIdx.x < 6) coef_cur[threadIdx.x] = coef_table[i * 6 + threadIdx.x];
@@ -1245,6 +1330,7 @@ __global__ void k_sampler_prep(int* __restrict__ counter, const long long* __res
 // tap' = flip ? 8 - tap : tap   (flip for stride-1 3x3; no flip for the stride-2 gather form and 1x1)
 __global__ void k_pack_conv_w(const float* __restrict__ w, bf16* fwd, long long ld_f, int k_off, bf16* dgr, long long ld_d, int flip,
                               int Co, int Ci, int taps) {
+    pdl_entry();
     const long long total = (long long)Co * Ci * taps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
@@ -1255,6 +1341,7 @@ __global__ void k_pack_conv_w(const float* __restrict__ w, bf16* fwd, long long 
 }
 // dgrad pack with a padded Co (out_conv: Co=3 -> 8): dgr[ci][tap'*Cop + co]
 __global__ void k_pack_conv_w_padded(const float* __restrict__ w, bf16* dgr, long long ld_d, int flip, int Co, int Cop, int Ci, int taps) {
+    pdl_entry();
     const long long total = (long long)Co * Ci * taps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
@@ -1265,6 +1352,7 @@ __global__ void k_pack_conv_w_padded(const float* __restrict__ w, bf16* dgr, lon
 // data-gradient pack of a stride-2 3x3 conv: [Ci][9*Co] bf16 in four output-parity blocks
 // {(py,px)=(0,0): 4 taps @0, (0,1): 2 taps @4Co, (1,0): 2 taps @6Co, (1,1): 1 tap @8Co}; taps ordered (ky asc, kx asc).
 __global__ void k_pack_conv_w_s2dgrad(const float* __restrict__ w, bf16* __restrict__ dgr, long long ld_d, int Co, int Ci) {
+    pdl_entry();
     const long long total = (long long)Co * Ci * 9;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % 9); const long long r = i / 9; const int ci = (int)(r % Ci), co = (int)(r / Ci);
@@ -1290,6 +1378,7 @@ __device__ __forceinline__ int pack_dcol(const PackEntry& e, int t) {     // col
 // the fp32 side and the packed side are accessed in 16-byte-or-larger contiguous pieces (the element-wise first version spent
 // 0.6 ms/step on 2-byte scattered writes).
 __global__ void __launch_bounds__(256) k_pack_table(const PackEntry* __restrict__ table) {
+    pdl_entry();
     const PackEntry e = table[blockIdx.y];
     if (e.kind == PK_BIAS_ADD) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.Co; i += gridDim.x * blockDim.x) e.fout[i] = e.w[i] + (e.w2 ? e.w2[i] : 0.f);
@@ -1356,6 +1445,7 @@ __global__ void __launch_bounds__(256) k_pack_table(const PackEntry* __restrict_
 __global__ void __launch_bounds__(256) k_splitk_finalize(float* __restrict__ scratch, const float* __restrict__ bias, const float* __restrict__ rowvec,
                                                         int rowvec_ld, int rows_per_vec, const bf16* __restrict__ residual, bf16* __restrict__ out,
                                                         long long M, int N) {
+    pdl_entry();
     const long long total = M * (N / 8);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / (N / 8); const int c = (int)(i % (N / 8)) * 8;
@@ -1372,6 +1462,7 @@ __global__ void __launch_bounds__(256) k_splitk_finalize(float* __restrict__ scr
 // packed grad [tap][Co][Ci] fp32 -> OIHW fp32 (=)
 // (the scratch is cleared behind the read so the next backward starts from zeros without a memset)
 __global__ void k_unpack_conv_grad(float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps) {
+    pdl_entry();
     const long long total = (long long)Co * Ci * taps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % taps); const long long r = i / taps; const int ci = (int)(r % Ci), co = (int)(r / Ci);
@@ -1381,10 +1472,12 @@ __global__ void k_unpack_conv_grad(float* __restrict__ packed, float* __restrict
     }
 }
 __global__ void k_fill_f32(float* p, float v, long long n) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 // small fp32 elementwise helpers for the timestep-embedding MLP backward: dx = dy * silu'(x)
 __global__ void k_silu_bwd_f32(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dx[i] = dy[i] * silu_grad_f(x[i]);
 }
 

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
+    pdl_trigger();                                  // dependents may be scheduled; they block in their own pdl_wait()
     using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS>;
     constexpr int A_MN = (MODE == GEMM_MNMN) ? 1 : 0;
     constexpr int B_MN = (MODE == GEMM_KK) ? 0 : 1;
@@ -135,6 +136,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncthreads();
     if (CLUSTER > 1) cluster_sync_all();            // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
+    pdl_wait();                                     // prologue above overlapped the previous kernel's tail; its data is visible from here
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {

@@ -205,7 +205,7 @@ struct UnetEngine {
                 if (rc) { plan_error = rc; return; }
                 push(L, c.name + "[splitk]", fl, [=](cudaStream_t st) {
                     const int r2 = launch_gemm(g, st); if (r2) return r2;
-                    k_splitk_finalize<<<nfin, 256, 0, st>>>(scratch, bias, rowvec, rvld, rpv, resid, outp, M, N);
+                    launch_k(k_splitk_finalize, nfin, 256, 0, st, scratch, bias, rowvec, rvld, rpv, resid, outp, M, N);
                     return (int)cudaGetLastError(); }, 2);
                 return;
             }
@@ -226,11 +226,11 @@ struct UnetEngine {
         UnetEngine* self = this;
         push(L, c.name + "[simt]", fl, [g, grid, nchw_dyn, self](cudaStream_t st) {
             ConvG gg = g; if (nchw_dyn && self->eps_dst) gg.out = self->eps_dst;
-            k_conv_generic<<<grid, 256, 0, st>>>(gg); return (int)cudaGetLastError(); });
+            launch_k(k_conv_generic, grid, 256, 0, st, gg); return (int)cudaGetLastError(); });
         if (c.has_skip) {
             ConvG s = g; s.in = gsrc(c.skip_in); s.wp = c.wp + (long long)taps * Cin; s.ksize = 1; s.pad = 0; s.map = MAP_NORMAL; s.stride = 1;
             s.bias = nullptr; s.rowvec = nullptr; s.residual = nullptr; s.accumulate = 1;
-            push(L, c.name + ".skip[simt]", 0, [s, grid](cudaStream_t st) { k_conv_generic<<<grid, 256, 0, st>>>(s); return (int)cudaGetLastError(); });
+            push(L, c.name + ".skip[simt]", 0, [s, grid](cudaStream_t st) { launch_k(k_conv_generic, grid, 256, 0, st, s); return (int)cudaGetLastError(); });
         }
     }
     float* eps_dst = nullptr;   // run-time destination of the final conv (caller buffer or internal eps buffer)
@@ -292,7 +292,7 @@ struct UnetEngine {
         w.pix_per_split = (int)(((P + splits - 1) / splits + 15) / 16 * 16);
         splits = (int)((P + w.pix_per_split - 1) / w.pix_per_split);
         const dim3 grid((Cin + 63) / 64, (Co + 63) / 64, taps * splits);
-        push(bwd_ops, name + "[simt]", fl, [w, grid](cudaStream_t st) { k_wgrad_generic<<<grid, 256, 0, st>>>(w); return (int)cudaGetLastError(); }, 1, true);
+        push(bwd_ops, name + "[simt]", fl, [w, grid](cudaStream_t st) { launch_k(k_wgrad_generic, grid, 256, 0, st, w); return (int)cudaGetLastError(); }, 1, true);
     }
     size_t alloc_once_zero(size_t bytes) {   // carve from the plan-time-zeroed arena (contiguous region grown on demand)
         const size_t o = alloc(bytes);
@@ -360,16 +360,16 @@ struct UnetEngine {
         }
         int nblk, ppb; gn_grid(Bn, HW, 6, nblk, ppb);
         const dim3 g1(nblk, Bn);
+        GnFin fin; fin.gamma = ga; fin.beta = be; fin.K = K; fin.eps = 1e-6f; fin.ticket = at<int>(zero_fwd((size_t)Bn * 4));
         push(L, name + ".stats", 0, [=](cudaStream_t st) {
-            k_gn_stats<<<g1, thr, 0, st>>>(gs, stats, HW, ppb);
-            k_gn_finalize<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, ga, be, K, Bn, C, 1.0 / ((double)HW * (C / 32)), 1e-6f);
-            return (int)cudaGetLastError(); }, 2);
+            launch_k(k_gn_stats, g1, thr, 0, st, gs, stats, HW, ppb, fin);
+            return (int)cudaGetLastError(); });
         GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
         int nb2, ppb2; gn_grid(Bn, HW, 4, nb2, ppb2);
         const dim3 g2(nb2, Bn);
         UnetEngine* self = this;
         push(L, name + ".apply", 0, [a, g2, thr, ppb2, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
-            k_gn_apply<<<g2, thr, 0, st>>>(aa, ppb2); return (int)cudaGetLastError(); });
+            launch_k(k_gn_apply, g2, thr, 0, st, aa, ppb2); return (int)cudaGetLastError(); });
         return sv;
     }
     // dx(in) (=|+=) gn_bwd(dy) + addend ; dgamma/dbeta accumulate into the flat grads
@@ -385,6 +385,9 @@ struct UnetEngine {
         const T4 g0 = grad_of(in.t0, &f0); a.dx0 = bp(g0); a.acc0 = f0 ? 0 : 1;
         if (in.two) { const T4 g1 = grad_of(in.t1, &f1); a.dx1 = bp(g1); a.acc1 = f1 ? 0 : 1; }
         a.addend = addend; a.B = Bn; a.HW = HW; a.silu = sv.silu; a.drop_p = sv.drop_p; a.layer = sv.layer; a.mask = sv.mask;
+        a.ticket = at<int>(zero_bwd((size_t)Bn * 4));
+        static const bool no_dn = getenv("DDPM_GN_NO_DN") != nullptr;
+        a.dn_inplace = (sv.silu && !no_dn) ? 1 : 0;
         const int thr = oct_threads(C);
         {
             const size_t extra = (size_t)(5 * C + 64) * 4 + 64;
@@ -414,11 +417,10 @@ struct UnetEngine {
         UnetEngine* self = this;
         push(bwd_ops, name + ".gn_bwd", 0, [=](cudaStream_t st) {
             GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
-            k_gn_bwd_reduce<<<g1, thr, shm, st>>>(aa);
-            k_gn_bwd_finalize<<<Bn, 256, 0, st>>>(aa);
-            if (shm2) k_gn_bwd_apply<true><<<g1, thr, shm2, st>>>(aa, cs_per_img, cs_ld, cs_total, cs_total2);
-            else      k_gn_bwd_apply<false><<<g1, thr, 0, st>>>(aa, cs_per_img, cs_ld, cs_total, cs_total2);
-            return (int)cudaGetLastError(); }, 3);
+            launch_k(k_gn_bwd_reduce, g1, thr, shm, st, aa);
+            if (shm2) launch_k(k_gn_bwd_apply<true>, g1, thr, shm2, st, aa, cs_per_img, cs_ld, cs_total, cs_total2);
+            else      launch_k(k_gn_bwd_apply<false>, g1, thr, 0, st, aa, cs_per_img, cs_ld, cs_total, cs_total2);
+            return (int)cudaGetLastError(); }, 2);
     }
     void colsum_op(const std::string& name, const T4& dy, float* per_img, int ld, float* total, float* total2, int C_valid) {
         const int HW = dy.H * dy.W, C = dy.C, Bn = dy.B;
@@ -427,7 +429,7 @@ struct UnetEngine {
         const int ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
         const dim3 g(nblk, Bn); const bf16* p = bp(dy);
         const size_t shm = (size_t)C * 4;
-        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { k_colsum<<<g, thr, shm, st>>>(p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); }, 1, /*side=*/true);
+        push(bwd_ops, name + ".colsum", 0, [=](cudaStream_t st) { launch_k(k_colsum, g, thr, shm, st, p, per_img, ld, total, total2, HW, C, C_valid, ppb); return (int)cudaGetLastError(); }, 1, /*side=*/true);
     }
 
     // ------------------------------------------------------------------ packed weights (table-driven: one launch re-packs everything)
@@ -470,28 +472,64 @@ struct UnetEngine {
     // Ops flagged `side` (bias-gradient column sums, gradient unpacks: small, memory-bound, nothing downstream needs them
     // before the end of the pass) are forked onto a second stream so they overlap the tensor-core kernels, and joined at
     // the end of the list.  Fork/join are event edges, so the pattern is CUDA-graph capturable.
+    // With side work in the list, the dependent main chain itself moves to a HIGH-priority stream (forked from / joined to the
+    // caller's stream) so that at every kernel boundary the block scheduler prefers the critical path over the leaf work.
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int run_list(std::vector<Op>& L, cudaStream_t st) {
+    cudaStream_t hp_stream = nullptr; cudaEvent_t ev_hp_fork = nullptr, ev_hp_join = nullptr;
+    int run_list(std::vector<Op>& L, cudaStream_t caller_st) {
+        static const bool hp_main = getenv("DDPM_HP_MAIN") != nullptr;
+        cudaStream_t st = caller_st;
+        bool any_side = false; for (auto& o : L) any_side |= o.side;
+        const bool use_hp = hp_main && hp_stream && any_side && !getenv("DDPM_DEBUG_SYNC") && !getenv("DDPM_NO_SIDE_STREAM");
+        if (use_hp) {
+            if (cudaEventRecord(ev_hp_fork, caller_st) || cudaStreamWaitEvent(hp_stream, ev_hp_fork, 0)) return fail(-20, "priority-stream fork failed");
+            st = hp_stream;
+        }
         static const bool dbg = getenv("DDPM_DEBUG_SYNC") != nullptr;   // serialise + attribute faults to an op (never under graph capture)
         static const bool no_side = getenv("DDPM_NO_SIDE_STREAM") != nullptr;
         bool forked = false;
+        // DDPM_OP_TIMING=<file>: CUDA events after every main-stream op (side stream stays concurrent), appended as "name ms" lines
+        static const char* timing_path = getenv("DDPM_OP_TIMING");
+        std::vector<cudaEvent_t> tev;
+        if (timing_path && !dbg) { tev.resize(L.size() + 1); for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], st); }
+        size_t oi = 0; int main_since_fork = 0;
         for (auto& o : L) {
             int rc;
+            ++oi;
             if (o.side && side_stream && !dbg && !no_side) {
-                rc = (int)cudaEventRecord(ev_fork, st);
-                if (!rc) rc = (int)cudaStreamWaitEvent(side_stream, ev_fork, 0);
+                rc = 0;
+                if (main_since_fork || !forked) {     // consecutive side ops share one fork edge
+                    rc = (int)cudaEventRecord(ev_fork, st);
+                    if (!rc) rc = (int)cudaStreamWaitEvent(side_stream, ev_fork, 0);
+                    main_since_fork = 0;
+                }
                 if (!rc) rc = o.run(side_stream);
                 forked = true;
             } else {
                 rc = o.run(st);
+                ++main_since_fork;
             }
             if (!rc && dbg) rc = (int)cudaStreamSynchronize(st);
             if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc));
+            if (!tev.empty()) cudaEventRecord(tev[oi], st);
         }
         if (forked) {
             int rc = (int)cudaEventRecord(ev_join, side_stream);
             if (!rc) rc = (int)cudaStreamWaitEvent(st, ev_join, 0);
             if (rc) return fail(-20, "side-stream join failed: %s", cudaGetErrorString((cudaError_t)rc));
+        }
+        if (!tev.empty()) {
+            cudaEvent_t fin; cudaEventCreate(&fin); cudaEventRecord(fin, st); cudaStreamSynchronize(st);
+            if (FILE* f = fopen(timing_path, "a")) {
+                for (size_t i = 0; i < L.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, tev[i], tev[i + 1]); fprintf(f, "%s%s %.5f\n", L[i].side ? "[side]" : "", L[i].name.c_str(), ms); }
+                float ms = 0; cudaEventElapsedTime(&ms, tev[L.size()], fin); fprintf(f, "[join] %.5f\n", ms);
+                fclose(f);
+            }
+            for (auto& e : tev) cudaEventDestroy(e);
+            cudaEventDestroy(fin);
+        }
+        if (use_hp) {
+            if (cudaEventRecord(ev_hp_join, hp_stream) || cudaStreamWaitEvent(caller_st, ev_hp_join, 0)) return fail(-20, "priority-stream join failed");
         }
         return 0;
     }

@@ -46,8 +46,8 @@ inline void UnetEngine::bmm(std::vector<Op>& L, const std::string& name, int for
     else if (form == 1) { p.sa_m = lda; p.sa_k = 1; p.sb_k = ldb; p.sb_n = 1; }
     else { p.sa_m = 1; p.sa_k = lda; p.sb_k = ldb; p.sb_n = 1; }
     const dim3 grid((N + 63) / 64, (M + 63) / 64, nb);
-    if (c_f32) push(L, name + "[simt]", fl, [p, grid](cudaStream_t st) { k_sgemm<bf16, bf16, float><<<grid, 256, 0, st>>>(p); return (int)cudaGetLastError(); });
-    else       push(L, name + "[simt]", fl, [p, grid](cudaStream_t st) { k_sgemm<bf16, bf16, bf16><<<grid, 256, 0, st>>>(p); return (int)cudaGetLastError(); });
+    if (c_f32) push(L, name + "[simt]", fl, [p, grid](cudaStream_t st) { launch_k(k_sgemm<bf16, bf16, float>, grid, 256, 0, st, p); return (int)cudaGetLastError(); });
+    else       push(L, name + "[simt]", fl, [p, grid](cudaStream_t st) { launch_k(k_sgemm<bf16, bf16, bf16>, grid, 256, 0, st, p); return (int)cudaGetLastError(); });
 }
 
 // ResidualBlock (unet.py:63-89):  out = skip(x) + conv2(drop(silu(gn2(conv1(silu(gn1(x))) + fc(silu(temb))))))
@@ -125,7 +125,7 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     const long long ldq = 3 * C, sq = (long long)T * 3 * C;
     bmm(fwd_ops, p + ".qk", 0, q, ldq, sq, q + C, ldq, sq, S, T, (long long)T * T, true, Bn, T, C, scale, &fwd_flops);
     { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
-      push(fwd_ops, p + ".softmax", 0, [=](cudaStream_t st) { k_softmax_rows<<<nblk, 256, 0, st>>>(S, Pm, rows, T); return (int)cudaGetLastError(); }); }
+      push(fwd_ops, p + ".softmax", 0, [=](cudaStream_t st) { launch_k(k_softmax_rows, nblk, 256, 0, st, S, Pm, rows, T); return (int)cudaGetLastError(); }); }
     T4 O = newT(Bn, h, w, C);
     bmm(fwd_ops, p + ".pv", 1, Pm, T, (long long)T * T, q + 2 * C, ldq, sq, bp(O), C, (long long)T * C, false, Bn, T, C, 1.f, &fwd_flops);
     const Packed wout = pack_conv(p + ".project_out", C, C, 1, 0, false, true);
@@ -147,7 +147,7 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
         bmm(bwd_ops, p + ".dP", 0, dOp, C, (long long)T * C, q + 2 * C, ldq, sq, dP, T, (long long)T * T, true, Bn, T, C, 1.f, &bwd_flops);
         bmm(bwd_ops, p + ".dV", 2, Pm, T, (long long)T * T, dOp, C, (long long)T * C, dq + 2 * C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
-          push(bwd_ops, p + ".softmax_bwd", 0, [=](cudaStream_t st) { k_softmax_bwd<<<nblk, 256, 0, st>>>(Pm, dP, dS, rows, T, scale); return (int)cudaGetLastError(); }); }
+          push(bwd_ops, p + ".softmax_bwd", 0, [=](cudaStream_t st) { launch_k(k_softmax_bwd, nblk, 256, 0, st, Pm, dP, dS, rows, T, scale); return (int)cudaGetLastError(); }); }
         bmm(bwd_ops, p + ".dQ", 1, dS, T, (long long)T * T, q + C, ldq, sq, dq, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         bmm(bwd_ops, p + ".dK", 2, dS, T, (long long)T * T, q, ldq, sq, dq + C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         colsum_op(p + ".project_in.bias", dqkv, nullptr, 0, GP(p + ".project_in.bias"), nullptr, 3 * C);
@@ -215,7 +215,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
     const int C = x.C, Bn = x.B, h = x.H, w = x.W;
     T4 up = newT(Bn, 2 * h, 2 * w, C);
     { const bf16* src = bp(x); bf16* dst = bp(up); const int n = grid_for((long long)Bn * 4 * h * w * (C / 8));
-      push(fwd_ops, p + ".upsample", 0, [=](cudaStream_t st) { k_upsample2x<<<n, 256, 0, st>>>(src, dst, Bn, h, w, C); return (int)cudaGetLastError(); }); }
+      push(fwd_ops, p + ".upsample", 0, [=](cudaStream_t st) { launch_k(k_upsample2x, n, 256, 0, st, src, dst, Bn, h, w, C); return (int)cudaGetLastError(); }); }
     const Packed pk = pack_conv(p, C, C, 3, 0, true, true);
     T4 out = newT(Bn, 2 * h, 2 * w, C);
     { ConvSpec c; c.name = p; c.in = one(up); c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = 2 * h; c.Wo = 2 * w;
@@ -230,7 +230,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
         wgrad_op(p + ".wgrad", dY, one(up), 3, 1, MAP_NORMAL, GP(p + ".weight"), C);
         bool first = true; const T4 dx = grad_of(x, &first);
         const bf16* src = bp(dUp); bf16* dst = bp(dx); const int n = grid_for((long long)Bn * h * w * (C / 8)); const int acc = first ? 0 : 1;
-        push(bwd_ops, p + ".upsample_bwd", 0, [=](cudaStream_t st) { k_upsample2x_bwd<<<n, 256, 0, st>>>(src, dst, Bn, h, w, C, acc); return (int)cudaGetLastError(); });
+        push(bwd_ops, p + ".upsample_bwd", 0, [=](cudaStream_t st) { launch_k(k_upsample2x_bwd, n, 256, 0, st, src, dst, Bn, h, w, C, acc); return (int)cudaGetLastError(); });
     });
     return out;
 }
@@ -274,18 +274,18 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     tp_table_off = alloc(sizeof(SgemmParams) * nblocks); tpw_table_off = alloc(sizeof(SgemmParams) * nblocks); tpd_table_off = alloc(sizeof(SgemmParams) * nblocks);
     {
         const int Bn = B;
-        push(fwd_ops, "temb.sin", 0, [=](cudaStream_t st) { k_timestep_embedding<<<(Bn * (ch / 2) + 127) / 128, 128, 0, st>>>(self->t_in, emb, Bn, ch); return (int)cudaGetLastError(); });
+        push(fwd_ops, "temb.sin", 0, [=](cudaStream_t st) { launch_k(k_timestep_embedding, (Bn * (ch / 2) + 127) / 128, 128, 0, st, self->t_in, emb, Bn, ch); return (int)cudaGetLastError(); });
         SgemmParams a; memset(&a, 0, sizeof a);
         a.A = emb; a.B = PP("embed.0.weight"); a.C = e0; a.bias = PP("embed.0.bias"); a.M = B; a.N = E; a.K = ch;
         a.sa_m = ch; a.sa_k = 1; a.sb_k = 1; a.sb_n = ch; a.sc_m = E; a.sc_n = 1; a.alpha = 1.f;
         const dim3 g0((E + 63) / 64, (B + 63) / 64, 1);
-        push(fwd_ops, "temb.fc0", 2.0 * B * E * ch, [a, g0](cudaStream_t st) { k_sgemm<float, float, float><<<g0, 256, 0, st>>>(a); return (int)cudaGetLastError(); });
+        push(fwd_ops, "temb.fc0", 2.0 * B * E * ch, [a, g0](cudaStream_t st) { launch_k(k_sgemm<float, float, float>, g0, 256, 0, st, a); return (int)cudaGetLastError(); });
         SgemmParams b = a; b.A = e0; b.B = PP("embed.2.weight"); b.C = e1; b.bias = PP("embed.2.bias"); b.K = E; b.sa_m = E; b.sb_n = E; b.silu_a = 1; b.ksplit = KS;
         const dim3 g0s((E + 63) / 64, (B + 63) / 64, KS);
-        push(fwd_ops, "temb.fc1", 2.0 * B * E * E, [b, g0s](cudaStream_t st) { k_sgemm<float, float, float><<<g0s, 256, 0, st>>>(b); return (int)cudaGetLastError(); });
+        push(fwd_ops, "temb.fc1", 2.0 * B * E * E, [b, g0s](cudaStream_t st) { launch_k(k_sgemm<float, float, float>, g0s, 256, 0, st, b); return (int)cudaGetLastError(); });
         const SgemmParams* tab = at<SgemmParams>(tp_table_off);
         const dim3 g1((maxc + 63) / 64, (B + 63) / 64, nblocks * KS);
-        push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { k_sgemm_table<<<g1, 256, 0, st>>>(tab, KS); return (int)cudaGetLastError(); });
+        push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { launch_k(k_sgemm_table, g1, 256, 0, st, tab, (int)KS); return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * E * ch + 2.0 * B * E * E;
     }
     int blk = 0;
@@ -316,25 +316,25 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         tape.push_back([=]() {
             const SgemmParams* tw = at<SgemmParams>(tpw_table_off); const SgemmParams* td = at<SgemmParams>(tpd_table_off);
             const dim3 gw((maxc + 63) / 64, (E + 63) / 64, nblocks), gd((E + 63) / 64, (B + 63) / 64, nblocks);
-            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { k_sgemm_table<<<gw, 256, 0, st>>>(tw, 1); k_sgemm_table<<<gd, 256, 0, st>>>(td, 1); return (int)cudaGetLastError(); }, 2);
+            push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { launch_k(k_sgemm_table, gw, 256, 0, st, tw, 1); launch_k(k_sgemm_table, gd, 256, 0, st, td, 1); return (int)cudaGetLastError(); }, 2);
             float* d_e1 = at<float>(alloc((size_t)B * E * 4)); float* d_s0 = at<float>(zero_bwd((size_t)B * E * 4)); float* d_e0 = at<float>(alloc((size_t)B * E * 4));
             const long long nE = (long long)B * E; const int Bn = B;
             float* gw2 = GP("embed.2.weight"); float* gb2 = GP("embed.2.bias"); float* gw0 = GP("embed.0.weight"); float* gb0 = GP("embed.0.bias");
             const float* w2 = PP("embed.2.weight");
             push(bwd_ops, "temb.mlp.bwd", 0, [=](cudaStream_t st) {
-                k_silu_bwd_f32<<<grid_for(nE), 256, 0, st>>>(e1, d_st, d_e1, nE);
+                launch_k(k_silu_bwd_f32, grid_for(nE), 256, 0, st, e1, d_st, d_e1, nE);
                 SgemmParams a; memset(&a, 0, sizeof a);           // dW2[n][k] = sum_b silu(e0[b][k]) d_e1[b][n]
                 a.A = e0; a.B = d_e1; a.C = gw2; a.M = E; a.N = E; a.K = Bn; a.sa_m = 1; a.sa_k = E; a.sb_k = E; a.sb_n = 1; a.sc_m = 1; a.sc_n = E; a.alpha = 1.f; a.silu_a = 1;
-                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (E + 63) / 64, 1), 256, 0, st>>>(a);
-                k_colsum_f32<<<(E + 127) / 128, 128, 0, st>>>(d_e1, gb2, Bn, E, E);
+                launch_k(k_sgemm<float, float, float>, dim3((E + 63) / 64, (E + 63) / 64, 1), 256, 0, st, a);
+                launch_k(k_colsum_f32, (E + 127) / 128, 128, 0, st, d_e1, gb2, Bn, E, E);
                 SgemmParams b; memset(&b, 0, sizeof b);           // d_s0[b][k] = sum_n d_e1[b][n] W2[n][k]
                 b.A = d_e1; b.B = w2; b.C = d_s0; b.M = Bn; b.N = E; b.K = E; b.sa_m = E; b.sa_k = 1; b.sb_k = E; b.sb_n = 1; b.sc_m = E; b.sc_n = 1; b.alpha = 1.f; b.ksplit = 4;
-                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (Bn + 63) / 64, 4), 256, 0, st>>>(b);
-                k_silu_bwd_f32<<<grid_for(nE), 256, 0, st>>>(e0, d_s0, d_e0, nE);
+                launch_k(k_sgemm<float, float, float>, dim3((E + 63) / 64, (Bn + 63) / 64, 4), 256, 0, st, b);
+                launch_k(k_silu_bwd_f32, grid_for(nE), 256, 0, st, e0, d_s0, d_e0, nE);
                 SgemmParams c; memset(&c, 0, sizeof c);           // dW0[n][k] = sum_b emb[b][k] d_e0[b][n]
                 c.A = emb; c.B = d_e0; c.C = gw0; c.M = ch; c.N = E; c.K = Bn; c.sa_m = 1; c.sa_k = ch; c.sb_k = E; c.sb_n = 1; c.sc_m = 1; c.sc_n = ch; c.alpha = 1.f;
-                k_sgemm<float, float, float><<<dim3((E + 63) / 64, (ch + 63) / 64, 1), 256, 0, st>>>(c);
-                k_colsum_f32<<<(E + 127) / 128, 128, 0, st>>>(d_e0, gb0, Bn, E, E);
+                launch_k(k_sgemm<float, float, float>, dim3((E + 63) / 64, (ch + 63) / 64, 1), 256, 0, st, c);
+                launch_k(k_colsum_f32, (E + 127) / 128, 128, 0, st, d_e0, gb0, Bn, E, E);
                 return (int)cudaGetLastError(); }, 7);
         });
     }
@@ -347,10 +347,10 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         const int Bn = B, Hn = H, Wn = W;
         push(fwd_ops, "in_conv", 2.0 * B * H * W * ch * Cin * 9, [=](cudaStream_t st) {
             switch (Cin) {
-                case 1: k_in_conv<1><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                case 2: k_in_conv<2><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                case 3: k_in_conv<3><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                default: k_in_conv<4><<<n, 128, shm, st>>>(self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 1: launch_k(k_in_conv<1>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 2: launch_k(k_in_conv<2>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 3: launch_k(k_in_conv<3>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                default: launch_k(k_in_conv<4>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
             }
             return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
@@ -362,10 +362,10 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             const long long s_c = (long long)Cin * 9;
             push(bwd_ops, "in_conv.wgrad", 2.0 * P * ch * Cin * 9, [=](cudaStream_t st) {
                 switch (Cin) {
-                    case 1: k_corr3x3<1><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
-                    case 2: k_corr3x3<2><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
-                    case 3: k_corr3x3<3><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
-                    default: k_corr3x3<4><<<nb, ch, 0, st>>>(d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    case 1: launch_k(k_corr3x3<1>, nb, ch, 0, st, d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    case 2: launch_k(k_corr3x3<2>, nb, ch, 0, st, d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    case 3: launch_k(k_corr3x3<3>, nb, ch, 0, st, d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
+                    default: launch_k(k_corr3x3<4>, nb, ch, 0, st, d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
                 }
                 return (int)cudaGetLastError(); });
         });
@@ -411,10 +411,10 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         fwd_flops += fl;
         push(fwd_ops, "out_conv.2", fl, [=](cudaStream_t st) {
             switch (Cout) {
-                case 1: k_out_conv<1><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
-                case 2: k_out_conv<2><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
-                case 3: k_out_conv<3><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
-                default: k_out_conv<4><<<nblk, 256, shm, st>>>(ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                case 1: launch_k(k_out_conv<1>, nblk, 256, shm, st, ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                case 2: launch_k(k_out_conv<2>, nblk, 256, shm, st, ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                case 3: launch_k(k_out_conv<3>, nblk, 256, shm, st, ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
+                default: launch_k(k_out_conv<4>, nblk, 256, shm, st, ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
             }
             return (int)cudaGetLastError(); });
         if (train) {
@@ -430,16 +430,16 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 bwd_flops += 2.0 * fl;
                 push(bwd_ops, "out_conv.2.bwd", 2.0 * fl, [=](cudaStream_t st) {
                     const float* de = self->deps_src;
-                    k_chansum_nchw<<<dim3(64, Cout), 256, 0, st>>>(de, gb, Bn, Cout, Hn * Wn);
+                    launch_k(k_chansum_nchw, dim3(64, Cout), 256, 0, st, de, gb, Bn, Cout, Hn * Wn);
                     switch (Cout) {
-                        case 1: k_in_conv<1><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
-                                k_corr3x3<1><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        case 2: k_in_conv<2><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
-                                k_corr3x3<2><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        case 3: k_in_conv<3><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
-                                k_corr3x3<3><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        default: k_in_conv<4><<<n2, 128, shm2, st>>>(de, wt, nullptr, dap, Bn, Hn, Wn, ch);
-                                k_corr3x3<4><<<nb, ch, 0, st>>>(ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        case 1: launch_k(k_in_conv<1>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                launch_k(k_corr3x3<1>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        case 2: launch_k(k_in_conv<2>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                launch_k(k_corr3x3<2>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        case 3: launch_k(k_in_conv<3>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                launch_k(k_corr3x3<3>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
+                        default: launch_k(k_in_conv<4>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                                launch_k(k_corr3x3<4>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
                     }
                     return (int)cudaGetLastError(); }, 3);
                 gn_bwd("out_conv.0", g, d_a, nullptr);
@@ -458,13 +458,13 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         if (!unpack_table_host.empty()) {
             const PackEntry* tab = at<PackEntry>(unpack_table_off); const int n = (int)unpack_table_host.size();
             // on the side stream too: ordered after every wgrad GEMM there; the list's final join publishes the flat gradients
-            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { k_pack_table<<<dim3(32, n), 256, 0, st>>>(tab); return (int)cudaGetLastError(); }, 1, true);
+            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(32, n), 256, 0, st, tab); return (int)cudaGetLastError(); }, 1, true);
         }
     }
     pack_table_off = alloc(sizeof(PackEntry) * (pack_table_host.size() + 1));
     if (!pack_table_host.empty()) {
         const PackEntry* tab = at<PackEntry>(pack_table_off); const int n = (int)pack_table_host.size();
-        push(pack_ops, "pack_all", 0, [=](cudaStream_t st) { k_pack_table<<<dim3(32, n), 256, 0, st>>>(tab); return (int)cudaGetLastError(); });
+        push(pack_ops, "pack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(32, n), 256, 0, st, tab); return (int)cudaGetLastError(); });
     }
     if (plan_error) return plan_error;
     return 0;
@@ -487,6 +487,9 @@ inline int UnetEngine::build() {
     if (!side_stream) {
         if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) ||
             cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) return fail(-2, "side stream creation failed");
+        int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&hp_stream, cudaStreamNonBlocking, greatest) || cudaEventCreateWithFlags(&ev_hp_fork, cudaEventDisableTiming) ||
+            cudaEventCreateWithFlags(&ev_hp_join, cudaEventDisableTiming)) return fail(-2, "priority stream creation failed");
     }
     planned = true;
     return 0;
