@@ -51,6 +51,23 @@ class ClockSampler:
         self.th = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        try:                                   # NVML in-process: ~10 ms cadence, enough samples inside a 0.2 s timed region
+            import pynvml as nv
+            nv.nvmlInit()
+            hd = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(hd, nv.NVML_CLOCK_SM)
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(hd)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
+                self.rows.append([str(sm), str(mx), "", *("Active" if r & b else "Not Active" for _, b in bits)])
+                time.sleep(0.01)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -126,7 +143,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": CPU_THREADS, "kind": "port",
                              "sample": f"{args.steps} steps of bs={bs} (of the bs=128 workload), fp32, torch CPU, {torch.get_num_threads()} threads"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    args.emit(line)
 
 
 def cpu_baseline_sample(budget_s=20.0):
@@ -206,6 +223,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: anything a library writes to fd 1 meanwhile (e.g. the NCCL version banner) goes to stderr
+    sys.stdout.flush()
+    _real_stdout = os.dup(1); os.dup2(2, 1)
+    def emit(obj):
+        sys.stdout.flush(); os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+    args.emit = emit
     if args.impl == "reference":
         return run_reference(args)
 
@@ -327,7 +351,7 @@ def main():
             line["sampler"] = bench_sampler(D, model, dev)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line), flush=True)
+        args.emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
