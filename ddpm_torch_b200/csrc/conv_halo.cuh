@@ -37,9 +37,15 @@ struct HaloCfg {
     static constexpr int P = (SUB == 1) ? 16 : 24;             // halo row pitch in pixels (multiple of 8)
     static constexpr int A_ROWS = 18 * P;
     static constexpr int A_BYTES = A_ROWS * 128;               // 36 KB / 54 KB
-    static constexpr int B_BYTES = BLOCK_N * 128;
+    // Weight stage = TPS taps of one 64-channel chunk.  Measured (DDPM_HALO_DBG experiments, profiles/README.md): every
+    // producer -> issuer -> commit round trip costs ~300 cycles of the single issuing thread, whatever the stage holds; with
+    // one tap per stage (256 MMA cycles at N=128) the tensor pipe starves at 65 %.  Three taps (one ky row) per stage = 768
+    // MMA cycles per round trip.
+    static constexpr int TPS = (BLOCK_N == 256 || SUB != 1) ? 1 : 3;
+    static constexpr int TAP_BYTES = BLOCK_N * 128;
+    static constexpr int B_BYTES = TAP_BYTES * TPS;
     static constexpr int NA = 2;
-    static constexpr int NB_ST = (BLOCK_N == 256) ? ((SUB == 1) ? 4 : 3) : ((SUB == 1) ? 8 : 6);
+    static constexpr int NB_ST = (TPS == 3) ? ((BLOCK_N == 128) ? 3 : 6) : ((BLOCK_N == 256) ? ((SUB == 1) ? 4 : 3) : ((SUB == 1) ? 8 : 6));
     static constexpr int NACC = (2 * SUB * BLOCK_N <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * SUB * BLOCK_N <= 128) ? 128 : ((NACC * SUB * BLOCK_N <= 256) ? 256 : 512);
     static constexpr int TOTAL = NA * A_BYTES + NB_ST * B_BYTES + 1024 + 512;
@@ -115,11 +121,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             else              tma_load_4d(smA + sa * CF::A_BYTES, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
                             ++ia;
                         }
-                        for (int tp = 0; tp < sg.taps; ++tp) {
+                        for (int tp = 0; tp < sg.taps; tp += CF::TPS) {
+                            const int nt = (sg.taps - tp < CF::TPS) ? sg.taps - tp : CF::TPS;
                             const int sb = ib % CF::NB_ST; const uint32_t ph = (ib / CF::NB_ST) & 1;
                             if (!mbar_wait(&empty_b[sb], ph ^ 1, 6)) { ok = false; break; }
-                            mbar_expect_tx(&full_b[sb], CF::B_BYTES);
-                            tma_load_3d(smB + sb * CF::B_BYTES, &tmB, &full_b[sb], kbase + tp * Cseg + kc * 64, n_tile * BLOCK_N, 0);
+                            mbar_expect_tx(&full_b[sb], (uint32_t)(nt * CF::TAP_BYTES));
+                            for (int j = 0; j < nt; ++j)
+                                tma_load_3d(smB + sb * CF::B_BYTES + j * CF::TAP_BYTES, &tmB, &full_b[sb], kbase + (tp + j) * Cseg + kc * 64, n_tile * BLOCK_N, 0);
                             ++ib;
                         }
                     }
@@ -146,26 +154,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const int sa = ia % CF::NA; const uint32_t pha = (ia / CF::NA) & 1;
                         if (!mbar_wait(&full_a[sa], pha, 7)) { ok = false; break; }
                         const uint32_t a_base = smem_u32(smA + sa * CF::A_BYTES);
-                        for (int tp = 0; tp < sg.taps; ++tp) {
+                        for (int tp0 = 0; tp0 < sg.taps; tp0 += CF::TPS) {
+                            const int nt = (sg.taps - tp0 < CF::TPS) ? sg.taps - tp0 : CF::TPS;
                             const int sb = ib % CF::NB_ST; const uint32_t phb = (ib / CF::NB_ST) & 1;
                             if (!mbar_wait(&full_b[sb], phb, 2)) { ok = false; break; }
                             tc_fence_after();
-                            const uint32_t b_addr = smem_u32(smB + sb * CF::B_BYTES);
                             // haloed patch: row (y+ky)*P + (x+kx+8s) ; plain 1x1 patch: row y*(8*SUB) + x + 8s
                             const int pitch = (sg.taps == 9) ? P : 8 * SUB;
-                            const int row0 = (sg.taps == 9) ? (tp / 3) * P + (tp % 3) : 0;
 #pragma unroll
-                            for (int sub = 0; sub < SUB; ++sub) {
-                                const uint32_t a_row = a_base + (uint32_t)(row0 + 8 * sub) * 128u;
-                                const uint32_t bo = p.desc_base_offset_mode ? ((a_row >> 7) & 7u) : 0u;
+                            for (int j = 0; j < CF::TPS; ++j) {
+                                if (j >= nt) break;
+                                const int tp = tp0 + j;
+                                const uint32_t b_addr = smem_u32(smB + sb * CF::B_BYTES + j * CF::TAP_BYTES);
+                                const int row0 = (sg.taps == 9) ? (tp / 3) * P + (tp % 3) : 0;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t da = umma_smem_desc_bo(a_row + k * 32, 16, (uint32_t)pitch * 128u, bo);
-                                    const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-                                    umma_bf16(d_tmem + (uint32_t)(sub * BLOCK_N), da, db, idesc, (first && k == 0) ? 0u : 1u);
+                                for (int sub = 0; sub < SUB; ++sub) {
+                                    const uint32_t a_row = a_base + (uint32_t)(row0 + 8 * sub) * 128u;
+                                    const uint32_t bo = p.desc_base_offset_mode ? ((a_row >> 7) & 7u) : 0u;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint64_t da = umma_smem_desc_bo(a_row + k * 32, 16, (uint32_t)pitch * 128u, bo);
+                                        const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                                        umma_bf16(d_tmem + (uint32_t)(sub * BLOCK_N), da, db, idesc, (first && k == 0) ? 0u : 1u);
+                                    }
                                 }
+                                first = false;
                             }
-                            first = false;
                             umma_commit(&empty_b[sb]);
                             ++ib;
                         }
@@ -215,26 +229,26 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
                     }
                     if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + col);
+                        const __nv_bfloat16* rp = p.residual + pix * p.ldr + col;
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const uint4 u = __ldg(rp + j4);
-                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t u[8];
+                            ld_global_nc_256(rp + j * 16, u);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 t2 = __bfloat1622float2(h[e]);
-                                f[j4 * 8 + e * 2] += t2.x; f[j4 * 8 + e * 2 + 1] += t2.y;
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+                                f[j * 16 + e * 2] += t2.x; f[j * 16 + e * 2 + 1] += t2.y;
                             }
                         }
                     }
-                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col);
+                    // Cout % 64 == 0 and 32-column chunks: every lane's 64 output bytes are 32-byte aligned -> two STG.256
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                    for (int j = 0; j < 2; ++j) {
+                        uint32_t u[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-                        o[j] = u;
+                        for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[j * 16 + e * 2], f[j * 16 + e * 2 + 1]);
+                        st_global_256(o + j * 16, u);
                     }
                 }
             }

@@ -10,6 +10,8 @@
 
 namespace ddpm {
 
+__device__ __forceinline__ const uint32_t* v_as_u32(const float* f) { return reinterpret_cast<const uint32_t*>(f); }
+
 enum GemmMode { GEMM_KK = 0, GEMM_MNMN = 1, GEMM_KMN = 2 };
 enum EpiFlags { EPI_OUT_F32 = 1, EPI_ATOMIC = 2 };
 
@@ -341,18 +343,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     for (int j = 0; j < 32; j += 4)
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
                 } else if (p.flags & EPI_OUT_F32) {
-                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col);
+                    float* o = reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col;
+                    if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) st_global_256(o + j * 8, v_as_u32(f + j * 8));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    }
                 } else {
-                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + orow * p.ldo + col);
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + zoff + orow * p.ldo + col;
+                    uint32_t u[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                    for (int e = 0; e < 16; ++e) u[e] = pack_bf16x2(f[e * 2], f[e * 2 + 1]);
+                    if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) { st_global_256(o, u); st_global_256(o + 16, u + 8); }   // two full sectors per store
+                    else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-                        o[j] = u;
+                        for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(o)[j] = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
                     }
                 }
             }
