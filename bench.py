@@ -333,6 +333,42 @@ def main():
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_val = world * B / (ems.item() * 1e-3)
 
+    # ---- SURVEY 8d config 2 "with and without optimiser/EMA": the same device-resident step followed by the fused
+    # clip_grad_norm + Adam + LR warm-up + EMA update (ddpm_opt_step, 2 launches over the flat fp32 buffers)
+    from ddpm_torch_b200.optim import EMA, FusedAdam, hbm_bytes_per_step
+    opt = FusedAdam(model, lr=2e-4, betas=(0.9, 0.999), warmup=5000, grad_norm=1.0, ema=EMA(model, 0.9999))
+
+    def step_opt(i):
+        step(i)
+        opt.step()
+
+    for i in range(args.warmup):
+        step_opt(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_opt(i)
+    e1.record()
+    barrier()
+    oms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(oms, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(20):
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    opt_ms = e0.elapsed_time(e1) / 20
+    n_par = model.flat_params.numel()
+    opt_gbs = hbm_bytes_per_step(n_par, ema=True) / (opt_ms * 1e-3) / 1e9
+    with_opt = {"value": world * B / (oms.item() * 1e-3), "unit": "images/s", "ms_per_step": oms.item(),
+                "what": "step + fused clip_grad_norm/Adam/LR-warm-up/EMA (utils/train.py:159-165) over the flat buffers",
+                "opt_ms_isolated": opt_ms, "launches": 2,
+                "roofline": {"bound": "hbm", "achieved": opt_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": opt_gbs / pk["hbm"],
+                             "algorithmic_bytes": hbm_bytes_per_step(n_par, ema=True), "traffic": None}}
+
     line = {"metric": "unet_train_step_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -342,6 +378,7 @@ def main():
                        "l2": "4 rotating input batches; activations (2.2 GB fwd) exceed the 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 32 * 32 * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ems.item(), "api": "GaussianDiffusion.train_losses(model, x, t, noise).mean().backward()"},
+            "with_optimizer": with_opt,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks,
             "step_tflops": world * B * TRAIN_GFLOP_PER_IMG / ms, "step_frac_of_sustained_peak": B * TRAIN_GFLOP_PER_IMG / ms / pk["sustained"]}
 

@@ -7,5 +7,7 @@ from .unet import UNet
 from .diffusion import GaussianDiffusion, get_beta_schedule
 from .ddim import DDIM, get_selection_schedule
 from . import parallel
+from . import optim
+from .optim import EMA, FusedAdam
 
-__all__ = ["UNet", "GaussianDiffusion", "get_beta_schedule", "DDIM", "get_selection_schedule"]
+__all__ = ["UNet", "GaussianDiffusion", "get_beta_schedule", "DDIM", "get_selection_schedule", "EMA", "FusedAdam"]

@@ -50,6 +50,11 @@ class UnetCfg(C.Structure):
                 ("temb_dim", C.c_int), ("drop_rate", C.c_float)]
 
 
+class OptCfg(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("max_grad_norm", C.c_double), ("ema_decay", C.c_double), ("step", C.c_int), ("ema_num_updates", C.c_int)]
+
+
 _lib = None
 
 
@@ -89,6 +94,7 @@ def lib():
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
             "ddpm_unet_launches_per_forward": ([vp], i32),
             "ddpm_unet_launch_counts": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
+            "ddpm_opt_step": ([vp, vp, vp, vp, vp, i64, C.POINTER(OptCfg), vp, vp, vp], i32),
         }
         for name, (args, res) in sig.items():
             fn = getattr(L, name)
@@ -103,7 +109,7 @@ EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "d
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",
            "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_unet_plan_stats",
-           "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts"]
+           "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts", "ddpm_opt_step"]
 
 
 def check(rc, what=""):

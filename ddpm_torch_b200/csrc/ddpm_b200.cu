@@ -1,7 +1,10 @@
 // libddpm_b200.so — single translation unit (device-side error flag and kernels share one module).
 #include <cstdarg>
 #include <new>
+#include <cmath>
+#include <initializer_list>
 #include "unet_engine_impl.cuh"
+#include "optim.cuh"
 
 using namespace ddpm;
 
@@ -188,6 +191,37 @@ int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, voi
     if (rc) return rc;
     const long long total = (long long)e.B * e.cfg.out_channels * e.H * e.W;
     launch_k(k_psample_tail, grid_for(total), 256, 0, st, eps, x, z, cc, (unsigned long long)seed, total);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int ddpm_opt_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, long long n,
+                  const ddpm_opt_cfg* c, void* state, float* norm_out, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !c || !state || !norm_out) return fail(-40, "ddpm_opt_step: null buffer");
+    if (n <= 0 || (n & 3)) return fail(-40, "ddpm_opt_step: n must be a positive multiple of 4");
+    if (c->step < 1) return fail(-40, "ddpm_opt_step: step is 1-based");
+    if (c->ema_decay >= 0 && !ema_shadow) return fail(-40, "ddpm_opt_step: EMA enabled but ema_shadow is NULL");
+    for (const void* q : {(const void*)params, (const void*)grads, (const void*)exp_avg, (const void*)exp_avg_sq, (const void*)ema_shadow})
+        if (reinterpret_cast<uintptr_t>(q) & 15) return fail(-40, "ddpm_opt_step: buffers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    OptScalars o;
+    const double bc1 = 1.0 - pow(c->beta1, (double)c->step), bc2 = 1.0 - pow(c->beta2, (double)c->step);
+    o.one_minus_b1 = (float)(1.0 - c->beta1); o.b2 = (float)c->beta2; o.one_minus_b2 = (float)(1.0 - c->beta2);
+    o.step_size = (float)(c->lr / bc1); o.bc2_sqrt = (float)sqrt(bc2); o.eps = (float)c->eps;
+    o.max_norm = (float)c->max_grad_norm;
+    if (c->ema_decay >= 0) {
+        const double nu = (double)c->ema_num_updates;
+        double d = (1.0 + nu) / (10.0 + nu); if (d > c->ema_decay) d = c->ema_decay;
+        o.ema_w = (float)(1.0 - d);
+    } else o.ema_w = -1.f;
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const long long n4 = n >> 2;
+    long long want = (n4 + 255) / 256; const int cap = num_sms * 8; const int grid = (int)(want < cap ? want : cap);
+    double* acc = reinterpret_cast<double*>(state); unsigned int* ticket = reinterpret_cast<unsigned int*>(acc + 1);
+    launch_k(k_grad_sumsq, grid, 256, 0, st, reinterpret_cast<const float4*>(grads), n4, acc, ticket, norm_out, o.max_norm);
+    DDPM_CUDA_OK(cudaGetLastError());
+    launch_k(k_adam_ema, grid, 256, 0, st, reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads), reinterpret_cast<float4*>(exp_avg),
+             reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<float4*>(ema_shadow), n4, o, (const float*)norm_out);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -128,6 +128,22 @@ int ddpm_unet_launches_per_forward(const ddpm_unet* h);
 /* kernel launches issued by one forward / backward / repack of the compiled plan (memsets not counted) */
 int ddpm_unet_launch_counts(const ddpm_unet* h, int* fwd, int* bwd, int* pack);
 
+/* ---- fused optimizer step over the flat fp32 buffers.
+ * Replaces, per training step, nn.utils.clip_grad_norm_(params, max_norm) + Adam.step() + LambdaLR warm-up + EMA.update()
+ * (utils/train.py:159-165, :300-305; train.py:128-132) = ~13 tiny kernels x 304 tensors, by two launches and no host sync.
+ *   step          : 1-based Adam step t (bias corrections 1 - beta^t), lr is the already-scheduled learning rate of this step
+ *   max_grad_norm : <= 0 disables clipping;  ema_decay : < 0 disables the EMA update (ema_shadow may then be NULL);
+ *   ema_num_updates: 0-based n of utils/train.py:301-302, decay_t = min(ema_decay, (1 + n) / (10 + n))
+ *   state         : device scratch of >= 64 bytes, zero-initialised ONCE by the caller (fp64 accumulator + ticket)
+ *   norm_out      : device float[2] <- {total_norm before clipping, clip coefficient applied}
+ * n (elements) must be a multiple of 4 and all buffers 16-byte aligned (the flat layout guarantees both). */
+typedef struct ddpm_opt_cfg {
+  double lr, beta1, beta2, eps, max_grad_norm, ema_decay;
+  int step, ema_num_updates;
+} ddpm_opt_cfg;
+int ddpm_opt_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, long long n,
+                  const ddpm_opt_cfg* cfg, void* state, float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

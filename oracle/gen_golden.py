@@ -184,7 +184,46 @@ def main():
         torch.save(dict(cfg=dict(R.CELEBAHQ_CFG), B=1, H=256, W=256, seed=99, x=x0, t=t,
                         eps=eps.to(torch.float16)), os.path.join(out_dir, "unet_celebahq_bs1.pt"))
         print(f"unet_celebahq_bs1.pt done |eps|max={eps.abs().max():.4f}")
+    gen_optim(out_dir)
+
+
+def gen_optim(out_dir):
+    """clip_grad_norm_ + torch.optim.Adam + LambdaLR warm-up + the reference EMA class (utils/train.py:159-165,280-316)
+    on a small parameter set for 8 steps; grads are deterministic.  Stored: initial params, per-step grads, and
+    params / shadow / total-norm after every step."""
+    ddpm_torch, _ = import_reference()
+    from ddpm_torch.utils.train import EMA
+    from torch.optim import Adam, lr_scheduler
+    g = torch.Generator().manual_seed(4242)
+    shapes = [(64,), (32, 16), (8, 3, 3, 3), (128,)]
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(s, generator=g) * 0.1) for s in shapes])
+    m = M()
+    hyper = dict(lr=2e-4, beta1=0.9, beta2=0.999, warmup=4, grad_norm=1.0, ema_decay=0.9999)
+    opt = Adam(m.parameters(), lr=hyper["lr"], betas=(hyper["beta1"], hyper["beta2"]))
+    sch = lr_scheduler.LambdaLR(opt, lr_lambda=lambda t: min((t + 1) / hyper["warmup"], 1.0))
+    ema = EMA(m, decay=hyper["ema_decay"])
+    fx = dict(hyper=hyper, shapes=shapes, p0=[p.detach().clone() for p in m.ps], grads=[], params=[], shadow=[], norms=[], lrs=[])
+    for k in range(8):
+        scale = [0.02, 5.0, 0.3, 1.0, 40.0, 0.001, 2.0, 0.7][k]           # both clipped and unclipped steps
+        gs = [torch.randn(s, generator=g) * scale for s in shapes]
+        for p, gr in zip(m.ps, gs):
+            p.grad = gr.clone()
+        fx["lrs"].append(opt.param_groups[0]["lr"])
+        tn = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=hyper["grad_norm"])
+        opt.step(); opt.zero_grad(set_to_none=True); sch.step(); ema.update()
+        fx["grads"].append(gs); fx["norms"].append(float(tn))
+        fx["params"].append([p.detach().clone() for p in m.ps])
+        fx["shadow"].append([ema.shadow[k_].clone() for k_, _ in m.named_parameters()])
+    fx["ema_num_updates"] = ema.num_updates
+    torch.save(fx, os.path.join(out_dir, "optim.pt"))
+    print("optim.pt written; norms", [round(n, 4) for n in fx["norms"]], "lrs", fx["lrs"])
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "optim":
+        gen_optim(os.path.join(ROOT, "tests", "golden")); sys.exit(0)
     main()

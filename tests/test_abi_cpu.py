@@ -33,14 +33,14 @@ def test_library_exports_every_declared_symbol(L):
 
 def test_struct_layouts_match_header():
     from ddpm_torch_b200 import _lib
-    src = '#include "include/ddpm_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu", sizeof(ddpm_gemm_desc), sizeof(ddpm_unet_cfg));}'
+    src = '#include "include/ddpm_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu", sizeof(ddpm_gemm_desc), sizeof(ddpm_unet_cfg), sizeof(ddpm_opt_cfg));}'
     import subprocess, tempfile
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c"); open(c, "w").write(src)
         exe = os.path.join(td, "s")
         subprocess.check_call(["gcc", "-I", ROOT, c, "-o", exe], cwd=ROOT)
-        a, b = map(int, subprocess.check_output([exe]).split())
-    assert a == C.sizeof(_lib.GemmDesc) and b == C.sizeof(_lib.UnetCfg)
+        a, b, c_ = map(int, subprocess.check_output([exe]).split())
+    assert a == C.sizeof(_lib.GemmDesc) and b == C.sizeof(_lib.UnetCfg) and c_ == C.sizeof(_lib.OptCfg)
 
 
 def test_no_gpu_means_error_not_fallback(L):
@@ -124,3 +124,23 @@ def test_python_module_mirrors_reference_surface():
     assert list(m.state_dict().keys()) == list(sd.keys())
     m.load_state_dict(sd)
     assert all(torch.equal(m.state_dict()[k], v) for k, v in sd.items()) and m._views_ok()
+
+
+def test_opt_step_validates_arguments_before_touching_the_device(L):
+    """ddpm_opt_step (clip + Adam + EMA, utils/train.py:159-165): argument errors are reported through the C ABI."""
+    from ddpm_torch_b200 import _lib
+    cfg = _lib.OptCfg(); cfg.lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.max_grad_norm, cfg.ema_decay, cfg.step = 2e-4, .9, .999, 1e-8, 1., .9999, 1
+    assert L.ddpm_opt_step(None, None, None, None, None, 16, C.byref(cfg), None, None, None) != 0
+    assert b"null" in L.ddpm_last_error()
+    buf = (C.c_float * 64)()
+    a = C.addressof(buf)
+    a16 = (a + 15) // 16 * 16
+    assert L.ddpm_opt_step(a16, a16, a16, a16, a16, 6, C.byref(cfg), a16, a16, None) != 0          # n % 4 != 0
+    assert b"multiple of 4" in L.ddpm_last_error()
+    cfg.step = 0
+    assert L.ddpm_opt_step(a16, a16, a16, a16, a16, 8, C.byref(cfg), a16, a16, None) != 0
+    assert b"1-based" in L.ddpm_last_error()
+    cfg.step = 1
+    assert L.ddpm_opt_step(a16, a16, a16, a16, None, 8, C.byref(cfg), a16, a16, None) != 0         # EMA on, no shadow
+    assert L.ddpm_opt_step(a16 + 4, a16, a16, a16, a16, 8, C.byref(cfg), a16, a16, None) != 0      # misaligned
+    assert b"aligned" in L.ddpm_last_error()
