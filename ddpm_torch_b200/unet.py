@@ -50,8 +50,10 @@ class UNet(nn.Module):
             cfg.attn[i] = int(bool(apply_attn[i]))
         cfg.temb_dim, cfg.drop_rate = self.time_embedding_dim, float(drop_rate)
         L = _lib.lib()
+        self._cfg = cfg
         self._h = C.c_void_p()
         _lib.check(L.ddpm_unet_create(C.byref(cfg), C.byref(self._h)), "unet_create")
+        self._aux = {}                      # auxiliary inference plans (extra handles over the SAME flat parameters)
 
         # parameter inventory from the engine (reference registration order)
         self._meta = []
@@ -85,6 +87,7 @@ class UNet(nn.Module):
         self._ws = None
         self._plan_key = None
         self._packed_version = None
+        self._packed_epoch = 0
         self._drop_calls = 0
 
     def __del__(self):
@@ -92,6 +95,9 @@ class UNet(nn.Module):
             if getattr(self, "_h", None) is not None and self._h.value:
                 _lib.lib().ddpm_unet_destroy(self._h)
                 self._h = C.c_void_p()
+            for a in getattr(self, "_aux", {}).values():
+                _lib.lib().ddpm_unet_destroy(a["h"])
+            self._aux = {}
         except Exception:
             pass
 
@@ -158,6 +164,37 @@ class UNet(nn.Module):
         self.repack_if_needed(force=training)
         return self._h
 
+    def aux_plan(self, idx, B, H, W):
+        """Extra inference plan #idx over the same flat parameters with its own workspace (the sampler runs two half
+        batches on two streams so that one half's HBM-bound GroupNorm kernels overlap the other's tensor-core kernels).
+        Returns the handle; its packed weights are refreshed whenever the parameters changed."""
+        if not self._flat.is_cuda:
+            raise RuntimeError("ddpm_torch_b200.UNet runs on sm_100a CUDA devices only (no CPU / PyTorch fallback)")
+        if not self._views_ok():
+            self._reflatten()
+        L = _lib.lib()
+        a = self._aux.get(idx)
+        key = (B, H, W, self._flat.data_ptr())
+        if a is None or a["key"] != key:
+            if a is None:
+                h = C.c_void_p()
+                _lib.check(L.ddpm_unet_create(C.byref(self._cfg), C.byref(h)), "unet_create")
+                a = {"h": h, "ws": None, "key": None, "ver": None}
+                self._aux[idx] = a
+            need = L.ddpm_unet_workspace_bytes(a["h"], B, H, W, 0)
+            if need < 0:
+                _lib.check(int(need), "workspace_bytes")
+            if a["ws"] is None or a["ws"].numel() < need or a["ws"].device != self._flat.device:
+                a["ws"] = None
+                a["ws"] = torch.empty(int(need), dtype=torch.uint8, device=self._flat.device)
+            with torch.cuda.device(self._flat.device):
+                _lib.check(L.ddpm_unet_plan(a["h"], B, H, W, 0, self._flat.data_ptr(), None, a["ws"].data_ptr(), a["ws"].numel()), "unet_plan")
+            a["key"], a["ver"] = key, None
+        if a["ver"] != (self._flat._version, self._packed_epoch):
+            _lib.check(L.ddpm_unet_repack(a["h"], _lib.stream_ptr()), "unet_repack")
+            a["ver"] = (self._flat._version, self._packed_epoch)
+        return a["h"]
+
     def repack_if_needed(self, force=False):
         v = self._flat._version
         if force or v != self._packed_version:
@@ -167,6 +204,7 @@ class UNet(nn.Module):
     def repack(self):
         """Call after out-of-band weight edits (e.g. ``p.data.copy_`` as the reference EMA does, utils/train.py:307-316)."""
         self._packed_version = None
+        self._packed_epoch += 1
 
     def next_dropout_seed(self):
         self._drop_calls += 1

@@ -260,3 +260,30 @@ def test_dropout_gradient_directional_derivative():
     print(f"\n[dropout grad] L0 {l0.item():.5f} predicted decrease {pred:.5f} measured {got:.5f}")
     assert 0.7 * pred < got < 1.3 * pred
     check_device_flag()
+
+
+@pytest.mark.gpu
+def test_sampler_split_batch_two_streams_matches_unsplit(golden):
+    """The split sampler (two half batches on two forked streams inside one captured graph) draws the same torch noise
+    per image and must reproduce the unsplit loop (up to the engine's run-to-run atomics noise)."""
+    import ddpm_torch_b200 as D
+    fx = golden("unet_tiny.pt")
+    m, sd = build(fx["cfg"], fx["seed"])
+    betas = D.get_beta_schedule("linear", 1e-4, 0.02, 1000)
+    sub = D.get_selection_schedule("linear", 6, 1000)
+    dd = D.DDIM.from_ddpm(D.GaussianDiffusion(betas, "eps", "fixed-small", "mse"), eta=1.0, subsequence=sub)
+    H = fx["x_t"].shape[-1]
+    noise = torch.randn(64, 3, H, H, generator=torch.Generator().manual_seed(5)).to(DEV)
+    outs = {}
+    for split in (1, 2):
+        for use_graph in (True, False):
+            outs[(split, use_graph)] = dd.p_sample(m, shape=tuple(noise.shape), device=torch.device(DEV), noise=noise, seed=77,
+                                                   use_graph=use_graph, split=split)
+    ref = outs[(1, True)]
+    for k, v in outs.items():
+        d = (v - ref).abs()
+        print(f"\n[split sampler] split={k[0]} graph={k[1]}: mean |d| {d.mean().item():.3e}, frac(|d|>0.1) {(d > 0.1).float().mean().item():.4f}")
+        assert d.mean().item() < 1e-2 and (d > 0.1).float().mean().item() < 0.03
+    # halves must not be copies of each other (distinct images, distinct noise)
+    assert (outs[(2, True)][:32] - outs[(2, True)][32:]).abs().mean().item() > 1e-2
+    check_device_flag()
