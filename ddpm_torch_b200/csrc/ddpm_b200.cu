@@ -187,7 +187,10 @@ int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, voi
     launch_k(k_sampler_prep, 1, 256, 0, st, e.at<int>(e.counter_off), h->d_tmodel, h->d_coef, tbuf, cc, e.B);
     DDPM_CUDA_OK(cudaGetLastError());
     e.x_in = x; e.t_in = tbuf; e.eps_dst = eps; e.drop_seed = 0;
+    static const bool no_uni = getenv("DDPM_NO_UNIFORM_T") != nullptr;
+    e.uniform_t = !no_uni;                                // the whole batch is at the same timestep (diffusion.py:166)
     const int rc = e.run_list(e.fwd_ops, st);
+    e.uniform_t = false;
     if (rc) return rc;
     const long long total = (long long)e.B * e.cfg.out_channels * e.H * e.W;
     launch_k(k_psample_tail, grid_for(total), 256, 0, st, eps, x, z, cc, (unsigned long long)seed, total);

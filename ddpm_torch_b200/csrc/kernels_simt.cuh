@@ -1313,6 +1313,12 @@ __global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict_
         x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sg), zz));
     }
 }
+// rows 1..B-1 of a [B][row4] float4 matrix <- row 0
+__global__ void k_bcast_rows(float4* __restrict__ m, long long row4, long long tot4) {
+    pdl_entry();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tot4) m[row4 + i] = m[i % row4];
+}
 // one block: fetch step i = *counter, broadcast t_model[i] to t_buf[B], copy the coefficient row, then advance the counter
 __global__ void k_sampler_prep(int* __restrict__ counter, const long long* __restrict__ t_model, const float* __restrict__ coef_table /*[S][6]*/,
                                long long* __restrict__ t_buf, float* __restrict__ coef_cur /*[7]*/, int B) {

@@ -16,7 +16,8 @@ struct ParamInfo { std::string name; int nd; int dims[4]; long long numel; long 
 struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
-struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; };
+enum { OP_TEMB = 1 };
+struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; int tag = 0; };
 struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; unsigned char* mask; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
@@ -38,6 +39,9 @@ struct UnetEngine {
     size_t zero_fwd_off = 0, zero_fwd_bytes = 0, zero_bwd_off = 0, zero_bwd_bytes = 0;   // per-pass zeroed regions
     size_t once_zero_off = 0, once_zero_bytes = 0;                                       // zeroed at plan time only
     std::vector<SgemmParams> tp_table_host; size_t tp_table_off = 0; int tp_max_c = 0;
+    std::vector<SgemmParams> tp_uni_table_host; size_t tp_uni_table_off = 0;
+    std::vector<Op> temb_uni_ops;          // one-row timestep path + broadcast (sampler: the whole batch shares t)
+    bool uniform_t = false;                // set by ddpm_sampler_step around its forward
     std::vector<SgemmParams> tpw_table_host, tpd_table_host; size_t tpw_table_off = 0, tpd_table_off = 0;
     uint32_t layer_counter = 0;
     double fwd_flops = 0, bwd_flops = 0;
@@ -493,9 +497,15 @@ struct UnetEngine {
         std::vector<cudaEvent_t> tev;
         if (timing_path && !dbg) { tev.resize(L.size() + 1); for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], st); }
         size_t oi = 0; int main_since_fork = 0;
+        const bool skip_temb = uniform_t && !temb_uni_ops.empty() && &L == &fwd_ops;
         for (auto& o : L) {
             int rc;
             ++oi;
+            if (skip_temb && o.tag == OP_TEMB) {
+                if (o.name == "temb.sin") for (auto& u : temb_uni_ops) { rc = u.run(st); if (rc) return fail(-20, "op '%s' failed: %s", u.name.c_str(), cudaGetErrorString((cudaError_t)rc)); }
+                if (!tev.empty()) cudaEventRecord(tev[oi], st);
+                continue;
+            }
             if (o.side && side_stream && !dbg && !no_side) {
                 rc = 0;
                 if (main_since_fork || !forked) {     // consecutive side ops share one fork edge

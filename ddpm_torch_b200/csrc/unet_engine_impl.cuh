@@ -238,7 +238,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
 inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     B = B_; H = H_; W = W_; train = train_; dry = dry_;
     cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); grads.clear(); once_list.clear();
-    tp_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
+    tp_table_host.clear(); tp_uni_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
     layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0;
     const size_t zf_total = zf_cursor, zb_total = zb_cursor;   // sizes learned by the preceding dry pass
     zf_cursor = zb_cursor = 0;
@@ -272,6 +272,8 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     float* dTP = at<float>(zero_bwd((size_t)B * tp_ld * 4));
     float* d_st = at<float>(zero_bwd((size_t)B * E * 4));
     tp_table_off = alloc(sizeof(SgemmParams) * nblocks); tpw_table_off = alloc(sizeof(SgemmParams) * nblocks); tpd_table_off = alloc(sizeof(SgemmParams) * nblocks);
+    tp_uni_table_off = alloc(sizeof(SgemmParams) * nblocks);
+    const size_t temb_first = fwd_ops.size();
     {
         const int Bn = B;
         push(fwd_ops, "temb.sin", 0, [=](cudaStream_t st) { launch_k(k_timestep_embedding, (Bn * (ch / 2) + 127) / 128, 128, 0, st, self->t_in, emb, Bn, ch); return (int)cudaGetLastError(); });
@@ -287,6 +289,21 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         const dim3 g1((maxc + 63) / 64, (B + 63) / 64, nblocks * KS);
         push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { launch_k(k_sgemm_table, g1, 256, 0, st, tab, (int)KS); return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * E * ch + 2.0 * B * E * E;
+        // Sampler steps feed ONE timestep to the whole batch (diffusion.py:166 `t.fill_(ti)`): the embedding MLP and the
+        // per-block projections are then computed for a single row and broadcast (ddpm_sampler_step sets uniform_t).
+        for (size_t i = temb_first; i < fwd_ops.size(); ++i) fwd_ops[i].tag = OP_TEMB;
+        temb_uni_ops.clear();
+        push(temb_uni_ops, "temb.sin[1]", 0, [=](cudaStream_t st) { launch_k(k_timestep_embedding, (ch / 2 + 127) / 128, 128, 0, st, self->t_in, emb, 1, ch); return (int)cudaGetLastError(); });
+        SgemmParams a1 = a; a1.M = 1; SgemmParams b1 = b; b1.M = 1;
+        const dim3 u0((E + 63) / 64, 1, 1), u0s((E + 63) / 64, 1, KS), u1((maxc + 63) / 64, 1, nblocks * KS);
+        push(temb_uni_ops, "temb.fc0[1]", 0, [a1, u0](cudaStream_t st) { launch_k(k_sgemm<float, float, float>, u0, 256, 0, st, a1); return (int)cudaGetLastError(); });
+        push(temb_uni_ops, "temb.fc1[1]", 0, [b1, u0s](cudaStream_t st) { launch_k(k_sgemm<float, float, float>, u0s, 256, 0, st, b1); return (int)cudaGetLastError(); });
+        const SgemmParams* tabu = at<SgemmParams>(tp_uni_table_off);
+        push(temb_uni_ops, "temb.proj[1]", 0, [tabu, u1](cudaStream_t st) { launch_k(k_sgemm_table, u1, 256, 0, st, tabu, (int)KS); return (int)cudaGetLastError(); });
+        const long long row4 = tp_ld / 4, tot4 = (long long)(Bn - 1) * row4;
+        if (Bn > 1 && tp_ld % 4 == 0)
+            push(temb_uni_ops, "temb.bcast", 0, [=](cudaStream_t st) { launch_k(k_bcast_rows, (int)((tot4 + 255) / 256), 256, 0, st, reinterpret_cast<float4*>(TP), row4, tot4); return (int)cudaGetLastError(); });
+        else if (Bn > 1) temb_uni_ops.clear();     // odd row length: keep the per-row path
     }
     int blk = 0;
     auto tp_entry = [&](const std::string& p, int cout) -> int {
@@ -295,6 +312,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         s.A = e1; s.B = PP(p + ".fc.weight"); s.C = TP + off; s.bias = PP(p + ".fc.bias"); s.M = B; s.N = cout; s.K = E;
         s.sa_m = E; s.sa_k = 1; s.sb_k = 1; s.sb_n = E; s.sc_m = tp_ld; s.sc_n = 1; s.alpha = 1.f; s.silu_a = 1;
         tp_table_host.push_back(s);
+        { SgemmParams u = s; u.M = 1; tp_uni_table_host.push_back(u); }
         fwd_flops += 2.0 * B * cout * E;
         if (train) {
             // dW_fc[o][e] = sum_b silu(e1[b][e]) * dTP[b][off+o]   (computed as C'[e][o], stored transposed)
@@ -477,6 +495,7 @@ inline int UnetEngine::build() {
         return (int)cudaMemcpy(ws + off, v.data(), v.size() * sizeof(SgemmParams), cudaMemcpyHostToDevice);
     };
     int rc;
+    if ((rc = up(tp_uni_table_off, tp_uni_table_host))) return rc;
     if ((rc = up(tp_table_off, tp_table_host)) || (rc = up(tpw_table_off, tpw_table_host)) || (rc = up(tpd_table_off, tpd_table_host)))
         return fail(-2, "table upload failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (!pack_table_host.empty() && cudaMemcpy(ws + pack_table_off, pack_table_host.data(), pack_table_host.size() * sizeof(PackEntry), cudaMemcpyHostToDevice))
