@@ -4,7 +4,7 @@
 // The generic engine (umma_gemm.cuh) re-loads the 128-pixel A tile once per tap: 9x the activation traffic out of L2, which
 // (with the weight tile) saturates the L2->SM path at ~35% tensor-pipe utilisation.  Here a CTA owns a 16 x (8*SUB) pixel
 // patch of one image.  Per 64-channel chunk ONE 4-D TMA box {64 ch, P px, 18 rows} lands the patch plus its 1-pixel halo in
-// shared memory (rows = pixels, 128 B each, SWIZZLE_128B, row pitch P = 16 or 24 pixels; out-of-image pixels are zero-filled
+// shared memory (rows = pixels, 128 B each, SWIZZLE_128B, row pitch P = patch width + 2 = 10 or 18 pixels; out-of-image pixels are zero-filled
 // by TMA = the conv's padding).  The A operand of tap (ky,kx) for sub-tile s is then just a UMMA descriptor into that
 // buffer: start row ky*P + kx + 8s, 8-row core matrices (8 consecutive x) with stride P*128 B between y rows.  The start is
 // then no longer 1024-B aligned; measured on B200 (tests/test_gemm_gpu.py::test_conv_halo_base_offset_probe): the
@@ -34,9 +34,10 @@ struct HaloParams {
 
 template <int BLOCK_N, int SUB>
 struct HaloCfg {
-    static constexpr int P = (SUB == 1) ? 16 : 24;             // halo row pitch in pixels (multiple of 8)
+    static constexpr int P = 8 * SUB + 2;                       // halo row pitch in pixels = patch width + 2 (10 or 18)
     static constexpr int A_ROWS = 18 * P;
-    static constexpr int A_BYTES = A_ROWS * 128;               // 36 KB / 54 KB
+    static constexpr int A_BYTES = A_ROWS * 128;                // 22.5 KB / 40.5 KB actually filled by TMA
+    static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;   // stage pitch (swizzle atoms need 1024-B aligned bases)
     // Weight stage = TPS taps of one 64-channel chunk.  Measured (DDPM_HALO_DBG experiments, profiles/README.md): every
     // producer -> issuer -> commit round trip costs ~300 cycles of the single issuing thread, whatever the stage holds; with
     // one tap per stage (256 MMA cycles at N=128) the tensor pipe starves at 65 %.  Three taps (one ky row) per stage = 768
@@ -48,8 +49,11 @@ struct HaloCfg {
     static constexpr int NB_ST = (TPS == 3) ? ((BLOCK_N == 128) ? 3 : 6) : ((BLOCK_N == 256) ? ((SUB == 1) ? 4 : 3) : ((SUB == 1) ? 8 : 6));
     static constexpr int NACC = (2 * SUB * BLOCK_N <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * SUB * BLOCK_N <= 128) ? 128 : ((NACC * SUB * BLOCK_N <= 256) ? 256 : 512);
-    static constexpr int TOTAL = NA * A_BYTES + NB_ST * B_BYTES + 1024 + 512;
+    static constexpr int OUT_STAGE_BYTES = 128 * 128;           // one 64-channel x 128-pixel output slab (TMA store source)
+    static constexpr int TOTAL = NA * A_STRIDE + NB_ST * B_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*bias vector*/;
 };
+constexpr int HALO_EPI_WARPS = 8;                               // two per TMEM lane quarter (see umma_gemm.cuh)
+constexpr int HALO_THREADS = 64 + 32 * HALO_EPI_WARPS;
 
 // descriptor with explicit base offset (bits 49..51)
 __device__ __forceinline__ uint64_t umma_smem_desc_bo(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
@@ -57,23 +61,27 @@ __device__ __forceinline__ uint64_t umma_smem_desc_bo(uint32_t saddr, uint32_t l
 }
 
 template <int BLOCK_N, int SUB>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const HaloParams p) {
     pdl_trigger();
     using CF = HaloCfg<BLOCK_N, SUB>;
     constexpr int P = CF::P;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
-    uint8_t* smB = smem + CF::NA * CF::A_BYTES;
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(smB + CF::NB_ST * CF::B_BYTES);
+    uint8_t* smB = smem + CF::NA * CF::A_STRIDE;
+    uint8_t* out_stage = smB + CF::NB_ST * CF::B_BYTES;            // [2][128 px][128 B]
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(out_stage + 2 * CF::OUT_STAGE_BYTES);
     uint64_t* empty_a = full_a + CF::NA;
     uint64_t* full_b = empty_a + CF::NA;
     uint64_t* empty_b = full_b + CF::NB_ST;
     uint64_t* tmem_full = empty_b + CF::NB_ST;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_vec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_a) + 512);     // [BLOCK_N] bias + per-image vector
+    const uint32_t s_vec_u32 = smem_u32(s_vec);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -84,7 +92,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
         for (int s = 0; s < CF::NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < CF::NB_ST; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], HALO_EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, CF::TMEM_COLS);
@@ -117,8 +125,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             if (!mbar_wait(&empty_a[sa], ph ^ 1, 5)) { ok = false; break; }
                             const uint32_t bytes = (sg.taps == 9) ? (uint32_t)CF::A_BYTES : (uint32_t)(16 * 8 * SUB * 128);
                             mbar_expect_tx(&full_a[sa], bytes);
-                            if (sg.taps == 9) tma_load_4d(smA + sa * CF::A_BYTES, mA, &full_a[sa], sg.c_base + kc * 64, x0 - 1, y0 - 1, n);
-                            else              tma_load_4d(smA + sa * CF::A_BYTES, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
+                            if (sg.taps == 9) tma_load_4d(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0 - 1, y0 - 1, n);
+                            else              tma_load_4d(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
                             ++ia;
                         }
                         for (int tp = 0; tp < sg.taps; tp += CF::TPS) {
@@ -153,7 +161,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     for (int kc = 0; kc < sg.kchunks && ok; ++kc) {
                         const int sa = ia % CF::NA; const uint32_t pha = (ia / CF::NA) & 1;
                         if (!mbar_wait(&full_a[sa], pha, 7)) { ok = false; break; }
-                        const uint32_t a_base = smem_u32(smA + sa * CF::A_BYTES);
+                        const uint32_t a_base = smem_u32(smA + sa * CF::A_STRIDE);
                         for (int tp0 = 0; tp0 < sg.taps; tp0 += CF::TPS) {
                             const int nt = (sg.taps - tp0 < CF::TPS) ? sg.taps - tp0 : CF::TPS;
                             const int sb = ib % CF::NB_ST; const uint32_t phb = (ib / CF::NB_ST) & 1;
@@ -193,8 +201,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     } else {
         // ======================= epilogue =======================
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;             // which 32-channel half of every 64-channel slab this warp converts
         const int r = q * 32 + lane;                 // accumulator row = pixel (y = r/8, x = r%8) of the sub-tile
+        const int tid_epi = (int)threadIdx.x - 64;
+        constexpr int EPI_T = 32 * HALO_EPI_WARPS;
         int it = 0;
+        uint32_t slab_ctr = 0;                       // staging-buffer parity, continues across tiles
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int m_tile = t % m_tiles, n_tile = t / m_tiles;
             const int n = m_tile / tiles_per_img, rr = m_tile % tiles_per_img;
@@ -203,59 +215,70 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const uint32_t acc_ph = (CF::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
             if (!mbar_wait(&tmem_full[acc], acc_ph, 3)) break;
             tc_fence_after();
-            const float* rv = p.rowvec ? p.rowvec + (long long)n * p.rowvec_ld : nullptr;
+            // bias + per-image timestep vector of this tile, staged once (a patch lies inside one image)
+            named_bar_sync(1, EPI_T);
+            for (int c = tid_epi; c < BLOCK_N; c += EPI_T) {
+                const int col = n_tile * BLOCK_N + c;
+                float v = 0.f;
+                if (col < p.N) {
+                    if (p.bias) v = __ldg(p.bias + col);
+                    if (p.rowvec) v += __ldg(p.rowvec + (long long)n * p.rowvec_ld + col);
+                }
+                s_vec[c] = v;
+            }
+            named_bar_sync(1, EPI_T);
 #pragma unroll 1
             for (int sub = 0; sub < SUB; ++sub) {
                 const long long pix = ((long long)n * p.H + y0 + (r >> 3)) * p.W + x0 + 8 * sub + (r & 7);
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * SUB * BLOCK_N + sub * BLOCK_N);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                for (int s0 = 0; s0 < BLOCK_N; s0 += 64) {            // Cout % 64 == 0: every slab is full
+                    if (n_tile * BLOCK_N + s0 >= p.N) break;
+                    const int c0 = s0 + grp * 32;
                     const int col = n_tile * BLOCK_N + c0;
-                    if (col >= p.N) break;
                     uint32_t v[32];
                     tmem_ld32(t_addr + (uint32_t)c0, v);
                     tmem_ld_wait();
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
-                    }
-                    if (rv) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + col) + j);
-                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b4;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(s_vec_u32 + (uint32_t)(c0 + 4 * j) * 4u));
+                        f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
                     }
                     if (p.residual) {
-                        const __nv_bfloat16* rp = p.residual + pix * p.ldr + col;
+                        uint32_t rs[16];
+                        ld_row64B(p.residual + pix * p.ldr + col, rs);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint32_t u[8];
-                            ld_global_nc_256(rp + j * 16, u);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
-                                f[j * 16 + e * 2] += t2.x; f[j * 16 + e * 2 + 1] += t2.y;
-                            }
+                        for (int e = 0; e < 16; ++e) {
+                            const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rs[e]));
+                            f[2 * e] += t2.x; f[2 * e + 1] += t2.y;
                         }
                     }
-                    // Cout % 64 == 0 and 32-column chunks: every lane's 64 output bytes are 32-byte aligned -> two STG.256
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col;
+                    // registers -> 128B-swizzled staging slab (row r = pixel, 16-byte chunk j at physical chunk j ^ (r & 7))
+                    uint8_t* buf = out_stage + (slab_ctr & 1) * CF::OUT_STAGE_BYTES + r * 128;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint32_t u[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(f[j * 16 + e * 2], f[j * 16 + e * 2 + 1]);
-                        st_global_256(o + j * 16, u);
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(buf + (((grp * 4 + j) ^ (r & 7)) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    // one barrier per slab: before it the issuing thread has waited until the previous store finished reading its
+                    // buffer (the one the next slab overwrites); after it all 128 pixel rows of this slab are staged
+                    fence_proxy_async_smem();
+                    if (tid_epi == 0) bulk_wait_group_read0();
+                    named_bar_sync(1, EPI_T);
+                    if (tid_epi == 0) {
+                        tma_store_4d(&tmO, out_stage + (slab_ctr & 1) * CF::OUT_STAGE_BYTES, n_tile * BLOCK_N + s0, x0 + 8 * sub, y0, n);
+                        bulk_commit_group();
                     }
+                    ++slab_ctr;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (threadIdx.x == 64) bulk_wait_group0();   // outstanding TMA stores read this CTA's shared memory
     }
 
     tc_fence_before();
@@ -267,7 +290,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct HaloLaunch { CUtensorMap a[3], b; HaloParams p; int block_n, sub; int tiles; double flops; };
+struct HaloLaunch { CUtensorMap a[3], b, o; HaloParams p; int block_n, sub; int tiles; double flops; };
 
 typedef ddpm_halo_desc HaloDesc;   // the C-ABI struct doubles as the internal description
 
@@ -286,7 +309,7 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
     p.N = d.Cout; p.out = d.out; p.ldo = d.Cout; p.bias = d.bias; p.rowvec = d.rowvec; p.rowvec_ld = d.rowvec_ld;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual); p.ldr = d.Cout; p.desc_base_offset_mode = d.base_offset_mode;
     p.nseg = d.nseg;
-    const int P = sub == 1 ? 16 : 24;
+    const int P = 8 * sub + 2;
     int rc;
     for (int s = 0; s < d.nseg; ++s) {
         p.seg[s] = HaloSeg{d.seg_map[s], d.seg_taps[s], d.seg_kchunks[s], d.seg_cbase[s]};
@@ -296,6 +319,7 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
     }
     for (int i = 0; i < 3; ++i) { bool used = false; for (int s = 0; s < d.nseg; ++s) used |= d.seg_map[s] == i; if (!used) g.a[i] = g.a[d.seg_map[0]]; }
     if ((rc = make_tmap_3d(&g.b, d.w, d.Ktot, d.Cout, 1, d.ldw, 0, 64, g.block_n))) return rc;
+    if ((rc = make_tmap_4d(&g.o, d.out, d.Cout, d.W, d.H, d.NB, d.Cout, 64, 8, 16, 1))) return rc;      // output slab = 64 ch x (8 x 16) px
     g.tiles = d.NB * p.tiles_x * p.tiles_y * p.n_tiles;
     g.flops = 2.0 * d.NB * d.H * d.W * (double)d.Cout * d.Ktot;
     return 0;
@@ -305,12 +329,13 @@ template <int BLOCK_N, int SUB>
 inline int launch_halo_inst(const HaloLaunch& g, cudaStream_t st) {
     using CF = HaloCfg<BLOCK_N, SUB>;
     auto kern = conv3x3_halo_kernel<BLOCK_N, SUB>;
+    static_assert(CF::TOTAL <= 232448, "halo conv: shared memory budget (227 KB) exceeded");
     static bool attr_done = false;
     if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL)); attr_done = true; }
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     const int ctas = g.tiles < num_sms ? g.tiles : num_sms;
-    launch_k(kern, ctas, 192, CF::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.p);
+    launch_k(kern, ctas, HALO_THREADS, CF::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.o, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

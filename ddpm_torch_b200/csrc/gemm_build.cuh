@@ -82,6 +82,15 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     } else {
         return fail(-10, "unknown gemm mode %d", d.mode);
     }
+    // TMA-store epilogue: plain bf16 outputs with identity row mapping (everything but fp32 / atomic / scattered-row outputs)
+    g.o = g.b; p.tma_store = 0;
+    static const bool no_tma_store = getenv("DDPM_NO_TMA_STORE") != nullptr;
+    const bool plain_rows = (d.mode != GEMM_KK || p.o_mul == 1) && d.mode != GEMM_MNMN;   // MN-major mode keeps 4 epilogue warps + direct stores
+    if (!no_tma_store && !(d.flags & (EPI_OUT_F32 | EPI_ATOMIC)) && plain_rows && d.out && (d.ldo % 8) == 0 &&
+        (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (d.out_z_stride % 8) == 0) {
+        if ((rc = make_tmap_3d(&g.o, d.out, d.N, d.M, gz, d.ldo, d.out_z_stride, 64, 128))) return rc;
+        p.tma_store = 1;
+    }
     return 0;
 }
 

@@ -81,7 +81,7 @@ inline bool pick_box(int W, int H, int rows, int& w_t, int& h_t, int& n_t) {
 
 // A fully-resolved GEMM launch (tensor maps are baked for fixed pointers; re-launchable, graph-capturable).
 struct GemmLaunch {
-    CUtensorMap a[3], b;
+    CUtensorMap a[3], b, o;   // o: output map of the TMA-store epilogue (p.tma_store), else a copy of b
     GemmParams p;
     dim3 grid;
     int mode, block_n;
@@ -97,7 +97,7 @@ inline bool gemm_shallow() { static const bool v = getenv("DDPM_GEMM_SHALLOW") !
 
 template <int BLOCK_N, int MODE, int STAGES, int CLUSTER, int KSTEPS>
 inline int launch_gemm_inst3(const GemmLaunch& g, cudaStream_t st) {
-    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS>;
+    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
     auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES, CLUSTER, KSTEPS>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -108,17 +108,18 @@ inline int launch_gemm_inst3(const GemmLaunch& g, cudaStream_t st) {
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
     // persistent: one CTA per SM (two when two fit: <= 96 KB of stages and 2 x 2*BLOCK_N <= 512 TMEM columns)
     const int per_sm = (SM::TOTAL <= 110 * 1024 && 4 * BLOCK_N <= 512) ? 2 : 1;
+    if (SM::TOTAL > 232448) return fail(-6, "gemm variant needs %d B of shared memory (> 227 KB)", SM::TOTAL);
     int ctas = (int)g.grid.x; if (ctas > num_sms * per_sm) ctas = num_sms * per_sm;
     if (CLUSTER > 1) {
         ctas = ctas / CLUSTER * CLUSTER;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+        cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(gemm_threads(MODE)); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        DDPM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.a[0], g.a[1], g.a[2], g.b, g.p));
+        DDPM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.a[0], g.a[1], g.a[2], g.b, g.o, g.p));
         return 0;
     }
-    launch_k(kern, ctas, 192, SM::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.p);
+    launch_k(kern, ctas, gemm_threads(MODE), SM::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.o, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -14,6 +14,14 @@ __device__ __forceinline__ const uint32_t* v_as_u32(const float* f) { return rei
 
 enum GemmMode { GEMM_KK = 0, GEMM_MNMN = 1, GEMM_KMN = 2 };
 enum EpiFlags { EPI_OUT_F32 = 1, EPI_ATOMIC = 2 };
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.  EIGHT epilogue warps (two per TMEM lane quarter, each
+// taking every other 32-column chunk): with one warp per scheduler the ~340-instruction chunk body ran at IPC < 0.5 and the
+// epilogue, not the MMA, bounded every short-K GEMM (ncu source view, profiles/README.md).
+// The MN-major mode (weight gradients: long K, fp32 atomic epilogue, run on the SIDE stream) keeps 4 epilogue warps: at 320
+// threads x 144 registers its CTA would leave no room in the register file for a GroupNorm block of the main chain to be
+// co-resident on the SM, which is the whole point of the side stream.
+__host__ __device__ constexpr int gemm_epi_warps(int mode) { return mode == 1 /*GEMM_MNMN*/ ? 4 : 8; }
+__host__ __device__ constexpr int gemm_threads(int mode) { return 64 + 32 * gemm_epi_warps(mode); }
 
 struct GemmSeg {
     int map;       // which A tensor map (0..2)
@@ -48,6 +56,7 @@ struct GemmParams {
                                     // 2 = MMA warp consumes stages without issuing MMAs, 4 = producer signals stages without TMA loads
     // epilogue
     void* out; int ldo; long long out_z_stride; long long out_tap_stride; int flags;
+    int tma_store;            // bf16 output goes registers -> swizzled shared memory -> cp.async.bulk.tensor store (tmO)
     const float* bias;        // [N] or null
     const float* rowvec;      // [M/rows_per_vec][rowvec_ld] or null (timestep-embedding projection per image)
     int rowvec_ld, rows_per_vec;
@@ -59,13 +68,17 @@ struct GemmParams {
 // ~400 cycles of dependent mbarrier / TMA-issue / commit instructions on the single issuing threads (measured: the kernel with
 // loads, MMAs and epilogue math disabled still ran at 52% of its full time), more than the 256-cycle MMA time of one N=128
 // slab - so N <= 128 configurations move two slabs per handshake.
-template <int BLOCK_N, int STAGES, int KSTEPS = 1>
+template <int BLOCK_N, int STAGES, int KSTEPS = 1, int OUT_STAGING = 1>
 struct GemmSmem {
     static constexpr int A_BYTES = 128 * 64 * 2;
     static constexpr int B_BYTES = BLOCK_N * 64 * 2;
     static constexpr int SLAB_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = KSTEPS * SLAB_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // epilogue staging: 2 x {128 rows x 128 B} output slabs for the TMA store + BLOCK_N floats of (bias + per-image vector)
+    // (OUT_STAGING = 0 for the MN-major mode: its CTAs run on the side stream and must leave shared memory for the GroupNorm
+    // blocks of the main chain to be co-resident; they use direct stores.)
+    static constexpr int OUT_STAGE_BYTES = OUT_STAGING ? 128 * 128 : 0;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*epilogue vector*/;
 };
 
 __device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& y, int& x) {
@@ -83,23 +96,26 @@ __device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& 
 // CLUSTER > 1 (KK only): CLUSTER CTAs with consecutive m_tiles (same weight tile) form a thread-block cluster; each loads
 // 1/CLUSTER of the B tile and multicasts it to all of them, so the weight traffic out of L2 drops by CLUSTER.
 template <int BLOCK_N, int MODE, int STAGES, int CLUSTER, int KSTEPS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
     pdl_trigger();                                  // dependents may be scheduled; they block in their own pdl_wait()
-    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS>;
+    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
     constexpr int A_MN = (MODE == GEMM_MNMN) ? 1 : 0;
     constexpr int B_MN = (MODE == GEMM_KK) ? 0 : 1;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+    uint8_t* out_stage = smem + STAGES * SM::STAGE_BYTES;                  // [2][128 rows][128 B], 1024-aligned
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * SM::OUT_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_vec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [BLOCK_N] bias (+ per-image vector) of the current tile
+    const uint32_t s_vec_u32 = smem_u32(s_vec);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -130,7 +146,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], gemm_epi_warps(MODE)); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -278,10 +294,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         }
     } else {
-        // ======================= epilogue: 4 warps <-> 4 TMEM lane quarters =======================
+        // ======================= epilogue: 8 warps, 2 per TMEM lane quarter =======================
         const int q = warp & 3;
+        constexpr int NGRP = gemm_epi_warps(MODE) / 4;   // warp groups per TMEM lane quarter (1 or 2)
+        const int grp = (warp - 2) >> 2;             // which 32-column part of every (32*NGRP)-column slab this warp converts
         const int r = q * 32 + lane;                 // accumulator row
         int it = 0;
+        uint32_t slab_ctr = 0;                       // staging-buffer parity of the TMA-store path, continues across tiles
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int m_tile = t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
             const int ns = slabs_of(z);
@@ -301,43 +320,67 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             const long long zoff = (MODE == GEMM_MNMN) ? (long long)batch * p.out_z_stride + (long long)tap * p.out_tap_stride
                                                       : ((MODE == GEMM_KK && p.kk_splits > 1) ? 0 : (long long)z * p.out_z_stride);
-            const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
+            // Bias and (when every row of the tile belongs to the same image) the per-image vector are staged ONCE per tile in
+            // shared memory: fetched per chunk with global loads they cost as much as the stores (measured, K=256 GEMMs:
+            // 35.0 us -> 24.0 us without the bias loads, 23.3 us without the stores, 13.8 us without either).
+            const bool vec_uniform = p.rowvec != nullptr && (p.rows_per_vec % 128) == 0;
+            const float* rv = (p.rowvec && !vec_uniform && row_ok) ? p.rowvec + (long long)(row / p.rows_per_vec) * p.rowvec_ld : nullptr;
+            const int tid_epi = (int)threadIdx.x - 64;
+            constexpr int EPI_T = 32 * gemm_epi_warps(MODE);
+            named_bar_sync(1, EPI_T);                                 // the previous tile's readers are done with s_vec
+            for (int c = tid_epi; c < BLOCK_N; c += EPI_T) {
+                const int col = n_tile * BLOCK_N + c;
+                float v = 0.f;
+                if (col < p.N && ns > 0) {
+                    if (p.bias) v = __ldg(p.bias + col);
+                    if (vec_uniform) v += __ldg(p.rowvec + (long long)((m_tile * 128) / p.rows_per_vec) * p.rowvec_ld + col);
+                }
+                s_vec[c] = v;
+            }
+            named_bar_sync(1, EPI_T);
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            const bool tma_out = p.tma_store != 0 && NGRP == 2;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int s0 = 0; s0 < BLOCK_N; s0 += 32 * NGRP) {         // one slab per iteration: 64 columns (2 groups) or 32 (1 group)
+                if (n_tile * BLOCK_N + s0 >= p.N || ns == 0) break;   // uniform across the CTA
+                const int c0 = s0 + grp * 32;
                 const int col = n_tile * BLOCK_N + c0;
-                if (col >= p.N || ns == 0) break;         // uniform across the CTA
+                const bool active = col < p.N;                        // N % 64 == 32: the last slab has one chunk only
                 uint32_t v[32];
-                tmem_ld32(t_addr + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (!row_ok || (p.dbg & 1)) continue;
+                if (active) { tmem_ld32(t_addr + (uint32_t)c0, v); tmem_ld_wait(); }
+                if (p.dbg & 1) continue;
+                if (active && (row_ok || tma_out)) {
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-                        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
+                for (int j = 0; j < 8; ++j) {
+                    float4 b4;                                          // broadcast read (explicit ld.shared: the carved pointer is generic)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(s_vec_u32 + (uint32_t)(c0 + 4 * j) * 4u));
+                    f[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.alpha, b4.x); f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b4.y);
+                    f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b4.z); f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b4.w);
                 }
                 if (rv) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + col) + j);
                         f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w; }
                 }
-                if (p.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
+                if (p.residual && row_ok) {
+                    uint32_t rs[16];
+                    ld_row64B(p.residual + orow * p.ldr + col, rs);
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const uint4 u = __ldg(rp + j4);
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 t2 = __bfloat1622float2(h[e]);
-                            f[j4 * 8 + e * 2] += t2.x; f[j4 * 8 + e * 2 + 1] += t2.y;
-                        }
+                    for (int e = 0; e < 16; ++e) {
+                        const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rs[e]));
+                        f[2 * e] += t2.x; f[2 * e + 1] += t2.y;
                     }
                 }
-                if (p.flags & EPI_ATOMIC) {
+                if (tma_out && NGRP == 2) {
+                    // registers -> 128B-swizzled staging slab (row r, 16-byte chunk j at physical chunk j ^ (r & 7))
+                    uint8_t* buf = out_stage + (slab_ctr & 1) * SM::OUT_STAGE_BYTES + r * 128;
+                    const int jb = grp * 4;                          // which half of the 64-column slab
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(buf + (((jb + j) ^ (r & 7)) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                } else if (p.flags & EPI_ATOMIC) {
                     float* o = reinterpret_cast<float*>(p.out) + zoff + orow * p.ldo + col;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -362,12 +405,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(o)[j] = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
                     }
                 }
+                }
+                if (tma_out && NGRP == 2) {
+                    // one barrier per slab: before it, the issuing thread has waited until the PREVIOUS store finished reading
+                    // its buffer (the one the next slab will overwrite); after it, every lane's rows are in the staging slab
+                    fence_proxy_async_smem();
+                    if (tid_epi == 0) bulk_wait_group_read0();
+                    named_bar_sync(1, EPI_T);
+                    if (tid_epi == 0) {
+                        tma_store_3d(&tmO, out_stage + (slab_ctr & 1) * SM::OUT_STAGE_BYTES, n_tile * BLOCK_N + s0, m_tile * 128, z);
+                        bulk_commit_group();
+                    }
+                    ++slab_ctr;
+                }
             }
             // hand the accumulator buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (threadIdx.x == 64) bulk_wait_group0();  // outstanding TMA stores read this CTA's shared memory
     }
 
     tc_fence_before();
