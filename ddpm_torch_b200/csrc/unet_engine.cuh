@@ -362,14 +362,16 @@ struct UnetEngine {
                 return launch_cluster(k_gn_fused_fwd, gf, thr5, shm, cl, st, aa, K, ga, be, ppc, 1e-6f); });
             return sv;
         }
-        int nblk, ppb; gn_grid(Bn, HW, 6, nblk, ppb);
+        static const int st_occ = getenv("DDPM_GN_STATS_OCC") ? atoi(getenv("DDPM_GN_STATS_OCC")) : 4;
+        static const int ap_occ = getenv("DDPM_GN_APPLY_OCC") ? atoi(getenv("DDPM_GN_APPLY_OCC")) : 4;
+        int nblk, ppb; gn_grid(Bn, HW, st_occ, nblk, ppb);
         const dim3 g1(nblk, Bn);
         GnFin fin; fin.gamma = ga; fin.beta = be; fin.K = K; fin.eps = 1e-6f; fin.ticket = at<int>(zero_fwd((size_t)Bn * 4));
         push(L, name + ".stats", 0, [=](cudaStream_t st) {
             launch_k(k_gn_stats, g1, thr, 0, st, gs, stats, HW, ppb, fin);
             return (int)cudaGetLastError(); });
         GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
-        int nb2, ppb2; gn_grid(Bn, HW, 4, nb2, ppb2);
+        int nb2, ppb2; gn_grid(Bn, HW, ap_occ, nb2, ppb2);
         const dim3 g2(nb2, Bn);
         UnetEngine* self = this;
         push(L, name + ".apply", 0, [a, g2, thr, ppb2, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
@@ -413,7 +415,11 @@ struct UnetEngine {
                 return;
             }
         }
-        int nblk, ppb; gn_grid(Bn, HW, 2, nblk, ppb);
+        // Grid granularity measured on the whole step (bench.py, DDPM_GN_BWD_OCC / _STATS_OCC / _APPLY_OCC sweeps): blocks per
+        // image = 148*occ/B; occ 4 is best for all three passes (10.49 ms/step; occ 2: 10.69, 8: 11.04, 16: 11.71) - per-block
+        // prologue / atomics cost more than the wave-quantisation they would save.
+        static const int gn_bwd_occ = getenv("DDPM_GN_BWD_OCC") ? atoi(getenv("DDPM_GN_BWD_OCC")) : 4;
+        int nblk, ppb; gn_grid(Bn, HW, gn_bwd_occ, nblk, ppb);
         a.pix_per_block = ppb;
         const dim3 g1(nblk, Bn);
         const size_t shm = (size_t)2 * C * 4;
