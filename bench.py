@@ -419,6 +419,22 @@ def bench_sampler(D, model, dev, bs=256):
         s = e0.elapsed_time(e1) * 1e-3
         assert torch.isfinite(x).all()
         out[name] = {"images_per_s": bs / s, "seconds_per_batch": s, "ms_per_step": s / S * 1e3, "bs": bs, "steps": S, "rng": "torch generator (reference-compatible stream)"}
+    # generate.py:128-130 tail: device uint8 NHWC conversion + pinned async D2H of the finished batch vs the reference's
+    # fp32 .cpu() + five host passes
+    from ddpm_torch_b200.postprocess import to_uint8_host_async
+    from oracle import ddpm_ref as R
+    pinned, ev = to_uint8_host_async(x); ev.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        pinned, ev = to_uint8_host_async(x, pinned); ev.synchronize()
+    t_dev = (time.perf_counter() - t0) / 10
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ref = R.to_uint8_nhwc(x.cpu()).numpy()
+    t_ref = (time.perf_counter() - t0) / 3
+    assert (ref == pinned.numpy()).all()
+    out["postprocess_uint8"] = {"device_kernel_plus_pinned_d2h_ms": t_dev * 1e3, "reference_host_path_ms": t_ref * 1e3, "bs": bs,
+                                "bit_exact_vs_reference_expression": True}
     model.train()
     return out
 

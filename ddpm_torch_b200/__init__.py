@@ -8,6 +8,8 @@ from .diffusion import GaussianDiffusion, get_beta_schedule
 from .ddim import DDIM, get_selection_schedule
 from . import parallel
 from . import optim
+from . import postprocess
+from . import checkpoint
 from .optim import EMA, FusedAdam
 
 __all__ = ["UNet", "GaussianDiffusion", "get_beta_schedule", "DDIM", "get_selection_schedule", "EMA", "FusedAdam"]

@@ -95,6 +95,7 @@ def lib():
             "ddpm_unet_launches_per_forward": ([vp], i32),
             "ddpm_unet_launch_counts": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
             "ddpm_opt_step": ([vp, vp, vp, vp, vp, i64, C.POINTER(OptCfg), vp, vp, vp], i32),
+            "ddpm_to_uint8_nhwc": ([vp, vp, i32, i32, i32, i32, vp], i32),
         }
         for name, (args, res) in sig.items():
             fn = getattr(L, name)
@@ -109,7 +110,7 @@ EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "d
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",
            "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_unet_plan_stats",
-           "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts", "ddpm_opt_step"]
+           "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts", "ddpm_opt_step", "ddpm_to_uint8_nhwc"]
 
 
 def check(rc, what=""):

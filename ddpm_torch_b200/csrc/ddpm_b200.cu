@@ -228,6 +228,21 @@ int ddpm_opt_step(float* params, const float* grads, float* exp_avg, float* exp_
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }
+int ddpm_to_uint8_nhwc(const float* x, uint8_t* out, int B, int C, int H, int W, void* stream) {
+    if (!x || !out) return fail(-41, "ddpm_to_uint8_nhwc: null buffer");
+    if (B <= 0 || H <= 0 || W <= 0 || C < 1 || C > 4) return fail(-41, "ddpm_to_uint8_nhwc: need B,H,W > 0 and 1 <= C <= 4");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long npix = (long long)B * H * W;
+    const int grid = (int)((npix + 255) / 256 < 148 * 16 ? (npix + 255) / 256 : 148 * 16);
+    switch (C) {
+        case 1: launch_k(k_to_uint8_nhwc<1>, grid, 256, 0, st, x, out, npix, H * W); break;
+        case 2: launch_k(k_to_uint8_nhwc<2>, grid, 256, 0, st, x, out, npix, H * W); break;
+        case 3: launch_k(k_to_uint8_nhwc<3>, grid, 256, 0, st, x, out, npix, H * W); break;
+        default: launch_k(k_to_uint8_nhwc<4>, grid, 256, 0, st, x, out, npix, H * W); break;
+    }
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd, int* n_bwd, int* n_tc, int* n_gen, double* ff, double* bf) {
     if (n_fwd) *n_fwd = (int)h->e.fwd_ops.size();
     if (n_bwd) *n_bwd = (int)h->e.bwd_ops.size();

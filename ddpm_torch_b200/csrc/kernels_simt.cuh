@@ -1313,6 +1313,29 @@ __global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict_
         x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sg), zz));
     }
 }
+// generate.py:129  (x * 127.5 + 127.5).round().clamp(0, 255).to(uint8).permute(0, 2, 3, 1): NCHW fp32 -> NHWC uint8.
+// Bit-exact with the reference expression: separate fp32 multiply and add (no FMA contraction), round-half-to-even.
+template <int C>
+__global__ void k_to_uint8_nhwc(const float* __restrict__ x, unsigned char* __restrict__ out, long long npix /*B*H*W*/, int HW) {
+    pdl_entry();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / HW; const int p = (int)(i - b * HW);
+        const float* src = x + b * C * (long long)HW + p;
+        unsigned char v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float f = __fadd_rn(__fmul_rn(__ldg(src + (long long)c * HW), 127.5f), 127.5f);
+            f = fminf(fmaxf(rintf(f), 0.f), 255.f);
+            v[c] = (unsigned char)f;
+        }
+        unsigned char* o = out + i * C;
+        if (C == 4) *reinterpret_cast<uchar4*>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[c] = v[c];
+        }
+    }
+}
 // rows 1..B-1 of a [B][row4] float4 matrix <- row 0
 __global__ void k_bcast_rows(float4* __restrict__ m, long long row4, long long tot4) {
     pdl_entry();

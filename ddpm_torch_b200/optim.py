@@ -128,7 +128,9 @@ class FusedAdam:
 
     @property
     def param_groups(self):
-        return [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+        # the full key set of torch.optim.Adam's param group, so that a stock Adam can load the state and keep stepping
+        return [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
                  "initial_lr": self.base_lr, "params": list(range(len(self._model._params)))}]
 
     def step(self):

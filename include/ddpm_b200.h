@@ -144,6 +144,11 @@ typedef struct ddpm_opt_cfg {
 int ddpm_opt_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, long long n,
                   const ddpm_opt_cfg* cfg, void* state, float* norm_out, void* stream);
 
+/* ---- generate.py:129 post-processing on the device:
+ * out[b][y][x][c] = uint8(clamp(round(x[b][c][y][x] * 127.5 + 127.5), 0, 255)) - NCHW fp32 samples -> NHWC uint8 images, the
+ * layout PIL.Image.fromarray consumes (generate.py:112-114).  Bit-exact with the reference expression.  C in 1..4. */
+int ddpm_to_uint8_nhwc(const float* x, uint8_t* out, int B, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

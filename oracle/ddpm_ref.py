@@ -436,3 +436,8 @@ TINY_CFG = dict(in_channels=3, hid_channels=32, out_channels=3, ch_multipliers=(
 # smallest config whose every channel count is a multiple of 64 (tensor-core path eligible)
 SMALL64_CFG = dict(in_channels=3, hid_channels=64, out_channels=3, ch_multipliers=(1, 2),
                    num_res_blocks=1, apply_attn=(False, True), drop_rate=0.0)
+
+
+def to_uint8_nhwc(x):
+    """generate.py:129, verbatim: fp32 NCHW samples in [-1, 1] -> uint8 NHWC images."""
+    return (x * 127.5 + 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)

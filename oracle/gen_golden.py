@@ -185,6 +185,7 @@ def main():
                         eps=eps.to(torch.float16)), os.path.join(out_dir, "unet_celebahq_bs1.pt"))
         print(f"unet_celebahq_bs1.pt done |eps|max={eps.abs().max():.4f}")
     gen_optim(out_dir)
+    gen_checkpoint(out_dir)
 
 
 def gen_optim(out_dir):
@@ -223,7 +224,42 @@ def gen_optim(out_dir):
     print("optim.pt written; norms", [round(n, 4) for n in fx["norms"]], "lrs", fx["lrs"])
 
 
+MICRO_CFG = dict(in_channels=3, hid_channels=32, out_channels=3, ch_multipliers=(1,), num_res_blocks=1, apply_attn=(False,), drop_rate=0.0)
+
+
+def gen_checkpoint(out_dir):
+    """A checkpoint in the reference's wire format (utils/train.py:264-276: {"model", "optimizer", "ema", "scheduler",
+    "epoch"}), written after 3 real optimisation steps of the UNMODIFIED reference UNet / EMA with torch Adam + LambdaLR,
+    with DDP-style "module." key prefixes on the model and EMA entries (what `train.py --distributed` writes and
+    generate.py:83-85 / utils/train.py:255-259 strip)."""
+    ddpm_torch, _ = import_reference()
+    from ddpm_torch.utils.train import EMA
+    from torch.optim import Adam, lr_scheduler
+    m, sd = build_ref_unet(ddpm_torch, MICRO_CFG, 77)
+    m.train()
+    opt = Adam(m.parameters(), lr=2e-4, betas=(0.9, 0.999))
+    sch = lr_scheduler.LambdaLR(opt, lr_lambda=lambda t: min((t + 1) / 5, 1.0))
+    ema = EMA(m, decay=0.9999)
+    diff = ddpm_torch.GaussianDiffusion(betas=ddpm_torch.get_beta_schedule("linear", 1e-4, 0.02, 1000), model_mean_type="eps",
+                                        model_var_type="fixed-large", loss_type="mse")
+    g = torch.Generator().manual_seed(5)
+    for _ in range(3):
+        x0 = torch.randn(2, 3, 16, 16, generator=g); t = torch.randint(1000, (2,), generator=g); nz = torch.randn(2, 3, 16, 16, generator=g)
+        diff.train_losses(m, x0, t, nz).mean().backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=1.0)
+        opt.step(); opt.zero_grad(set_to_none=True); sch.step(); ema.update()
+    pre = lambda d: {"module." + k: v for k, v in d.items()}
+    esd = ema.state_dict()
+    chk = {"model": pre(m.state_dict()), "optimizer": opt.state_dict(),
+           "ema": {"decay": esd["decay"], "shadow": pre(esd["shadow"]), "num_updates": esd["num_updates"]},
+           "scheduler": sch.state_dict(), "epoch": 7}
+    torch.save(dict(cfg=MICRO_CFG, seed=77, chkpt=chk), os.path.join(out_dir, "checkpoint_micro.pt"))
+    print("checkpoint_micro.pt written; scheduler", {k: v for k, v in chk["scheduler"].items() if k != "lr_lambdas"})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        gen_checkpoint(os.path.join(ROOT, "tests", "golden")); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "optim":
         gen_optim(os.path.join(ROOT, "tests", "golden")); sys.exit(0)
     main()

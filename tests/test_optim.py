@@ -149,3 +149,31 @@ def test_optim_refuses_cpu_and_foreign_models():
         m = D.UNet(**{k: cfg[k] for k in ("in_channels", "hid_channels", "out_channels", "ch_multipliers", "num_res_blocks", "apply_attn")})
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             FusedAdam(m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5, 3, 32, 32), (2, 3, 256, 256), (3, 1, 7, 5), (2, 4, 16, 16)])
+def test_to_uint8_nhwc_bit_exact(shape):
+    """generate.py:129 on the device: bit-exact against the literal reference expression evaluated on the CPU, including
+    rounding ties (k + 0.5 -> even), out-of-range values and the exact end points."""
+    from ddpm_torch_b200.postprocess import to_uint8_nhwc, to_uint8_host_async
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(shape, generator=g) * 0.8
+    flat = x.view(-1)
+    ties = (torch.arange(0, 256, dtype=torch.float32) + 0.5 - 127.5) / 127.5           # pre-images of k + 0.5
+    n = min(flat.numel() // 2, ties.numel())
+    flat[:n] = ties[:n]
+    flat[n:n + 6] = torch.tensor([-1.0, 1.0, -3.0, 3.0, 0.0, 1.0 - 2 ** -24])
+    ref = R.to_uint8_nhwc(x)                                                            # CPU, as the reference runs it
+    out = to_uint8_nhwc(x.cuda())
+    assert out.dtype == torch.uint8 and out.shape == ref.shape and out.is_contiguous()
+    assert torch.equal(out.cpu(), ref.contiguous())
+    pinned, ev = to_uint8_host_async(x.cuda())
+    ev.synchronize()
+    assert pinned.is_pinned() and torch.equal(pinned, ref.contiguous())
+
+
+def test_to_uint8_refuses_cpu():
+    from ddpm_torch_b200.postprocess import to_uint8_nhwc
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        to_uint8_nhwc(torch.zeros(1, 3, 4, 4))
