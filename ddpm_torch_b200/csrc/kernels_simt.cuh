@@ -1336,6 +1336,81 @@ __global__ void k_to_uint8_nhwc(const float* __restrict__ x, unsigned char* __re
         }
     }
 }
+// out_conv on the tensor cores (unet.py:138-142): the 3x3 conv C -> CO<=4 is computed as a 1x1 GEMM to 9*CO "tap outputs"
+// per pixel, T[p][t*CO + co] = sum_c a[p][c] * w[co][c][t] (fp32, [P][32]), followed by this gather:
+// out[b][co][y][x] = bias[co] + sum_t T[(b, y + t/3 - 1, x + t%3 - 1)][t*CO + co]  (zero outside the image).
+// k_pack_tapco builds the GEMM's B operand: rows r = t*CO + co of [32][C] bf16 (rows >= 9*CO stay zero).
+__global__ void k_pack_tapco(const float* __restrict__ w /*[CO][C][9]*/, bf16* __restrict__ out /*[32][C]*/, int CO, int C) {
+    pdl_entry();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CO * C * 9) return;
+    const int t = i % 9, c = (i / 9) % C, co = i / (9 * C);
+    out[(long long)(t * CO + co) * C + c] = __float2bfloat16_rn(w[i]);
+}
+// transposed pack for the data gradient: out[c][t*CO + co] = w[co][c][t]   ([C][64] bf16, columns >= 9*CO stay zero)
+__global__ void k_pack_tapco_t(const float* __restrict__ w, bf16* __restrict__ out, int CO, int C) {
+    pdl_entry();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CO * C * 9) return;
+    const int t = i % 9, c = (i / 9) % C, co = i / (9 * C);
+    out[(long long)c * 64 + t * CO + co] = __float2bfloat16_rn(w[i]);
+}
+// 3x3 im2col of a narrow NCHW fp32 image (CI <= 7 channels) into NHWC bf16 rows of 64: dst[p][t*CI + ci] = src[ci][p + sign*o_t],
+// o_t = (t/3 - 1, t%3 - 1), zero outside the image and for columns >= 9*CI.  sign = +1: the conv's input patches (weight
+// gradient of in_conv); sign = -1: the patches the transposed conv sees (data and weight gradients of out_conv over d_eps).
+template <int CI>
+__global__ void __launch_bounds__(256) k_im2col3(const float* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int sign) {
+    pdl_entry();
+    const long long P = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H); const long long b = i / ((long long)W * H);
+        __align__(16) bf16 row[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + sign * (t / 3 - 1), xx = x + sign * (t % 3 - 1);
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) row[t * CI + ci] = __float2bfloat16_rn(__ldg(src + ((b * CI + ci) * H + yy) * W + xx));
+        }
+        uint4* o = reinterpret_cast<uint4*>(dst + i * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const uint4*>(row)[j];
+    }
+}
+// tap-major GEMM results back to OIHW fp32 gradients:
+//   mode 0 (out_conv):  gw[(co*C + c)*9 + t]  = S[(t*CO + co)*C + c]      S = [64][C]
+//   mode 1 (in_conv):   gw[(co*CI + ci)*9 + t] = S[co*64 + t*CI + ci]      S = [C][64]
+__global__ void k_unpack_tap(const float* __restrict__ S, float* __restrict__ gw, int CO, int CI, int mode) {
+    pdl_entry();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CO * CI * 9) return;
+    const int t = i % 9, ci = (i / 9) % CI, co = i / (9 * CI);
+    gw[i] = mode == 0 ? S[(long long)(t * CO + co) * CI + ci] : S[(long long)co * 64 + t * CI + ci];
+}
+template <int CO>
+__global__ void __launch_bounds__(256) k_out_gather(const float* __restrict__ T /*[P][32]*/, const float* __restrict__ bias, float* __restrict__ out /*NCHW*/,
+                                                   int B, int H, int W) {
+    pdl_entry();
+    const long long P = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H); const long long b = i / ((long long)W * H);
+        float acc[CO];
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[co] = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float* r = T + ((b * H + yy) * W + xx) * 32 + t * CO;
+#pragma unroll
+            for (int co = 0; co < CO; ++co) acc[co] += __ldg(r + co);
+        }
+#pragma unroll
+        for (int co = 0; co < CO; ++co) out[((b * CO + co) * H + y) * W + x] = acc[co];
+    }
+}
 // rows 1..B-1 of a [B][row4] float4 matrix <- row 0
 __global__ void k_bcast_rows(float4* __restrict__ m, long long row4, long long tot4) {
     pdl_entry();

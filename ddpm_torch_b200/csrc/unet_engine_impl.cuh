@@ -378,6 +378,27 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
             bwd_flops += 2.0 * P * ch * Cin * 9;
             const long long s_c = (long long)Cin * 9;
+            static const bool no_tc_in = getenv("DDPM_NO_TC_OUTCONV") != nullptr;
+            if (!no_tc_in && ch % 64 == 0 && tc_ok_geom(H, W) && 9 * Cin <= 64) {
+                // weight gradient on the tensor cores: X = im2col(x) [P][64] bf16, S[ch][64] = dY^T x X (MN-major GEMM, side stream)
+                T4 X = newT(B, H, W, 64);
+                bf16* Xp = bp(X);
+                const int nim = grid_for(P);
+                push(bwd_ops, "in_conv.im2col", 0, [=](cudaStream_t st) {
+                    switch (Cin) {
+                        case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
+                        case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
+                        case 3: launch_k(k_im2col3<3>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
+                        default: launch_k(k_im2col3<4>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
+                    }
+                    return (int)cudaGetLastError(); }, 1, true);
+                float* S2 = at<float>(zero_bwd((size_t)ch * 64 * 4));
+                wgrad_op("in_conv.wgrad", dY, one(X), 1, 1, MAP_NORMAL, S2, ch);
+                const int nun = (ch * Cin * 9 + 255) / 256;
+                push(bwd_ops, "in_conv.wunpack", 0, [=](cudaStream_t st) { launch_k(k_unpack_tap, nun, 256, 0, st, S2, gw, ch, Cin, 1); return (int)cudaGetLastError(); }, 1, true);
+                colsum_op("in_conv.bias", dY, nullptr, 0, gb, nullptr, ch);
+                return;
+            }
             push(bwd_ops, "in_conv.wgrad", 2.0 * P * ch * Cin * 9, [=](cudaStream_t st) {
                 switch (Cin) {
                     case 1: launch_k(k_corr3x3<1>, nb, ch, 0, st, d, self->x_in, gw, s_c, 9, 1, 0, gb, Bn, Hn, Wn, ch, ppb); break;
@@ -427,6 +448,40 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         const int nblk = grid_for((long long)B * H * W);
         const double fl = 2.0 * B * H * W * ch * Cout * 9;
         fwd_flops += fl;
+        static const bool no_tc_out = getenv("DDPM_NO_TC_OUTCONV") != nullptr;
+        bool tc_out = !no_tc_out && ch % 64 == 0 && tc_ok_geom(H, W) && 9 * Cout <= 32;
+        bf16* w27t = nullptr;
+        if (tc_out) {
+            // tensor-core path: 1x1 GEMM a[P][ch] x W27[32][ch]^T -> fp32 tap outputs T[P][32], then a 9-point gather
+            bf16* w27 = at<bf16>(alloc_once_zero((size_t)32 * ch * 2));
+            float* T = at<float>(alloc((size_t)B * H * W * 32 * 4));
+            const int npk = (Cout * ch * 9 + 255) / 256;
+            push(pack_ops, "out_conv.pack27", 0, [=](cudaStream_t st) { launch_k(k_pack_tapco, npk, 256, 0, st, wo, w27, Cout, ch); return (int)cudaGetLastError(); });
+            if (train) {
+                w27t = at<bf16>(alloc_once_zero((size_t)ch * 64 * 2));
+                bf16* w27tp = w27t;
+                push(pack_ops, "out_conv.pack27t", 0, [=](cudaStream_t st) { launch_k(k_pack_tapco_t, npk, 256, 0, st, wo, w27tp, Cout, ch); return (int)cudaGetLastError(); });
+            }
+            ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+            d.mode = GEMM_KK; d.M = B * H * W; d.N = 32; d.block_n = 64; d.W = W; d.H = H; d.NB = B;
+            d.a_ptr[0] = ap; d.a_C[0] = ch; d.a_ld[0] = ch;
+            d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 1; d.seg_kchunks[0] = ch / 64; d.seg_cbase[0] = 0;
+            d.b_ptr = w27; d.b_K = ch; d.b_rows = 32; d.b_batch = 1; d.b_ld = ch; d.b_bs = 0;
+            d.out = T; d.ldo = 32; d.alpha = 1.f; d.grid_z = 1; d.flags = EPI_OUT_F32;
+            ++n_tc_gemms;
+            if (!dry) {
+                GemmLaunch g; const int rc = build_gemm(d, g);
+                if (rc) return rc;
+                push(fwd_ops, "out_conv.2", fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+            } else push(fwd_ops, "out_conv.2", fl, [](cudaStream_t) { return 0; });
+            push(fwd_ops, "out_conv.2.gather", 0, [=](cudaStream_t st) {
+                switch (Cout) {
+                    case 1: launch_k(k_out_gather<1>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn); break;
+                    case 2: launch_k(k_out_gather<2>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn); break;
+                    default: launch_k(k_out_gather<3>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn); break;
+                }
+                return (int)cudaGetLastError(); });
+        } else
         push(fwd_ops, "out_conv.2", fl, [=](cudaStream_t st) {
             switch (Cout) {
                 case 1: launch_k(k_out_conv<1>, nblk, 256, shm, st, ap, wo, bo, self->eps_dst, Bn, Hn, Wn, ch); break;
@@ -446,6 +501,29 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 const size_t shm2 = (size_t)(ch * Cout * 9 + ch) * 4; const int n2 = grid_for((long long)Bn * Hn * Wn / 2, 128);
                 const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
                 bwd_flops += 2.0 * fl;
+                if (tc_out) {
+                    // tensor-core backward: E = im2col(d_eps) [P][64] bf16 (shared by both gradients);
+                    // d_a = E x W27^T (1x1 conv 64 -> ch), dW = E^T x a (MN-major GEMM on the side stream) -> OIHW
+                    T4 E = newT(B, H, W, 64);
+                    bf16* Ep = bp(E);
+                    const int nim = grid_for((long long)Bn * Hn * Wn);
+                    push(bwd_ops, "out_conv.2.im2col", 0, [=](cudaStream_t st) {
+                        const float* de = self->deps_src;
+                        launch_k(k_chansum_nchw, dim3(64, Cout), 256, 0, st, de, gb, Bn, Cout, Hn * Wn);
+                        switch (Cout) {
+                            case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1); break;
+                            case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1); break;
+                            default: launch_k(k_im2col3<3>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1); break;
+                        }
+                        return (int)cudaGetLastError(); }, 2);
+                    ConvSpec cs; cs.name = "out_conv.2.dgrad"; cs.in = one(E); cs.ksize = 1; cs.wp = w27t; cs.ldw = 64;
+                    cs.out = d_a; cs.Co = ch; cs.Ho = H; cs.Wo = W;
+                    conv_op(bwd_ops, cs, nullptr);
+                    float* S = at<float>(zero_bwd((size_t)64 * ch * 4));
+                    wgrad_op("out_conv.2.wgrad", E, one(a_out), 1, 1, MAP_NORMAL, S, 64);
+                    const int nun = (Cout * ch * 9 + 255) / 256;
+                    push(bwd_ops, "out_conv.2.wunpack", 0, [=](cudaStream_t st) { launch_k(k_unpack_tap, nun, 256, 0, st, S, gw, Cout, ch, 0); return (int)cudaGetLastError(); }, 1, true);
+                } else
                 push(bwd_ops, "out_conv.2.bwd", 2.0 * fl, [=](cudaStream_t st) {
                     const float* de = self->deps_src;
                     launch_k(k_chansum_nchw, dim3(64, Cout), 256, 0, st, de, gb, Bn, Cout, Hn * Wn);
