@@ -1411,6 +1411,47 @@ __global__ void __launch_bounds__(256) k_out_gather(const float* __restrict__ T 
         for (int co = 0; co < CO; ++co) out[((b * CO + co) * H + y) * W + x] = acc[co];
     }
 }
+// ---- timestep-embedding projections on the tensor cores (unet.py:77,86: 22 x Linear(512 -> Cout) share one input):
+// the per-block fc weights are concatenated into Wcat [tp_ld][E] (bf16, K-major; padding rows zero), its transpose
+// WcatT [E][tp_ld] (for the data gradient) and bias_cat [tp_ld]; the weight gradient lands in a [tp_ld][E] scratch and is
+// scattered back to the per-block OIHW gradients.
+struct FcEnt { const float* w; const float* b; float* gw; int cout; int off; };
+// grid (E/32, maxc/32, nblocks), block (32, 8): 32x32 tiles through shared memory so both layouts are written coalesced
+__global__ void k_pack_fc(const FcEnt* __restrict__ tab, bf16* __restrict__ Wcat, bf16* __restrict__ WcatT, float* __restrict__ bias_cat, int E, int tp_ld) {
+    pdl_entry();
+    const FcEnt e = tab[blockIdx.z];
+    const int o0 = blockIdx.y * 32, e0 = blockIdx.x * 32;
+    if (o0 >= e.cout) return;
+    __shared__ float tile[32][33];
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int o = o0 + j;
+        const float v = (o < e.cout) ? e.w[(long long)o * E + e0 + threadIdx.x] : 0.f;
+        tile[j][threadIdx.x] = v;
+        if (o < e.cout) Wcat[(long long)(e.off + o) * E + e0 + threadIdx.x] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    if (WcatT)
+        for (int j = threadIdx.y; j < 32; j += 8) {
+            const int o = o0 + threadIdx.x;
+            if (o < e.cout) WcatT[(long long)(e0 + j) * tp_ld + e.off + o] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+        }
+    if (blockIdx.x == 0 && threadIdx.y == 0 && o0 + threadIdx.x < e.cout) bias_cat[e.off + o0 + threadIdx.x] = e.b[o0 + threadIdx.x];
+}
+// grid (ceil(maxc*E/4/256), nblocks): gw[o][e] = Sw[off + o][e]
+__global__ void k_scatter_fc_grad(const FcEnt* __restrict__ tab, const float4* __restrict__ Sw, int E) {
+    pdl_entry();
+    const FcEnt e = tab[blockIdx.y];
+    const long long n4 = (long long)e.cout * E / 4, i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) reinterpret_cast<float4*>(e.gw)[i] = Sw[(long long)e.off * E / 4 + i];
+}
+__global__ void k_cast_bf16(const float* __restrict__ x, bf16* __restrict__ y, long long n, int silu) {
+    pdl_entry();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (silu) v = v / (1.f + __expf(-v));
+        y[i] = __float2bfloat16_rn(v);
+    }
+}
 // rows 1..B-1 of a [B][row4] float4 matrix <- row 0
 __global__ void k_bcast_rows(float4* __restrict__ m, long long row4, long long tot4) {
     pdl_entry();

@@ -41,6 +41,7 @@ struct UnetEngine {
     std::vector<SgemmParams> tp_table_host; size_t tp_table_off = 0; int tp_max_c = 0;
     std::vector<SgemmParams> tp_uni_table_host; size_t tp_uni_table_off = 0;
     std::vector<Op> temb_uni_ops;          // one-row timestep path + broadcast (sampler: the whole batch shares t)
+    std::vector<FcEnt> fc_table_host; size_t fc_table_off = 0;   // tensor-core timestep projections (concatenated fc weights)
     bool uniform_t = false;                // set by ddpm_sampler_step around its forward
     std::vector<SgemmParams> tpw_table_host, tpd_table_host; size_t tpw_table_off = 0, tpd_table_off = 0;
     uint32_t layer_counter = 0;

@@ -238,7 +238,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
 inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     B = B_; H = H_; W = W_; train = train_; dry = dry_;
     cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); grads.clear(); once_list.clear();
-    tp_table_host.clear(); tp_uni_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
+    tp_table_host.clear(); tp_uni_table_host.clear(); fc_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
     layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0;
     const size_t zf_total = zf_cursor, zb_total = zb_cursor;   // sizes learned by the preceding dry pass
     zf_cursor = zb_cursor = 0;
@@ -273,6 +273,14 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     float* d_st = at<float>(zero_bwd((size_t)B * E * 4));
     tp_table_off = alloc(sizeof(SgemmParams) * nblocks); tpw_table_off = alloc(sizeof(SgemmParams) * nblocks); tpd_table_off = alloc(sizeof(SgemmParams) * nblocks);
     tp_uni_table_off = alloc(sizeof(SgemmParams) * nblocks);
+    // tensor-core projections need a power-of-two batch (plain-matrix TMA boxes) and, for the weight gradient, B % 64 == 0
+    static const bool no_tc_temb = getenv("DDPM_NO_TC_TEMB") != nullptr;
+    const bool tc_temb = !no_tc_temb && (B & (B - 1)) == 0 && B >= 64 && E % 64 == 0 && maxc % 32 == 0 && tp_ld % 64 == 0;
+    fc_table_off = alloc(sizeof(FcEnt) * nblocks);
+    bf16* Wcat = tc_temb ? at<bf16>(alloc_once_zero((size_t)tp_ld * E * 2)) : nullptr;
+    bf16* WcatT = (tc_temb && train) ? at<bf16>(alloc_once_zero((size_t)tp_ld * E * 2)) : nullptr;
+    float* bias_cat = tc_temb ? at<float>(alloc_once_zero((size_t)tp_ld * 4)) : nullptr;
+    bf16* A_f = tc_temb ? at<bf16>(alloc((size_t)B * E * 2)) : nullptr;
     const size_t temb_first = fwd_ops.size();
     {
         const int Bn = B;
@@ -287,6 +295,27 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         push(fwd_ops, "temb.fc1", 2.0 * B * E * E, [b, g0s](cudaStream_t st) { launch_k(k_sgemm<float, float, float>, g0s, 256, 0, st, b); return (int)cudaGetLastError(); });
         const SgemmParams* tab = at<SgemmParams>(tp_table_off);
         const dim3 g1((maxc + 63) / 64, (B + 63) / 64, nblocks * KS);
+        if (tc_temb) {
+            // ONE tcgen05 GEMM for all per-block projections: TP[B][tp_ld] = bf16(silu(e1)) x Wcat^T + bias_cat
+            const FcEnt* ftab = at<FcEnt>(fc_table_off);
+            const dim3 gp(E / 32, maxc / 32, nblocks);
+            bf16* WcatT_p = train ? WcatT : nullptr;
+            push(pack_ops, "temb.pack_fc", 0, [=](cudaStream_t st) { launch_k(k_pack_fc, gp, dim3(32, 8), 0, st, ftab, Wcat, WcatT_p, bias_cat, E, tp_ld); return (int)cudaGetLastError(); });
+            const long long nE = (long long)B * E;
+            push(fwd_ops, "temb.silu_cast", 0, [=](cudaStream_t st) { launch_k(k_cast_bf16, grid_for(nE), 256, 0, st, e1, A_f, nE, 1); return (int)cudaGetLastError(); });
+            ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+            d.mode = GEMM_KK; d.M = B; d.N = tp_ld; d.W = B; d.H = 1; d.NB = 1;
+            d.a_ptr[0] = A_f; d.a_C[0] = E; d.a_ld[0] = E;
+            d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 1; d.seg_kchunks[0] = E / 64; d.seg_cbase[0] = 0;
+            d.b_ptr = Wcat; d.b_K = E; d.b_rows = tp_ld; d.b_batch = 1; d.b_ld = E; d.b_bs = 0;
+            d.out = TP; d.ldo = tp_ld; d.alpha = 1.f; d.grid_z = 1; d.flags = EPI_OUT_F32; d.bias = bias_cat;
+            ++n_tc_gemms;
+            if (!dry) {
+                GemmLaunch g; const int rc = build_gemm(d, g);
+                if (rc) return rc;
+                push(fwd_ops, "temb.proj", 0, [g](cudaStream_t st) { return launch_gemm(g, st); });
+            } else push(fwd_ops, "temb.proj", 0, [](cudaStream_t) { return 0; });
+        } else
         push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { launch_k(k_sgemm_table, g1, 256, 0, st, tab, (int)KS); return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * E * ch + 2.0 * B * E * E;
         // Sampler steps feed ONE timestep to the whole batch (diffusion.py:166 `t.fill_(ti)`): the embedding MLP and the
@@ -313,6 +342,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         s.sa_m = E; s.sa_k = 1; s.sb_k = 1; s.sb_n = E; s.sc_m = tp_ld; s.sc_n = 1; s.alpha = 1.f; s.silu_a = 1;
         tp_table_host.push_back(s);
         { SgemmParams u = s; u.M = 1; tp_uni_table_host.push_back(u); }
+        { FcEnt f; f.w = PP(p + ".fc.weight"); f.b = PP(p + ".fc.bias"); f.gw = train ? GP(p + ".fc.weight") : nullptr; f.cout = cout; f.off = off; fc_table_host.push_back(f); }
         fwd_flops += 2.0 * B * cout * E;
         if (train) {
             // dW_fc[o][e] = sum_b silu(e1[b][e]) * dTP[b][off+o]   (computed as C'[e][o], stored transposed)
@@ -334,6 +364,39 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         tape.push_back([=]() {
             const SgemmParams* tw = at<SgemmParams>(tpw_table_off); const SgemmParams* td = at<SgemmParams>(tpd_table_off);
             const dim3 gw((maxc + 63) / 64, (E + 63) / 64, nblocks), gd((E + 63) / 64, (B + 63) / 64, nblocks);
+            if (tc_temb) {
+                // dTP -> bf16 once; dW_cat [tp_ld][E] = dTP^T x silu(e1) (MN-major GEMM) scattered to the 22 fc.weight grads;
+                // d_st [B][E] = dTP x Wcat (K-major GEMM over K = tp_ld, split-K atomics into the zeroed d_st)
+                bf16* dTPb = at<bf16>(alloc((size_t)B * tp_ld * 2));
+                float* Sw = at<float>(alloc((size_t)tp_ld * E * 4));
+                const long long nT = (long long)B * tp_ld;
+                const FcEnt* ftab = at<FcEnt>(fc_table_off);
+                push(bwd_ops, "temb.dtp_cast", 0, [=](cudaStream_t st) { launch_k(k_cast_bf16, grid_for(nT), 256, 0, st, dTP, dTPb, nT, 0); return (int)cudaGetLastError(); });
+                ddpm_gemm_desc w; memset(&w, 0, sizeof w);
+                w.mode = GEMM_MNMN; w.M = tp_ld; w.N = E; w.W = B; w.H = 1; w.NB = 1;
+                w.a_ptr[0] = dTPb; w.a_C[0] = tp_ld; w.a_ld[0] = tp_ld;
+                w.b_ptr = A_f; w.b_K = E; w.b_ld = E;
+                w.taps = 1; w.kblocks = B / 64; w.splits = 1; w.grid_z = 1;
+                w.flags = EPI_OUT_F32; w.alpha = 1.f; w.out = Sw; w.ldo = E;
+                ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+                d.mode = GEMM_KK; d.M = B; d.N = E; d.W = B; d.H = 1; d.NB = 1;
+                d.a_ptr[0] = dTPb; d.a_C[0] = tp_ld; d.a_ld[0] = tp_ld;
+                d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 1; d.seg_kchunks[0] = tp_ld / 64; d.seg_cbase[0] = 0;
+                d.b_ptr = WcatT; d.b_K = tp_ld; d.b_rows = E; d.b_batch = 1; d.b_ld = tp_ld; d.b_bs = 0;
+                const int n_t = (E + 255) / 256; int ks = 148 / n_t; if (ks > tp_ld / 64 / 4) ks = tp_ld / 64 / 4; if (ks > 32) ks = 32; if (ks < 1) ks = 1;
+                d.kk_splits = ks; d.grid_z = ks; d.out = d_st; d.ldo = E; d.alpha = 1.f; d.flags = EPI_OUT_F32 | EPI_ATOMIC;
+                n_tc_gemms += 2;
+                const dim3 gsc((unsigned)(((long long)maxc * E / 4 + 255) / 256), nblocks);
+                if (!dry) {
+                    GemmLaunch gwl, gdl; int rc = build_gemm(w, gwl); if (!rc) rc = build_gemm(d, gdl);
+                    if (rc) { plan_error = rc; return; }
+                    push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) {
+                        int r = launch_gemm(gwl, st); if (r) return r;
+                        launch_k(k_scatter_fc_grad, gsc, 256, 0, st, ftab, reinterpret_cast<const float4*>(Sw), E);
+                        r = launch_gemm(gdl, st); if (r) return r;
+                        return (int)cudaGetLastError(); }, 3);
+                } else push(bwd_ops, "temb.proj.bwd", 0, [](cudaStream_t) { return 0; }, 3);
+            } else
             push(bwd_ops, "temb.proj.bwd", 0, [=](cudaStream_t st) { launch_k(k_sgemm_table, gw, 256, 0, st, tw, 1); launch_k(k_sgemm_table, gd, 256, 0, st, td, 1); return (int)cudaGetLastError(); }, 2);
             float* d_e1 = at<float>(alloc((size_t)B * E * 4)); float* d_s0 = at<float>(zero_bwd((size_t)B * E * 4)); float* d_e0 = at<float>(alloc((size_t)B * E * 4));
             const long long nE = (long long)B * E; const int Bn = B;
@@ -574,6 +637,8 @@ inline int UnetEngine::build() {
     };
     int rc;
     if ((rc = up(tp_uni_table_off, tp_uni_table_host))) return rc;
+    if (!fc_table_host.empty() && cudaMemcpy(ws + fc_table_off, fc_table_host.data(), fc_table_host.size() * sizeof(FcEnt), cudaMemcpyHostToDevice))
+        return fail(-2, "fc table upload failed");
     if ((rc = up(tp_table_off, tp_table_host)) || (rc = up(tpw_table_off, tpw_table_host)) || (rc = up(tpd_table_off, tpd_table_host)))
         return fail(-2, "table upload failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (!pack_table_host.empty() && cudaMemcpy(ws + pack_table_off, pack_table_host.data(), pack_table_host.size() * sizeof(PackEntry), cudaMemcpyHostToDevice))

@@ -287,3 +287,40 @@ def test_sampler_split_batch_two_streams_matches_unsplit(golden):
     # halves must not be copies of each other (distinct images, distinct noise)
     assert (outs[(2, True)][:32] - outs[(2, True)][32:]).abs().mean().item() > 1e-2
     check_device_flag()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,B", [("tiny", 64), ("cifar10_bs4", 64)])
+def test_train_batch64_tensor_core_paths(golden, name, B):
+    """Batch-size-dependent plan choices that the bs=4 fixtures never reach: the tensor-core timestep projections (one GEMM for
+    the 22 fc layers + their MN-major weight gradient, power-of-two batch >= 64), one-wave split-K choices, GroupNorm grids.
+    Loss and every gradient tensor against the oracle on the same seeded inputs."""
+    import ddpm_torch_b200 as D
+    fx = golden(f"unet_{name}.pt")
+    cfg = fx["cfg"]
+    m, sd = build(cfg, fx["seed"], train=True)
+    diff = D.GaussianDiffusion(D.get_beta_schedule("linear", 1e-4, 0.02, 1000), "eps", "fixed-large", "mse")
+    g = torch.Generator(DEV).manual_seed(21)
+    H = fx["x0"].shape[-1]
+    x0 = torch.randn(B, 3, H, H, device=DEV, generator=g); t = torch.randint(1000, (B,), device=DEV, generator=g)
+    noise = torch.randn(B, 3, H, H, device=DEV, generator=g)
+    losses = diff.train_losses(m, x0, t, noise)
+    losses.mean().backward()
+    check_device_flag()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rd = R.RefDiffusion(R.get_beta_schedule("linear", 1e-4, 0.02, 1000), "fixed-large")
+    lref = rd.train_losses(lambda x, tt: R.unet_forward(sdg, cfg, x, tt), x0, t, noise)
+    lref.mean().backward()
+    lr = (losses - lref).abs().max().item() / lref.abs().max().item()
+    gm = torch.cat([p.grad.flatten() for p in m.parameters()])
+    gr = torch.cat([sdg[k].grad.flatten() for k, _ in m.named_parameters()])
+    worst = (1.0, "")
+    for k, p in m.named_parameters():
+        a, b = p.grad.flatten().double(), sdg[k].grad.flatten().double()
+        if b.norm() < 1e-6 * gr.norm():
+            continue
+        cos = (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+        if cos < worst[0]:
+            worst = (cos, k)
+    print(f"\n[{name} B={B}] loss rel err {lr:.3e}; flat grad rel-L2 {rel(gm, gr):.3e}; worst per-tensor cosine {worst[0]:.5f} ({worst[1]})")
+    assert lr < 2e-2 and rel(gm, gr) < 5e-2 and worst[0] > 0.995, worst
