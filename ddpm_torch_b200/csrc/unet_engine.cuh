@@ -192,8 +192,12 @@ struct UnetEngine {
             ++n_tc_gemms;
             // small-M problems (8x8 / 4x4 levels) do not fill 148 SMs with output tiles: split the K loop across CTAs
             // (fp32 atomics into a zeroed scratch) and finish bias / timestep vector / residual / bf16 in a tiny second kernel
-            const int bn = pick_block_n(c.Co);
-            const int tiles = (int)((Pout + 127) / 128) * ((c.Co + bn - 1) / bn);
+            int bn = pick_block_n(c.Co);
+            int tiles = (int)((Pout + 127) / 128) * ((c.Co + bn - 1) / bn);
+            // 8x8 levels: 64 tiles of 128x256 would need split-K (+ a finalize launch and fp32 atomics); 128 tiles of 128x128
+            // fill the machine in one wave with the same MMA time per CTA and no second pass
+            static const bool no_n128 = getenv("DDPM_NO_N128_FILL") != nullptr;
+            if (!no_n128 && bn == 256 && tiles <= 74 && tiles * 2 <= 148) { bn = 128; tiles *= 2; d.block_n = 128; }
             const int slabs = (int)(K / 64);
             int splits = 1;
             if (tiles <= 74 && slabs >= 16) { splits = 148 / tiles; if (splits > slabs / 8) splits = slabs / 8; if (splits > 16) splits = 16; if (splits < 1) splits = 1; }
