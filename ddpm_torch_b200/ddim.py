@@ -5,7 +5,7 @@ import math
 
 import torch
 
-from .diffusion import GaussianDiffusion
+from .diffusion import GaussianDiffusion, _coef_tables
 
 __all__ = ["get_selection_schedule", "DDIM"]
 
@@ -26,20 +26,7 @@ class DDIM(GaussianDiffusion):
         if eta2 != 1. and model_var_type != "fixed-small":
             self.model_var_type = "fixed-small"          # ddim.py:54-59: DDIM with eta<1 implies the small variance
         # re-derive every table on the sub-sequence (ddim.py:61-92)
-        one = torch.ones(1, dtype=torch.float64)
-        self.alphas_bar = self.alphas_bar[subsequence]
-        self.alphas_bar_prev = torch.cat([one, self.alphas_bar[:-1]], dim=0)
-        self.alphas = self.alphas_bar / self.alphas_bar_prev
-        self.betas = 1. - self.alphas
-        self.sqrt_alphas_bar_prev = self.alphas_bar_prev.sqrt()
-        self.sqrt_alphas_bar = self.alphas_bar.sqrt()
-        self.sqrt_one_minus_alphas_bar = (1. - self.alphas_bar).sqrt()
-        self.posterior_var = self.betas * (1. - self.alphas_bar_prev) / (1. - self.alphas_bar) * eta2
-        self.posterior_logvar_clipped = torch.log(torch.cat([self.posterior_var[[1]], self.posterior_var[1:]]).clip(min=1e-20))
-        self.sqrt_recip_alphas_bar = (1. / self.alphas_bar).sqrt()
-        self.sqrt_recip_m1_alphas_bar = (1. / self.alphas_bar - 1.).sqrt()
-        self.posterior_mean_coef2 = (1 - self.alphas_bar - eta2 * self.betas).sqrt() * (1 - self.alphas_bar_prev).sqrt() / (1. - self.alphas_bar)
-        self.posterior_mean_coef1 = self.sqrt_alphas_bar_prev * (1. - self.alphas.sqrt() * self.posterior_mean_coef2)
+        self.__dict__.update(_coef_tables(alphas_bar=self.alphas_bar[subsequence], eta2=eta2))
         self._set_fixed_var(clip=True)
         self.subsequence = torch.as_tensor(subsequence)
 

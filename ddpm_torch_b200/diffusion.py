@@ -56,6 +56,39 @@ def _flat_mean(x):
     return x.mean(dim=list(range(1, x.ndim)))
 
 
+def _coef_tables(betas=None, alphas_bar=None, eta2=None):
+    """All fp64 coefficient tables as a dict keyed by the reference's attribute names.
+
+    ``betas`` given: the full-chain tables of diffusion.py:52-67.  ``alphas_bar`` given (already restricted to a
+    sub-sequence) with ``eta2 = eta**2``: the DDIM re-derivation of ddim.py:61-92.  Every expression keeps the reference's
+    operand order, so the tables are bit-identical (tests/test_oracle_golden.py::test_mirror_tables_bit_exact)."""
+    T = {}
+    one = torch.ones(1, dtype=torch.float64)
+    if alphas_bar is None:
+        alphas = 1 - betas
+        ab = torch.cumprod(alphas, dim=0)
+        prev = torch.cat([one, ab[:-1]])
+    else:
+        ab = alphas_bar
+        prev = torch.cat([one, ab[:-1]], dim=0)
+        alphas = ab / prev
+        betas = 1. - alphas
+        T.update(betas=betas, alphas=alphas, alphas_bar_prev=prev, sqrt_alphas_bar_prev=prev.sqrt())
+    rest = 1. - ab                                     # 1 - alpha_bar_t
+    T.update(alphas_bar=ab, sqrt_alphas_bar=ab.sqrt(), sqrt_one_minus_alphas_bar=rest.sqrt(),
+             sqrt_recip_alphas_bar=(1. / ab).sqrt(), sqrt_recip_m1_alphas_bar=(1. / ab - 1.).sqrt())
+    if eta2 is None:
+        pv = betas * (1. - prev) / rest
+        T.update(posterior_var=pv, posterior_logvar_clipped=torch.log(torch.cat([pv[[1]], pv[1:]])),
+                 posterior_mean_coef1=betas * prev.sqrt() / rest, posterior_mean_coef2=alphas.sqrt() * (1. - prev) / rest)
+    else:
+        pv = betas * (1. - prev) / rest * eta2
+        c2 = (1 - ab - eta2 * betas).sqrt() * (1 - prev).sqrt() / rest
+        T.update(posterior_var=pv, posterior_logvar_clipped=torch.log(torch.cat([pv[[1]], pv[1:]]).clip(min=1e-20)),
+                 posterior_mean_coef2=c2, posterior_mean_coef1=prev.sqrt() * (1. - alphas.sqrt() * c2))
+    return T
+
+
 class GaussianDiffusion:
     def __init__(self, betas, model_mean_type, model_var_type, loss_type, **kwargs):
         assert isinstance(betas, torch.Tensor) and betas.dtype == torch.float64
@@ -63,17 +96,7 @@ class GaussianDiffusion:
         self.betas = betas
         self.model_mean_type, self.model_var_type, self.loss_type = model_mean_type, model_var_type, loss_type
         self.timesteps = len(betas)
-        alphas = 1 - betas
-        self.alphas_bar = torch.cumprod(alphas, dim=0)
-        ab_prev = torch.cat([torch.ones(1, dtype=torch.float64), self.alphas_bar[:-1]])
-        self.sqrt_alphas_bar = self.alphas_bar.sqrt()
-        self.sqrt_one_minus_alphas_bar = (1. - self.alphas_bar).sqrt()
-        self.sqrt_recip_alphas_bar = (1. / self.alphas_bar).sqrt()
-        self.sqrt_recip_m1_alphas_bar = (1. / self.alphas_bar - 1.).sqrt()
-        self.posterior_var = betas * (1. - ab_prev) / (1. - self.alphas_bar)
-        self.posterior_logvar_clipped = torch.log(torch.cat([self.posterior_var[[1]], self.posterior_var[1:]]))
-        self.posterior_mean_coef1 = betas * ab_prev.sqrt() / (1. - self.alphas_bar)
-        self.posterior_mean_coef2 = alphas.sqrt() * (1. - ab_prev) / (1. - self.alphas_bar)
+        self.__dict__.update(_coef_tables(betas))
         self._set_fixed_var(clip=False)
         self._dev_cache = {}
 

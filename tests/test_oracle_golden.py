@@ -52,6 +52,29 @@ def test_ddim_tables_bit_exact(golden, name, sched, S, eta):
         assert torch.equal(getattr(d, k), tabs[k]), k
 
 
+def test_mirror_tables_bit_exact(golden):
+    """The host mirror (ddpm_torch_b200.GaussianDiffusion / DDIM) derives the same fp64 tables as the unmodified reference."""
+    import ddpm_torch_b200 as D
+    tabs = golden("tables.pt")
+    betas = D.get_beta_schedule("linear", 1e-4, 0.02, 1000)
+    for vt in ("fixed-large", "fixed-small"):
+        d = D.GaussianDiffusion(betas, "eps", vt, "mse")
+        for k in TAB_KEYS:
+            assert torch.equal(getattr(d, k), tabs[vt][k]), (vt, k)
+    for name, sched, S, eta in (("ddim_lin50_eta0", "linear", 50, 0.0), ("ddim_quad50_eta0", "quadratic", 50, 0.0),
+                                ("ddim_lin100_eta0", "linear", 100, 0.0), ("ddim_lin10_eta1", "linear", 10, 1.0),
+                                ("ddim_lin20_eta05", "linear", 20, 0.5)):
+        sub = D.get_selection_schedule(sched, S, 1000)
+        assert torch.equal(sub, tabs[name]["subsequence"])
+        dd = D.DDIM.from_ddpm(D.GaussianDiffusion(betas, "eps", "fixed-small", "mse"), eta=eta, subsequence=sub)
+        assert dd.model_var_type == tabs[name]["model_var_type"]
+        # ddim.py:54-59: eta != 1 forces the small variance whatever the base object used
+        forced = D.DDIM.from_ddpm(D.GaussianDiffusion(betas, "eps", "fixed-large", "mse"), eta=eta, subsequence=sub)
+        assert forced.model_var_type == ("fixed-large" if eta == 1.0 else "fixed-small")
+        for k in TAB_KEYS:
+            assert torch.equal(getattr(dd, k), tabs[name][k]), (name, k)
+
+
 def test_selection_schedule_known_values():
     lin = R.get_selection_schedule("linear", 50, 1000)
     assert lin[:3].tolist() == [0, 20, 40] and lin[-1].item() == 980
