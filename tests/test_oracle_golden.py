@@ -171,3 +171,35 @@ def test_celebahq_forward(golden):
     with torch.no_grad():
         eps = R.unet_forward(sd, fx["cfg"], fx["x"], fx["t"])
     assert rel_l2(eps, fx["eps"].float()) < 1e-3   # golden stored as fp16
+
+
+@pytest.mark.parametrize("name", ["tiny"])
+def test_host_mirror_generic_path_matches_reference_goldens(golden, name):
+    """The host mirror handed a NON-native denoise_fn must behave exactly like the reference classes ("must fall
+    back to the generic PyTorch path"): q_sample / train_losses / p_sample_step / p_sample_progressive / DDIM loops on CPU
+    against the goldens written by the unmodified reference."""
+    import ddpm_torch_b200 as D
+    fx = golden(f"unet_{name}.pt")
+    cfg, seed, B = fx["cfg"], fx["seed"], fx["B"]
+    sd = R.make_state_dict(cfg, seed)
+    fn = lambda x, t: R.unet_forward(sd, cfg, x, t)
+    betas = D.get_beta_schedule("linear", 1e-4, 0.02, 1000)
+    assert torch.equal(betas, R.get_beta_schedule("linear", 1e-4, 0.02, 1000))
+    d = D.GaussianDiffusion(betas, "eps", "fixed-large", "mse")
+    assert torch.equal(d.q_sample(fx["x0"], fx["t"], fx["noise"]), fx["x_t"])
+    with torch.no_grad():
+        assert torch.allclose(d.train_losses(fn, fx["x0"], fx["t"], fx["noise"]), fx["losses"], rtol=1e-5, atol=1e-6)
+        for vt in ("fixed-large", "fixed-small"):
+            dv = D.GaussianDiffusion(betas, "eps", vt, "mse")
+            rv = R.RefDiffusion(betas, vt)
+            for tv in (0, 1, 500, 999):
+                tt = torch.full((B,), tv, dtype=torch.int64)
+                xs = dv.p_sample_step(fn, fx["x_t"], tt, generator=torch.Generator().manual_seed(3))
+                z = torch.empty_like(fx["x_t"]).normal_(generator=torch.Generator().manual_seed(3))
+                assert (xs - rv.p_sample_step(fn, fx["x_t"], tt, z)).abs().max().item() < 1e-5, (vt, tv)
+                assert (dv.p_sample_step(fn, fx["x_t"], tt, generator=torch.Generator().manual_seed(3)) - xs).abs().max().item() == 0
+        for nm, sched, S, eta in (("ddim5_lin", "linear", 5, 0.0), ("ddim5_quad", "quadratic", 5, 0.0), ("ddim4_eta1", "linear", 4, 1.0)):
+            sub = D.get_selection_schedule(sched, S, 1000)
+            dd = D.DDIM.from_ddpm(D.GaussianDiffusion(betas, "eps", "fixed-small", "mse"), eta=eta, subsequence=sub)
+            out = dd.p_sample(fn, shape=tuple(fx["noise"].shape), device=torch.device("cpu"), noise=fx["noise"], seed=4321)
+            assert (out - fx[nm]).abs().max().item() < 2e-4, nm
