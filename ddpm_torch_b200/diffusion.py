@@ -13,6 +13,8 @@ Any other ``denoise_fn`` (toy MLPs, wrappers) takes the generic formulas below, 
 """
 import ctypes as C
 
+import math
+
 import torch
 
 from . import _lib
@@ -233,11 +235,51 @@ class GaussianDiffusion:
             return _TrainLossFn.apply(self, model, denoise_fn, x_0.contiguous().float(), t.contiguous(), noise.contiguous().float(),
                                       *model._params)
         x_t = self.q_sample(x_0, t, noise=noise)
+        if self.loss_type == "kl":      # diffusion.py:226-228: weighted variational bound, generic torch path only
+            return self._loss_term_bpd(denoise_fn, x_0=x_0, x_t=x_t, t=t, clip_denoised=False, return_pred=False)
         if self.loss_type != "mse":
-            raise NotImplementedError("loss_type='kl' (bits-per-dim path) is outside the accelerated scope")
+            raise NotImplementedError(self.loss_type)
         assert self.model_var_type != "learned"
         target = {"mean": lambda: self.q_posterior_mean_var(x_0, x_t, t)[0], "x_0": lambda: x_0, "eps": lambda: noise}[self.model_mean_type]()
         return _flat_mean((target - denoise_fn(x_t, t)).pow(2))
+
+    # ------------------------------------------------------------------ log-likelihood in bits per dimension (generic torch)
+    def _loss_term_bpd(self, denoise_fn, x_0, x_t, t, clip_denoised, return_pred):
+        """diffusion.py:203-215: L_t = KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)) for t > 0, decoder NLL -log p(x_0|x_1) at t = 0."""
+        from .functions import discretized_gaussian_loglik, flat_mean, normal_kl
+        true_mean, _, true_logvar = self.q_posterior_mean_var(x_0=x_0, x_t=x_t, t=t)
+        model_mean, _, model_logvar, pred_x_0 = self.p_mean_var(denoise_fn, x_t=x_t, t=t, clip_denoised=clip_denoised, return_pred=True)
+        kl = flat_mean(normal_kl(true_mean, true_logvar, model_mean, model_logvar)) / math.log(2.)
+        nll = flat_mean(-discretized_gaussian_loglik(x_0, model_mean, log_scale=0.5 * model_logvar)) / math.log(2.)
+        out = torch.where(t.to(kl.device) > 0, kl, nll)
+        return (out, pred_x_0) if return_pred else out
+
+    def _prior_bpd(self, x_0):
+        """diffusion.py:245-250: KL(q(x_T|x_0) || N(0, I)) in bits per dimension."""
+        from .functions import flat_mean, normal_kl
+        B, T = len(x_0), self.timesteps
+        T_mean, _, T_logvar = self.q_mean_var(x_0=x_0, t=(T - 1) * torch.ones((B,), dtype=torch.int64))
+        zero = torch.zeros((), dtype=T_mean.dtype, device=T_mean.device)
+        return flat_mean(normal_kl(T_mean, T_logvar, zero, zero)) / math.log(2.)
+
+    def calc_all_bpd(self, denoise_fn, x_0, clip_denoised=True):
+        """diffusion.py:252-270.  Upstream unpacks ``B, T = x_0.shape, self.timesteps`` (B becomes the shape tuple and
+        ``torch.empty([B, ])`` raises); this is the evident intent, B = batch size.
+        Returns (total_bpd [B], losses [B, T], prior_bpd [B], mses [B, T])."""
+        from .functions import flat_mean
+        B, T = len(x_0), self.timesteps
+        t = torch.empty([B, ], dtype=torch.int64)
+        losses = torch.zeros([B, T], dtype=torch.float32)
+        mses = torch.zeros([B, T], dtype=torch.float32)
+        for ti in range(T - 1, -1, -1):
+            t.fill_(ti)
+            x_t = self.q_sample(x_0, t=t)
+            loss, pred_x_0 = self._loss_term_bpd(denoise_fn, x_0, x_t=x_t, t=t, clip_denoised=clip_denoised, return_pred=True)
+            losses[:, ti] = loss
+            mses[:, ti] = flat_mean((pred_x_0 - x_0).pow(2))
+        prior_bpd = self._prior_bpd(x_0)
+        total_bpd = torch.sum(losses, dim=1) + prior_bpd
+        return total_bpd, losses, prior_bpd, mses
 
     def _dev_tables(self, device):
         k = str(device)

@@ -441,3 +441,15 @@ SMALL64_CFG = dict(in_channels=3, hid_channels=64, out_channels=3, ch_multiplier
 def to_uint8_nhwc(x):
     """generate.py:129, verbatim: fp32 NCHW samples in [-1, 1] -> uint8 NHWC images."""
     return (x * 127.5 + 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+
+
+def toy_denoiser(C, out_mult, seed):
+    """A small deterministic NON-native denoise_fn (3x3 conv + timestep-dependent offset) shared by oracle/gen_golden.py and the
+    tests of the generic (bits-per-dim / learned-variance / x_0- and mean-prediction) paths; out_mult = 2 for "learned" variance."""
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn(out_mult * C, C, 3, 3, generator=g) * 0.2
+
+    def fn(x, t):
+        tb = torch.sin(t.to(torch.float32) * 0.37)[:, None, None, None]
+        return F.conv2d(x, W.to(x), padding=1) * 0.5 + 0.1 * tb
+    return fn

@@ -186,6 +186,7 @@ def main():
         print(f"unet_celebahq_bs1.pt done |eps|max={eps.abs().max():.4f}")
     gen_optim(out_dir)
     gen_checkpoint(out_dir)
+    gen_bpd(out_dir)
 
 
 def gen_optim(out_dir):
@@ -224,6 +225,32 @@ def gen_optim(out_dir):
     print("optim.pt written; norms", [round(n, 4) for n in fx["norms"]], "lrs", fx["lrs"])
 
 
+def gen_bpd(out_dir):
+    """Bits-per-dim path of the UNMODIFIED reference (diffusion.py:107-138,203-250) on a toy non-native denoiser: every
+    (model_mean_type, model_var_type) combination, loss terms at t = 0 / mid / T-1, the kl training loss, the prior term."""
+    ddpm_torch, _ = import_reference()
+    T = 20
+    betas = ddpm_torch.get_beta_schedule("linear", 1e-4, 0.02, T)
+    g = torch.Generator().manual_seed(31)
+    x0 = (torch.rand(4, 3, 8, 8, generator=g) * 2 - 1).mul(127.5).round().div(127.5)       # 8-bit data rescaled to [-1, 1]
+    noise = torch.randn(4, 3, 8, 8, generator=g)
+    t = torch.tensor([0, 1, 9, T - 1])
+    fx = dict(T=T, x0=x0, noise=noise, t=t, cases={})
+    for mt in ("eps", "x_0", "mean"):
+        for vt in ("fixed-small", "fixed-large"):      # "learned" cannot be constructed upstream (KeyError, diffusion.py:70-73)
+            fn = R.toy_denoiser(3, 1, seed=5)
+            d = ddpm_torch.GaussianDiffusion(betas=betas, model_mean_type=mt, model_var_type=vt, loss_type="kl")
+            x_t = d.q_sample(x0, t, noise=noise)
+            term, pred = d._loss_term_bpd(fn, x_0=x0, x_t=x_t, t=t, clip_denoised=True, return_pred=True)
+            mean, var, logvar = d.p_mean_var(fn, x_t, t, clip_denoised=False, return_pred=False)
+            fx["cases"][(mt, vt)] = dict(x_t=x_t, term=term, pred_x_0=pred, kl_loss=d.train_losses(fn, x0, t, noise=noise),
+                                         mean=mean, var=var.expand_as(mean).clone(), logvar=logvar.expand_as(mean).clone())
+            # (d._prior_bpd / d.calc_all_bpd raise upstream: the TorchScript-ed normal_kl rejects the float arguments of
+            #  diffusion.py:249 and calc_all_bpd unpacks the shape tuple into B, diffusion.py:253 - nothing to pin there)
+    torch.save(fx, os.path.join(out_dir, "bpd_toy.pt"))
+    print("bpd_toy.pt written;", {k: [round(float(v), 4) for v in c["term"]] for k, c in list(fx["cases"].items())[:2]})
+
+
 MICRO_CFG = dict(in_channels=3, hid_channels=32, out_channels=3, ch_multipliers=(1,), num_res_blocks=1, apply_attn=(False,), drop_rate=0.0)
 
 
@@ -258,6 +285,8 @@ def gen_checkpoint(out_dir):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bpd":
+        gen_bpd(os.path.join(ROOT, "tests", "golden")); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         gen_checkpoint(os.path.join(ROOT, "tests", "golden")); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "optim":
