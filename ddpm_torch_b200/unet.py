@@ -248,3 +248,21 @@ class _UNetFn(torch.autograd.Function):
         _lib.check(_lib.lib().ddpm_unet_backward(model._h, g.data_ptr(), _lib.stream_ptr()), "unet_backward")
         flat = model._grads.clone()
         return (None, None, None, *model.grad_views(flat))
+
+
+class ModelWrapper(nn.Module):
+    """utils/train.py:349-367: optional pre / post transforms around a model (the reference uses PixelUnshuffle / PixelShuffle
+    when ``block_size > 1``, train.py:70-73).  A wrapped model is a NON-native ``denoise_fn`` for the diffusion classes: the
+    loop and the loss run through the generic torch formulas while the inner ``UNet`` still executes on the engine."""
+
+    def __init__(self, model, pre_transform=None, post_transform=None):
+        super().__init__()
+        self._model = model
+        self.pre_transform = pre_transform
+        self.post_transform = post_transform
+
+    def forward(self, x, *args, **kwargs):
+        if self.pre_transform is not None:
+            x = self.pre_transform(x)
+        out = self._model(x, *args, **kwargs)
+        return out if self.post_transform is None else self.post_transform(out)

@@ -99,3 +99,24 @@ def test_learned_variance_generic_path():
     assert torch.isfinite(d.train_losses(fn, x0, t)).all()
     with pytest.raises(AssertionError):
         D.GaussianDiffusion(betas, "eps", "learned", "mse").train_losses(fn, x0, t)      # diffusion.py:230
+
+
+def test_model_wrapper_is_a_generic_denoise_fn():
+    """utils/train.py:349-367 / train.py:70-73: PixelUnshuffle -> model -> PixelShuffle; the diffusion classes treat the
+    wrapper as a non-native callable (generic torch path)."""
+    import ddpm_torch_b200 as D
+    inner_fn = R.toy_denoiser(12, 1, seed=8)
+
+    class Inner(torch.nn.Module):
+        def forward(self, x, t):
+            return inner_fn(x, t)
+    w = D.ModelWrapper(Inner(), torch.nn.PixelUnshuffle(2), torch.nn.PixelShuffle(2))
+    g = torch.Generator().manual_seed(4)
+    x0 = torch.rand(2, 3, 8, 8, generator=g) * 2 - 1
+    t = torch.tensor([3, 11]); noise = torch.randn(2, 3, 8, 8, generator=g)
+    ref = torch.nn.functional.pixel_shuffle(inner_fn(torch.nn.functional.pixel_unshuffle(x0, 2), t), 2)
+    assert torch.equal(w(x0, t), ref) and torch.equal(w(x0, t=t), ref)
+    d = D.GaussianDiffusion(D.get_beta_schedule("linear", 1e-4, 0.02, 20), "eps", "fixed-small", "mse")
+    rd = R.RefDiffusion(R.get_beta_schedule("linear", 1e-4, 0.02, 20), "fixed-small")
+    torch.testing.assert_close(d.train_losses(w, x0, t, noise), rd.train_losses(lambda x, tt: w(x, tt), x0, t, noise), rtol=1e-6, atol=1e-7)
+    assert D.ModelWrapper(Inner())(torch.nn.functional.pixel_unshuffle(x0, 2), t).shape == (2, 12, 4, 4)
