@@ -123,6 +123,9 @@ def runtime_check():
     check(lib().ddpm_runtime_check(), "runtime_check")
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Raw handle of torch's current stream ON ``device`` (default: the current device).  Engine calls of a model that
+    lives on cuda:N must be issued on cuda:N's stream under a ``torch.cuda.device(N)`` guard (generate.py:59 builds
+    ``cuda:{rank}`` models without ever calling set_device)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

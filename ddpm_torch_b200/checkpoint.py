@@ -74,8 +74,9 @@ def save_checkpoint(chkpt_path, model, optimizer=None, ema=None, **extra_info):
         chkpt.append(("optimizer", optimizer.state_dict()))
     if ema is not None:
         chkpt.append(("ema", ema.state_dict()))
-    if optimizer is not None and getattr(optimizer, "warmup", 0) > 0:
-        chkpt.append(("scheduler", scheduler_state(optimizer)))
+    # the reference ALWAYS writes the key (DummyScheduler.state_dict() is None without warm-up) and its loader indexes it
+    # unconditionally (utils/train.py:249-262, 264-276)
+    chkpt.append(("scheduler", scheduler_state(optimizer) if optimizer is not None and getattr(optimizer, "warmup", 0) > 0 else None))
     for k, v in extra_info.items():
         chkpt.append((k, v))
     if "epoch" in extra_info:

@@ -296,13 +296,19 @@ class _TrainLossFn(torch.autograd.Function):
     def forward(ctx, diffusion, model, wrapper, x0, t, noise, *params):
         B, _, H, W = x0.shape
         train = torch.is_grad_enabled() or any(p.requires_grad for p in params)
+        dev = model.flat_params.device
+        if x0.device != dev:
+            raise RuntimeError(f"UNet lives on {dev} but the batch is on {x0.device}")
         h = model.prepare(B, H, W, training=train)
-        ta, ts = diffusion._dev_tables(x0.device)
-        losses = torch.empty(B, dtype=torch.float32, device=x0.device)
+        ta, ts = diffusion._dev_tables(dev)
+        losses = torch.empty(B, dtype=torch.float32, device=dev)
         seed = model.next_dropout_seed() if (model.training and model.drop_rate > 0) else 0
-        _lib.check(_lib.lib().ddpm_train_forward(h, x0.data_ptr(), t.data_ptr(), noise.data_ptr(), ta.data_ptr(), ts.data_ptr(),
-                                                 losses.data_ptr(), seed, _lib.stream_ptr()), "train_forward")
+        t = t.to(device=dev, dtype=torch.int64)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddpm_train_forward(h, x0.data_ptr(), t.data_ptr(), noise.data_ptr(), ta.data_ptr(), ts.data_ptr(),
+                                                     losses.data_ptr(), seed, _lib.stream_ptr(dev)), "train_forward")
         ctx.model = model
+        ctx.wrapper = wrapper
         ctx.keep = (x0, t, noise)
         return losses
 
@@ -310,9 +316,29 @@ class _TrainLossFn(torch.autograd.Function):
     def backward(ctx, g):
         model = ctx.model
         g = g.contiguous().float()
-        _lib.check(_lib.lib().ddpm_train_backward(model._h, g.data_ptr(), _lib.stream_ptr()), "train_backward")
+        dev = model.flat_params.device
+        model._before_backward()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddpm_train_backward(model._h, g.data_ptr(), _lib.stream_ptr(dev)), "train_backward")
+        _ddp_allreduce(ctx.wrapper, model)
         flat = model._grads.clone()
         return (None, None, None, None, None, None, *model.grad_views(flat))
+
+
+def _ddp_allreduce(wrapper, model):
+    """The fused path calls the inner UNet directly, so a DistributedDataParallel wrapper's ``forward`` never runs and its
+    reducer stays disarmed (its autograd hooks return early) - the replicas would silently diverge under the reference flow
+    ``DDP(model)`` + ``diffusion.train_losses(self.model, ...)`` (train.py:110, utils/train.py:144-153).  The engine owns the
+    collective instead: ONE mean all-reduce of the flat gradient buffer over the wrapper's process group, issued here,
+    before autograd hands the views to ``p.grad``.  (If the reducer happens to be armed, averaging already-equal
+    gradients again is the identity.)"""
+    import torch.distributed as dist
+    if wrapper is model or not (dist.is_available() and dist.is_initialized()):
+        return
+    if not hasattr(wrapper, "process_group") and not hasattr(wrapper, "module"):
+        return
+    from .parallel import allreduce_mean_
+    allreduce_mean_(model._grads, group=getattr(wrapper, "process_group", None))
 
 
 def _native_sample_loop(diffusion, model, x, gen, rng, seed, use_graph, split=None):
@@ -332,7 +358,24 @@ def _native_sample_loop(diffusion, model, x, gen, rng, seed, use_graph, split=No
     if split not in (1, 2) or B % split:
         raise ValueError("sampler split must be 1 or 2 and divide the batch")
     Bh = B // split
-    hs = [model.prepare(Bh, H, W, training=False)] + [model.aux_plan(i, Bh, H, W) for i in range(1, split)]
+    dev = model.flat_params.device
+    if x.device != dev:
+        raise RuntimeError(f"UNet lives on {dev} but the sampler state is on {x.device}")
+    ctx_dev = torch.cuda.device(dev)
+    ctx_dev.__enter__()          # every launch below targets the model's device (generate.py:59 never calls set_device)
+    try:
+        return _native_sample_loop_on_device(diffusion, model, x, gen, rng, seed, use_graph, split, Bh, H, W, was_training)
+    finally:
+        ctx_dev.__exit__(None, None, None)
+        if was_training:
+            model.train()
+
+
+def _native_sample_loop_on_device(diffusion, model, x, gen, rng, seed, use_graph, split, Bh, H, W, was_training):
+    L = _lib.lib()
+    # weights are re-packed unconditionally at the head of every loop: the reference EMA swaps values with `p.data.copy_`
+    # (utils/train.py:307-316), which no version counter sees; 0.2 ms against a T-step loop
+    hs = [model.prepare(Bh, H, W, training=False, force_repack=True)] + [model.aux_plan(i, Bh, H, W, force=True) for i in range(1, split)]
     coef = diffusion._coef_rows()
     tmod = diffusion._model_timesteps().contiguous()
     S = coef.shape[0]
@@ -384,6 +427,4 @@ def _native_sample_loop(diffusion, model, x, gen, rng, seed, use_graph, split=No
             if z is not None:
                 z.normal_(generator=gen)
             step()
-    if was_training:
-        model.train()
     return x

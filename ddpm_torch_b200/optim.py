@@ -157,12 +157,16 @@ class FusedAdam:
                 self._state.data_ptr(), self.norm_out.data_ptr(), _lib.stream_ptr()), "opt_step")
         self.steps += 1
         m.repack()                       # packed bf16 weights are stale now
+        m.grads_consumed()               # the next backward starts a fresh accumulation
         return self.norm_out
 
     def zero_grad(self, set_to_none=True):
-        """The engine's backward overwrites the flat gradient buffer every step; only autograd's ``.grad`` views are dropped."""
+        """Drops autograd's ``.grad`` views and ends the current accumulation window of the flat gradient buffer (between
+        two ``zero_grad``/``step`` calls successive backward passes ADD UP in ``model.flat_grads``, like ``p.grad`` does
+        under the reference's ``--num-accum``)."""
         for p in self._model.parameters():
             p.grad = None
+        self._model.grads_consumed()
 
     # ---- torch.optim.Adam-compatible checkpoint layout
     def state_dict(self):

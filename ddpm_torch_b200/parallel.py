@@ -27,9 +27,9 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     world = dist.get_world_size(group)
     if world == 1:
         return flat
-    if flat.is_cuda:
+    if flat.is_cuda and dist.get_backend(group) == "nccl":
         dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
-    else:                                   # gloo has no AVG
+    else:                                   # gloo has no AVG (CPU tensors, or CUDA tensors over a gloo group)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.div_(world)
     return flat

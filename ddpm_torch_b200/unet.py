@@ -89,6 +89,10 @@ class UNet(nn.Module):
         self._packed_version = None
         self._packed_epoch = 0
         self._drop_calls = 0
+        self._acc = None                    # gradient-accumulation buffer (only exists when backward runs twice before a step)
+        self._acc_pending = False
+        self._bwd_since_zero = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.repack())
 
     def __del__(self):
         try:
@@ -129,14 +133,45 @@ class UNet(nn.Module):
 
     @property
     def flat_grads(self):
+        """Flat fp32 gradient buffer = SUM of the backward passes since the last ``zero_grad`` / optimizer step (the
+        reference accumulates in ``p.grad`` with ``--num-accum``, train.py / utils/train.py:152-165).  The engine's backward
+        overwrites its buffer, so earlier micro-batches are parked in ``_acc`` and folded back in here."""
+        if self._acc_pending:
+            self._grads.add_(self._acc)
+            self._acc_pending = False
         return self._grads
+
+    def _before_backward(self):
+        if self._bwd_since_zero > 0:        # a previous micro-batch's gradient is still unconsumed: park it
+            g = self.flat_grads
+            if self._acc is None or self._acc.device != g.device:
+                self._acc = torch.empty_like(g)
+            self._acc.copy_(g)
+            self._acc_pending = True
+        self._bwd_since_zero += 1
+
+    def grads_consumed(self):
+        """Called by ``FusedAdam.step`` / ``zero_grad``: the next backward starts a fresh accumulation."""
+        self._bwd_since_zero = 0
+        self._acc_pending = False
+
+    def zero_grad(self, set_to_none=True):
+        self.grads_consumed()
+        return super().zero_grad(set_to_none)
+
+    def _weights_version(self):
+        """Changes whenever a parameter was written through autograd-visible ops: optimizer steps, ``load_state_dict``,
+        ``p.copy_``.  After ``.cuda()`` the parameters no longer share the flat buffer's version counter (``p.data = view``),
+        so the per-parameter counters are summed.  ``p.data.copy_`` (the reference EMA swap, utils/train.py:307-316) bumps
+        NO counter: the sampler loops therefore re-pack unconditionally at their head (0.2 ms per loop)."""
+        return (self._flat._version, sum(p._version for p in self._params), self._packed_epoch)
 
     def grad_views(self, flat=None):
         flat = self._grads if flat is None else flat
         return [flat[off:off + math.prod(shape)].view(shape) for _, shape, off in self._meta]
 
     # ------------------------------------------------------------------ planning
-    def prepare(self, B, H, W, training):
+    def prepare(self, B, H, W, training, force_repack=False):
         """Compile (or reuse) the launch plan for this batch shape and (re)pack weights if they changed."""
         if not self._flat.is_cuda:
             raise RuntimeError("ddpm_torch_b200.UNet runs on sm_100a CUDA devices only (no CPU / PyTorch fallback); "
@@ -161,10 +196,10 @@ class UNet(nn.Module):
                                             self._ws.data_ptr(), self._ws.numel()), "unet_plan")
             self._plan_key = key
             self._packed_version = None
-        self.repack_if_needed(force=training)
+        self.repack_if_needed(force=training or force_repack)
         return self._h
 
-    def aux_plan(self, idx, B, H, W):
+    def aux_plan(self, idx, B, H, W, force=False):
         """Extra inference plan #idx over the same flat parameters with its own workspace (the sampler runs two half
         batches on two streams so that one half's HBM-bound GroupNorm kernels overlap the other's tensor-core kernels).
         Returns the handle; its packed weights are refreshed whenever the parameters changed."""
@@ -190,15 +225,17 @@ class UNet(nn.Module):
             with torch.cuda.device(self._flat.device):
                 _lib.check(L.ddpm_unet_plan(a["h"], B, H, W, 0, self._flat.data_ptr(), None, a["ws"].data_ptr(), a["ws"].numel()), "unet_plan")
             a["key"], a["ver"] = key, None
-        if a["ver"] != (self._flat._version, self._packed_epoch):
-            _lib.check(L.ddpm_unet_repack(a["h"], _lib.stream_ptr()), "unet_repack")
-            a["ver"] = (self._flat._version, self._packed_epoch)
+        if force or a["ver"] != self._weights_version():
+            with torch.cuda.device(self._flat.device):
+                _lib.check(L.ddpm_unet_repack(a["h"], _lib.stream_ptr(self._flat.device)), "unet_repack")
+            a["ver"] = self._weights_version()
         return a["h"]
 
     def repack_if_needed(self, force=False):
-        v = self._flat._version
+        v = self._weights_version()
         if force or v != self._packed_version:
-            _lib.check(_lib.lib().ddpm_unet_repack(self._h, _lib.stream_ptr()), "unet_repack")
+            with torch.cuda.device(self._flat.device):
+                _lib.check(_lib.lib().ddpm_unet_repack(self._h, _lib.stream_ptr(self._flat.device)), "unet_repack")
             self._packed_version = v
 
     def repack(self):
@@ -226,8 +263,12 @@ class UNet(nn.Module):
         h = self.prepare(B, H, W, training_plan)
         out = torch.empty(B, self.out_channels, H, W, dtype=torch.float32, device=x.device)
         seed = self.next_dropout_seed() if (self.training and self.drop_rate > 0) else 0
-        _lib.check(_lib.lib().ddpm_unet_forward(h, x.data_ptr(), t.data_ptr(), out.data_ptr(), seed, _lib.stream_ptr()),
-                   "unet_forward")
+        dev = self._flat.device
+        if x.device != dev or t.device != dev:
+            raise RuntimeError(f"UNet lives on {dev} but got x on {x.device}, t on {t.device}")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddpm_unet_forward(h, x.data_ptr(), t.data_ptr(), out.data_ptr(), seed, _lib.stream_ptr(dev)),
+                       "unet_forward")
         return out
 
 
@@ -245,7 +286,10 @@ class _UNetFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         model = ctx.model
         g = grad_out.contiguous().float()
-        _lib.check(_lib.lib().ddpm_unet_backward(model._h, g.data_ptr(), _lib.stream_ptr()), "unet_backward")
+        dev = model._flat.device
+        model._before_backward()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddpm_unet_backward(model._h, g.data_ptr(), _lib.stream_ptr(dev)), "unet_backward")
         flat = model._grads.clone()
         return (None, None, None, *model.grad_views(flat))
 

@@ -10,7 +10,6 @@ modules with ``load_state_dict(strict=True)`` (which also proves key/shape parit
 """
 import os
 import sys
-import types
 
 import torch
 
@@ -19,17 +18,10 @@ sys.path.insert(0, ROOT)
 from oracle import ddpm_ref as R  # noqa: E402
 
 
-def import_reference(path="/root/reference"):
-    """ddpm_torch/utils/__init__.py:1-2 imports matplotlib (absent) → stub it."""
-    if "matplotlib" not in sys.modules:
-        m = types.ModuleType("matplotlib"); m.rcParams = {}
-        p = types.ModuleType("matplotlib.pyplot"); m.pyplot = p
-        sys.modules["matplotlib"] = m; sys.modules["matplotlib.pyplot"] = p
-    if path not in sys.path:
-        sys.path.insert(0, path)
-    import ddpm_torch  # noqa
-    import ddim  # noqa
-    return ddpm_torch, ddim
+def import_reference():
+    """The unmodified reference, imported through oracle/ref_loader.py (matplotlib stub)."""
+    from oracle import ref_loader
+    return ref_loader.load()
 
 
 def build_ref_unet(ddpm_torch, cfg, seed):
