@@ -10,6 +10,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libddpm_b200.so")
 
 
+class GnEpi(C.Structure):
+    _fields_ = [("qstats", C.c_void_p), ("gnb_x0", C.c_void_p), ("gnb_x1", C.c_void_p), ("gnb_C0", C.c_int), ("gnb_C1", C.c_int),
+                ("gnb_K", C.c_void_p), ("gnb_gamma", C.c_void_p), ("gnb_beta", C.c_void_p), ("gnb_gs", C.c_void_p),
+                ("gnb_mask", C.c_void_p), ("gnb_keep_scale", C.c_float), ("gnb_silu", C.c_int)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("mode", C.c_int), ("block_n", C.c_int), ("M", C.c_int), ("N", C.c_int),
@@ -30,6 +36,7 @@ class GemmDesc(C.Structure):
         ("seg_custom", C.c_int * 3), ("seg_cmul", C.c_int * 3),
         ("seg_dx", (C.c_byte * 9) * 3), ("seg_dy", (C.c_byte * 9) * 3),
         ("o_mul", C.c_int), ("o_py", C.c_int), ("o_px", C.c_int), ("kk_splits", C.c_int),
+        ("gn", GnEpi),
     ]
 
 
@@ -41,6 +48,7 @@ class HaloDesc(C.Structure):
         ("w", C.c_void_p), ("ldw", C.c_longlong), ("Ktot", C.c_int),
         ("out", C.c_void_p), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int), ("residual", C.c_void_p),
         ("base_offset_mode", C.c_int), ("force_sub", C.c_int),
+        ("gn", GnEpi),
     ]
 
 

@@ -15,7 +15,7 @@ inline GemmSeg make_seg(int map, int taps, int kchunks, int c_base) {
 
 inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
     memset(&g, 0, sizeof g);
-    g.mode = d.mode; g.cluster = 1;
+    g.mode = d.mode;
     g.block_n = d.block_n ? d.block_n : pick_block_n(d.N);
     if (g.block_n != 64 && g.block_n != 128 && g.block_n != 256) return fail(-10, "block_n must be 64/128/256");
     if (d.N % 32) return fail(-10, "N=%d must be a multiple of 32", d.N);
@@ -59,11 +59,7 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
             if (!d.a_ptr[i]) { g.a[i] = g.a[0]; continue; }
             if ((rc = make_tmap_4d(&g.a[i], d.a_ptr[i], d.a_C[i], d.W * aes, d.H * aes, d.NB, d.a_ld[i], 64, p.w_t, p.h_t, p.n_t, aes))) return rc;
         }
-        // thread-block clusters of CTAs with consecutive m_tiles share (multicast) the weight tile
-        g.cluster = 1;
-        for (int cl = gemm_max_cluster(); cl > 1; cl >>= 1)
-            if (m_tiles % cl == 0 && (g.block_n / cl) % 8 == 0 && m_tiles * n_tiles * gz >= 2 * cl) { g.cluster = cl; break; }
-        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n / g.cluster))) return rc;
+        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n))) return rc;
         g.flops = 2.0 * d.M * d.N * 64.0 * slabs * gz;
     } else if (d.mode == GEMM_MNMN) {
         if (!pick_box(d.W, d.H, 64, p.wk_t, p.hk_t, p.nk_t)) return fail(-11, "MNMN: unsupported geometry W=%d H=%d", d.W, d.H);
@@ -81,6 +77,13 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
         g.flops = 2.0 * d.M * d.N * 64.0 * d.kblocks * gz;
     } else {
         return fail(-10, "unknown gemm mode %d", d.mode);
+    }
+    p.gn = gn_epi_from_abi(d.gn); p.gn_hw = d.W * d.H;
+    if (p.gn.qstats || p.gn.K) {
+        if (d.mode != GEMM_KK || p.o_mul != 1 || p.kk_splits > 1 || gz != 1 || (d.flags & (EPI_OUT_F32 | EPI_ATOMIC)) || (p.gn_hw % 32) || (d.M % 32))
+            return fail(-10, "GroupNorm epilogue fusion needs a plain bf16 KK conv over NHWC pixels with H*W %% 32 == 0");
+        if (p.gn.K && (p.gn.C0 + p.gn.C1 != d.N || p.gn.C0 % 32 || p.gn.C1 % 32 || !p.gn.gs || !p.gn.x0 || !p.gn.gamma || !p.gn.beta))
+            return fail(-10, "bad GroupNorm-backward epilogue description");
     }
     // TMA-store epilogue: plain bf16 outputs with identity row mapping (everything but fp32 / atomic / scattered-row outputs)
     g.o = g.b; p.tma_store = 0;

@@ -85,20 +85,12 @@ struct GemmLaunch {
     GemmParams p;
     dim3 grid;
     int mode, block_n;
-    int cluster;            // 1, 2 or 4 (KK with m_tiles % cluster == 0): the B map's box holds block_n / cluster rows
     double flops;
 };
-// multicast clusters measured no faster than unicast on B200 (L2 traffic is not the limiter) -> default off
-inline int gemm_max_cluster() { static const int v = getenv("DDPM_GEMM_CLUSTER") ? atoi(getenv("DDPM_GEMM_CLUSTER")) : 1; return v; }
-
-// Pipeline depth: "deep" = one CTA per SM with 4-8 stages; "shallow" (DDPM_GEMM_SHALLOW=1) = 2-4 stages so that two
-// CTAs are co-resident per SM and one's epilogue overlaps the other's main loop (A/B experiment knob).
-inline bool gemm_shallow() { static const bool v = getenv("DDPM_GEMM_SHALLOW") != nullptr; return v; }
-
-template <int BLOCK_N, int MODE, int STAGES, int CLUSTER, int KSTEPS>
-inline int launch_gemm_inst3(const GemmLaunch& g, cudaStream_t st) {
+template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
+inline int launch_gemm_inst2(const GemmLaunch& g, cudaStream_t st) {
     using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
-    auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES, CLUSTER, KSTEPS>;
+    auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES, KSTEPS>;
     static bool attr_done = false;
     if (!attr_done) {
         DDPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
@@ -110,35 +102,16 @@ inline int launch_gemm_inst3(const GemmLaunch& g, cudaStream_t st) {
     const int per_sm = (SM::TOTAL <= 110 * 1024 && 4 * BLOCK_N <= 512) ? 2 : 1;
     if (SM::TOTAL > 232448) return fail(-6, "gemm variant needs %d B of shared memory (> 227 KB)", SM::TOTAL);
     int ctas = (int)g.grid.x; if (ctas > num_sms * per_sm) ctas = num_sms * per_sm;
-    if (CLUSTER > 1) {
-        ctas = ctas / CLUSTER * CLUSTER;
-        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(gemm_threads(MODE)); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
-        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        DDPM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.a[0], g.a[1], g.a[2], g.b, g.o, g.p));
-        return 0;
-    }
     launch_k(kern, ctas, gemm_threads(MODE), SM::TOTAL, st, g.a[0], g.a[1], g.a[2], g.b, g.o, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
-}
-template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
-inline int launch_gemm_inst2(const GemmLaunch& g, cudaStream_t st) {
-    if (MODE == GEMM_KK) {
-        if (g.cluster == 4) return launch_gemm_inst3<BLOCK_N, GEMM_KK, STAGES, 4, KSTEPS>(g, st);
-        if (g.cluster == 2) return launch_gemm_inst3<BLOCK_N, GEMM_KK, STAGES, 2, KSTEPS>(g, st);
-    }
-    return launch_gemm_inst3<BLOCK_N, MODE, STAGES, 1, KSTEPS>(g, st);
 }
 template <int BLOCK_N, int MODE>
 inline int launch_gemm_inst(const GemmLaunch& g, cudaStream_t st) {
     // One persistent CTA per SM, ~192 KB of stages; TMEM double buffering overlaps the epilogue.
     //   N=256: 4 stages x 1 slab (48 KB);  N=128: 3 stages x 2 slabs (64 KB);  N=64: 4 stages x 2 slabs (48 KB)
-    // DDPM_GEMM_SHALLOW=1 selects the one-slab-per-stage variants for N<=128 (A/B experiment knob).
-    if (BLOCK_N == 256) return launch_gemm_inst2<BLOCK_N, MODE, 4, 1>(g, st);
-    if (gemm_shallow()) return launch_gemm_inst2<BLOCK_N, MODE, (BLOCK_N == 128 ? 6 : 8), 1>(g, st);
-    return launch_gemm_inst2<BLOCK_N, MODE, (BLOCK_N == 128 ? 3 : 4), 2>(g, st);
+    if constexpr (BLOCK_N == 256) return launch_gemm_inst2<BLOCK_N, MODE, 4, 1>(g, st);
+    else return launch_gemm_inst2<BLOCK_N, MODE, (BLOCK_N == 128 ? 3 : 4), 2>(g, st);
 }
 
 inline int launch_gemm(const GemmLaunch& g, cudaStream_t st) {

@@ -256,23 +256,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_stats(GnSrc s, double* __restrict
     }
 }
 
-// ---- GroupNorm v4: per-(image, channel) constants are materialised once by tiny "finalize" kernels, so the bandwidth-bound
-// passes start with a handful of independent 16-byte loads (no shared memory, no dependent load chains, few registers).
 // K[b][0..3][C] = { sc = rstd*gamma, sh = beta - mean*sc, r = rstd, mr = mean*rstd }   ->  y = x*sc + sh ; xh = x*r - mr
-__global__ void k_gn_finalize(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                              float* __restrict__ K, int B, int C, double inv_n, float eps) {
-    pdl_entry();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * C) return;
-    const int b = i / C, c = i % C, g = c / (C >> 5);
-    const double m = stats[(b * 32 + g) * 2] * inv_n;
-    double var = stats[(b * 32 + g) * 2 + 1] * inv_n - m * m;
-    if (var < 0) var = 0;
-    const float r = (float)(1.0 / sqrt(var + (double)eps)), mf = (float)m;
-    const float sc = r * gamma[c];
-    float* Kb = K + (long long)b * 4 * C;
-    Kb[c] = sc; Kb[C + c] = beta[c] - mf * sc; Kb[2 * C + c] = r; Kb[3 * C + c] = mf * r;
-}
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -283,7 +267,25 @@ struct GnApply {
     GnSrc s; const float* K; bf16* y;
     int HW; int silu; float drop_p; unsigned long long seed; uint32_t layer;
     unsigned char* mask;          // [B*HW*C/8] keep bits of the dropout (written when drop_p > 0 and mask != null; read by the backward)
+    // statistics delivered by the PRODUCERS of the two sources (conv epilogues, gn_epilogue.cuh): per (image, 4-channel quad)
+    // {sum, sum of squares} in fp64, [B][C0/4][2] and [B][C1/4][2].  When qs0 != null the per-channel constants are derived here
+    // (every block redoes the few loads of its image - cheaper than a launch) and block 0 of the image publishes them in Kout.
+    const double* qs0; const double* qs1; const float* gamma; const float* beta; float eps; float* Kout;
 };
+// mean / rstd of the group that holds concat-channel ch, from the producers' quad statistics
+__device__ __forceinline__ void gn_group_from_quads(const GnApply& a, int b, int ch, int cg, float& mean, float& rstd) {
+    const int q0 = (ch / cg) * (cg >> 2), nq = cg >> 2, Q0 = a.s.C0 >> 2, Q1 = a.s.C1 >> 2;
+    double S = 0.0, SS = 0.0;
+    for (int q = q0; q < q0 + nq; ++q) {
+        const double* p = q < Q0 ? a.qs0 + ((long long)b * Q0 + q) * 2 : a.qs1 + ((long long)b * Q1 + (q - Q0)) * 2;
+        S += p[0]; SS += p[1];
+    }
+    const double inv_n = 1.0 / ((double)a.HW * cg);
+    const double m = S * inv_n;
+    double var = SS * inv_n - m * m;
+    if (var < 0) var = 0;
+    mean = (float)m; rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+}
 __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_per_block) {
     pdl_entry();
     const int C = a.s.C0 + a.s.C1, oct = C >> 3;
@@ -294,7 +296,22 @@ __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_pe
     const int c = o * 8;
     const bool first = c < a.s.C0;
     float sc[8], sh[8];
-    ld8(a.K + (long long)b * 4 * C + c, sc); ld8(a.K + (long long)b * 4 * C + C + c, sh);
+    if (a.qs0) {
+        const int cg = C >> 5;                      // multiple of 4: the thread's 8 channels lie in at most two groups
+        float ga[8], be[8], r[2], m[2];
+        ld8(a.gamma + c, ga); ld8(a.beta + c, be);
+        gn_group_from_quads(a, b, c, cg, m[0], r[0]);
+        if ((c + 4) / cg != c / cg) gn_group_from_quads(a, b, c + 4, cg, m[1], r[1]); else { m[1] = m[0]; r[1] = r[0]; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[e] = r[e >> 2] * ga[e]; sh[e] = be[e] - m[e >> 2] * sc[e]; }
+        if (a.Kout && blockIdx.x == 0 && lp == 0) {
+            float* Kb = a.Kout + (long long)b * 4 * C + c;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { Kb[e] = sc[e]; Kb[C + e] = sh[e]; Kb[2 * C + e] = r[e >> 2]; Kb[3 * C + e] = m[e >> 2] * r[e >> 2]; }
+        }
+    } else {
+        ld8(a.K + (long long)b * 4 * C + c, sc); ld8(a.K + (long long)b * 4 * C + C + c, sh);
+    }
     const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
     const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
     const int sstride = first ? a.s.C0 : a.s.C1;
@@ -339,6 +356,10 @@ struct GnBwd {
     const unsigned char* mask;    // keep bits saved by the forward pass (drop_p > 0)
     int* ticket;                  // [B] arrival counters (zeroed per pass): the last reduce block of an image runs the finalize
     int dn_inplace;               // reduce pass overwrites dy with dn = mask*dy*silu'(y); apply pass reads it back as-is
+    int fin_in_apply;             // the data-gradient conv's epilogue already stored dn and filled gs (gn_epilogue.cuh): there is
+                                  // no reduce pass; the apply pass folds the quad terms into P, Q in its prologue and
+                                  // accumulates dgamma / dbeta (per-channel sums of dn*xh / dn) on the fly
+    const float* gs;              // [B][C/4][2] {sum gamma*dn, sum gamma*dn*xh} per (image, quad)
 };
 __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {
     pdl_entry();   // grid (pixel blocks, B), blockDim.x = (256/oct)*oct
@@ -421,31 +442,6 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {
         PQb[ch] = k3 * r; PQb[C + ch] = k2 - k3 * mr;
     }
 }
-// one block per image
-__global__ void __launch_bounds__(256) k_gn_bwd_finalize(const GnBwd a) {
-    pdl_entry();
-    const int C = a.s.C0 + a.s.C1, cg = C >> 5;
-    __shared__ float S[64];
-    const int b = blockIdx.x;
-    if (threadIdx.x < 64) S[threadIdx.x] = 0.f;
-    __syncthreads();
-    const float* csb = a.cs + (long long)b * 2 * C;
-    const float* Kb = a.K + (long long)b * 4 * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float g = __ldg(a.gamma + c), c0 = csb[c];
-        const float c1 = Kb[2 * C + c] * csb[C + c] - Kb[3 * C + c] * c0;       // sum dn*xh = r*sum(dn*x) - (m*r)*sum(dn)
-        atomicAdd(&S[(c / cg) * 2], g * c0); atomicAdd(&S[(c / cg) * 2 + 1], g * c1);
-        atomicAdd(a.dbeta + c, c0); atomicAdd(a.dgamma + c, c1);
-    }
-    __syncthreads();
-    const float inv_n = 1.f / ((float)a.HW * (float)cg);
-    float* PQb = a.PQ + (long long)b * 2 * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float r = Kb[2 * C + c], mr = Kb[3 * C + c];
-        const float k2 = r * S[(c / cg) * 2] * inv_n, k3 = r * S[(c / cg) * 2 + 1] * inv_n;   // dx = sc*dn - k2 - k3*xh
-        PQb[c] = k3 * r; PQb[C + c] = k2 - k3 * mr;
-    }
-}
 // grid (pixel blocks, B), blockDim.x = (256/oct)*oct.  Optionally accumulates per-image / total column sums of dx.
 template <bool do_cs>
 __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* cs_per_img, int cs_ld, float* cs_total, float* cs_total2) {
@@ -463,7 +459,29 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
     const float* Kb = a.K + (long long)b * 4 * C + c;
     const float* PQb = a.PQ + (long long)b * 2 * C + c;
     float sc[8], sh[8], P[8], Q[8];
-    ld8(Kb, sc); ld8(Kb + C, sh); ld8(PQb, P); ld8(PQb + C, Q);
+    ld8(Kb, sc); ld8(Kb + C, sh);
+    float rr[2] = {0.f, 0.f}, mr[2] = {0.f, 0.f};
+    if (a.fin_in_apply) {
+        // S1[g] = sum_{c in g} gamma*dn, S2[g] = sum gamma*dn*xh: whole quads of the dgrad epilogue's gs (C % 128 == 0)
+        const int cg = C >> 5, nq = cg >> 2;
+        const float* gsb = a.gs + (long long)b * (C >> 2) * 2;
+        const float* Kall = a.K + (long long)b * 4 * C;
+        const float inv_n = 1.f / ((float)a.HW * (float)cg);
+        float k2[2], k3[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ch0 = c + 4 * h, g = ch0 / cg;
+            if (h == 1 && c / cg == g) { k2[1] = k2[0]; k3[1] = k3[0]; rr[1] = rr[0]; mr[1] = mr[0]; continue; }
+            const float r = Kall[2 * C + ch0], m_r = Kall[3 * C + ch0];
+            float S1 = 0.f, S2 = 0.f;
+            for (int qd = g * nq; qd < (g + 1) * nq; ++qd) { S1 += gsb[2 * qd]; S2 += gsb[2 * qd + 1]; }
+            k2[h] = r * S1 * inv_n; k3[h] = r * S2 * inv_n; rr[h] = r; mr[h] = m_r;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { P[e] = k3[e >> 2] * rr[e >> 2]; Q[e] = k2[e >> 2] - k3[e >> 2] * mr[e >> 2]; }
+    } else {
+        ld8(PQb, P); ld8(PQb + C, Q);
+    }
     const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
     const int sstride = first ? a.s.C0 : a.s.C1;
     bf16* dst = first ? a.dx0 + (long long)b * a.HW * a.s.C0 + c : a.dx1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
@@ -472,6 +490,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
     const bf16* adp = a.addend ? a.addend + (long long)b * a.HW * C + c : nullptr;
     const unsigned char* mk = (a.drop_p > 0.f) ? a.mask + (long long)b * a.HW * oct + o : nullptr;
     float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float sdb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sdg[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // per-channel sums of dn and dn*xh (dbeta, dgamma)
     for (int pp = p0 + lp; pp < p1; pp += 2 * pstep) {
         uint4 ux[2], ud[2], ua[2], uo[2]; uint32_t kp[2] = {0xffu, 0xffu};
 #pragma unroll
@@ -504,6 +523,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
                 if (adp) v += ad[e];
                 if (acc) v += ov[e];
                 ov[e] = v; if (do_cs) cs[e] += v;
+                if (a.fin_in_apply) { sdb[e] += dn; sdg[e] = fmaf(dn, fmaf(x[e], rr[e >> 2], -mr[e >> 2]), sdg[e]); }
             }
             *reinterpret_cast<uint4*>(dst + (long long)q * sstride) = pack8(ov);
         }
@@ -520,229 +540,15 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
             if (cs_total2) atomicAdd(cs_total2 + i, v);
         }
     }
-}
-
-// ---- fused GroupNorm passes: one thread-block CLUSTER per image.  Each CTA stages its pixel range of the image in shared
-// memory (one HBM read), the per-group / per-channel partial sums are exchanged between the CTAs of the cluster through
-// distributed shared memory, and the normalisation / gradient is then applied straight from shared memory.  Replaces
-// {stats, finalize, apply} (2 reads + 1 write, 3 launches) by 1 read + 1 write in 1 launch, and in the backward
-// {reduce, finalize, apply} (x and dy read twice) by one read of each.  Used when an image's tile(s) fit in <= 8 CTAs.
-__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
-    uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr)), ra; float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-    return v;
-}
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-
-// grid (CL, B), cluster (CL,1,1), blockDim.x = 512-ish multiple of oct.  dynamic smem: [ppc][C] bf16 tile + [64] floats
-__global__ void __launch_bounds__(512, 1) k_gn_fused_fwd(const GnApply a, float* __restrict__ Kout, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, int ppc, float eps) {
-    pdl_entry();
-    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
-    extern __shared__ __align__(16) unsigned char smraw[];
-    float* part = reinterpret_cast<float*>(smraw);                 // [32][2] this CTA's group partials
-    float* gstat = part + 64;                                      // [32][2] mean, rstd (after the cluster reduction)
-    uint4* tile = reinterpret_cast<uint4*>(smraw + 512);           // [ppc][oct] 16-byte octets
-    const int b = blockIdx.y;
-    const uint32_t rank = cluster_rank(), CL = cluster_size();
-    const int p0 = rank * ppc;
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) part[i] = 0.f;
-    __syncthreads();
-    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
-    const int c = o * 8;
-    const bool first = c < a.s.C0;
-    const bf16* src = first ? a.s.x0 + ((long long)b * a.HW + p0) * a.s.C0 + c : a.s.x1 + ((long long)b * a.HW + p0) * a.s.C1 + (c - a.s.C0);
-    const int sstride = first ? a.s.C0 : a.s.C1;
-    float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int pp = lp; pp < ppc; pp += 4 * pstep) {
-        uint4 u[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const int q = pp + k * pstep; u[k] = q < ppc ? __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)) : make_uint4(0, 0, 0, 0); }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int q = pp + k * pstep;
-            if (q >= ppc) break;
-            tile[(long long)q * oct + o] = u[k];
-            float f[8];
-            unpack8(u[k], f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] = fmaf(f[e], f[e], sq[e]); }
-        }
-    }
-    {
-        int gcur = c / cg; float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int g = (c + e) / cg;
-            if (g != gcur) { atomicAdd(&part[gcur * 2], a1); atomicAdd(&part[gcur * 2 + 1], a2); a1 = a2 = 0.f; gcur = g; }
-            a1 += su[e]; a2 += sq[e];
-        }
-        atomicAdd(&part[gcur * 2], a1); atomicAdd(&part[gcur * 2 + 1], a2);
-    }
-    __syncthreads();
-    cluster_barrier();                                             // every CTA's partials are complete and visible
-    if (threadIdx.x < 32) {
-        double s = 0.0, q2 = 0.0;
-        for (uint32_t r = 0; r < CL; ++r) { s += (double)ld_dsmem_f32(&part[threadIdx.x * 2], r); q2 += (double)ld_dsmem_f32(&part[threadIdx.x * 2 + 1], r); }
-        const double inv_n = 1.0 / ((double)a.HW * cg);
-        const double m = s * inv_n; double var = q2 * inv_n - m * m; if (var < 0) var = 0;
-        gstat[threadIdx.x * 2] = (float)m; gstat[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    cluster_barrier();                                             // peers have finished reading this CTA's partials
-    float sc[8], sh[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int g = (c + e) / cg;
-        const float m = gstat[g * 2], r = gstat[g * 2 + 1];
-        sc[e] = r * __ldg(gamma + c + e); sh[e] = __ldg(beta + c + e) - m * sc[e];
-        if (Kout && rank == 0 && lp == 0) {
-            float* Kb = Kout + (long long)b * 4 * C;
-            Kb[c + e] = sc[e]; Kb[C + c + e] = sh[e]; Kb[2 * C + c + e] = r; Kb[3 * C + c + e] = m * r;
-        }
-    }
-    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    bf16* dst = a.y + ((long long)b * a.HW + p0) * C + c;
-    for (int q = lp; q < ppc; q += pstep) {
-        float f[8];
-        unpack8(tile[(long long)q * oct + o], f);
-        uint32_t keep = 0xffu;
-        if (a.drop_p > 0.f) {
-            keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + p0 + q) * oct + o) * 8, a.drop_p);
-            if (a.mask) a.mask[((long long)b * a.HW + p0 + q) * oct + o] = (unsigned char)keep;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float y = fmaf(f[e], sc[e], sh[e]);
-            if (a.silu) y *= sigmoid_fast(y);
-            f[e] = ((keep >> e) & 1u) ? y * keep_scale : 0.f;
-        }
-        *reinterpret_cast<uint4*>(dst + (long long)q * C) = pack8(f);
-    }
-}
-
-// backward twin: smem tiles of x and dy; per-channel sums exchanged through DSMEM; dynamic smem:
-// [2][C] floats partial + [2][C] floats P,Q + 2 x [ppc][oct] uint4
-template <bool do_cs>
-__global__ void __launch_bounds__(512, 1) k_gn_fused_bwd(const GnBwd a, int ppc, float* cs_per_img, int cs_ld, float* cs_total, float* cs_total2) {
-    pdl_entry();
-    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
-    extern __shared__ __align__(16) unsigned char smraw[];
-    float* part = reinterpret_cast<float*>(smraw);                 // [2][C]: sum dn, sum dn*x  (this CTA)
-    float* pq = part + 2 * C;                                      // [2][C]: P, Q
-    float* shc = pq + 2 * C;                                       // [C] column sums of dx (optional)
-    float* S = shc + C;                                            // [64] group sums
-    uint4* tx = reinterpret_cast<uint4*>(smraw + (((size_t)(5 * C + 64) * 4 + 15) / 16) * 16);
-    uint4* td = tx + (size_t)ppc * oct;
-    const int b = blockIdx.y;
-    const uint32_t rank = cluster_rank(), CL = cluster_size();
-    const int p0 = rank * ppc;
-    for (int i = threadIdx.x; i < 5 * C + 64; i += blockDim.x) part[i] = 0.f;
-    __syncthreads();
-    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
-    const int c = o * 8;
-    const bool first = c < a.s.C0;
-    const float* Kb = a.K + (long long)b * 4 * C + c;
-    float sc[8], sh[8];
-    ld8(Kb, sc); ld8(Kb + C, sh);
-    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    const bf16* src = first ? a.s.x0 + ((long long)b * a.HW + p0) * a.s.C0 + c : a.s.x1 + ((long long)b * a.HW + p0) * a.s.C1 + (c - a.s.C0);
-    const int sstride = first ? a.s.C0 : a.s.C1;
-    const bf16* dyp = a.dy + ((long long)b * a.HW + p0) * C + c;
-    const unsigned char* mk = (a.drop_p > 0.f) ? a.mask + ((long long)b * a.HW + p0) * oct + o : nullptr;
-    float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int pp = lp; pp < ppc; pp += 2 * pstep) {
-        uint4 ux[2], ud[2]; uint32_t kp[2] = {0xffu, 0xffu};
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int q = pp + k * pstep;
-            if (q < ppc) {
-                ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)); ud[k] = __ldg(reinterpret_cast<const uint4*>(dyp + (long long)q * C));
-                if (mk && !a.dn_inplace) kp[k] = mk[(long long)q * oct];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int q = pp + k * pstep;
-            if (q >= ppc) break;
-            float x[8], d[8];
-            unpack8(ux[k], x); unpack8(ud[k], d);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float dn = ((kp[k] >> e) & 1u) ? d[e] * keep_scale : 0.f;
-                if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
-                s0[e] += dn; s1[e] = fmaf(dn, x[e], s1[e]);
-            }
-            tx[(long long)q * oct + o] = ux[k];
-            td[(long long)q * oct + o] = ud[k];                    // raw dy: the apply phase recomputes dn in fp32 exactly as the unfused path
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { atomicAdd(&part[c + e], s0[e]); atomicAdd(&part[C + c + e], s1[e]); }
-    __syncthreads();
-    cluster_barrier();
-    // image-wide per-channel sums (every CTA computes them redundantly), then group sums S1/S2 and the P,Q constants
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-        float c0 = 0.f, c1x = 0.f;
-        for (uint32_t r = 0; r < CL; ++r) { c0 += ld_dsmem_f32(&part[ch], r); c1x += ld_dsmem_f32(&part[C + ch], r); }
-        const float* Kc = a.K + (long long)b * 4 * C;
-        const float c1 = Kc[2 * C + ch] * c1x - Kc[3 * C + ch] * c0;        // sum dn*xh
-        const float g = __ldg(a.gamma + ch);
-        atomicAdd(&S[(ch / cg) * 2], g * c0); atomicAdd(&S[(ch / cg) * 2 + 1], g * c1);
-        if (rank == 0) { atomicAdd(a.dbeta + ch, c0); atomicAdd(a.dgamma + ch, c1); }
-    }
-    __syncthreads();
-    cluster_barrier();                                             // peers are done reading this CTA's partials
-    {
-        const float inv_n = 1.f / ((float)a.HW * (float)cg);
-        const float* Kc = a.K + (long long)b * 4 * C;
-        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-            const float r = Kc[2 * C + ch], mr = Kc[3 * C + ch];
-            const float k2 = r * S[(ch / cg) * 2] * inv_n, k3 = r * S[(ch / cg) * 2 + 1] * inv_n;
-            pq[ch] = k3 * r; pq[C + ch] = k2 - k3 * mr;
-        }
-    }
-    __syncthreads();
-    float P[8], Q[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { P[e] = pq[c + e]; Q[e] = pq[C + c + e]; }
-    bf16* dst = first ? a.dx0 + ((long long)b * a.HW + p0) * a.s.C0 + c : a.dx1 + ((long long)b * a.HW + p0) * a.s.C1 + (c - a.s.C0);
-    const int acc = first ? a.acc0 : a.acc1;
-    const bf16* adp = a.addend ? a.addend + ((long long)b * a.HW + p0) * C + c : nullptr;
-    float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int q = lp; q < ppc; q += pstep) {
-        float x[8], d[8], ov[8], ad[8];
-        unpack8(tx[(long long)q * oct + o], x); unpack8(td[(long long)q * oct + o], d);
-        if (acc) unpack8(*reinterpret_cast<const uint4*>(dst + (long long)q * sstride), ov);
-        if (adp) unpack8(__ldg(reinterpret_cast<const uint4*>(adp + (long long)q * C)), ad);
-        const uint32_t keep = mk ? (uint32_t)mk[(long long)q * oct] : 0xffu;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float dn = ((keep >> e) & 1u) ? d[e] * keep_scale : 0.f;
-            if (a.silu) { const float y = fmaf(x[e], sc[e], sh[e]); const float sg = sigmoid_fast(y); dn *= sg * fmaf(y, 1.f - sg, 1.f); }
-            float v = fmaf(sc[e], dn, -fmaf(P[e], x[e], Q[e]));
-            if (adp) v += ad[e];
-            if (acc) v += ov[e];
-            ov[e] = v; if (do_cs) cs[e] += v;
-        }
-        *reinterpret_cast<uint4*>(dst + (long long)q * sstride) = pack8(ov);
-    }
-    if (do_cs) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&shc[c + e], cs[e]);
+    if (a.fin_in_apply) {      // block-level sums of dbeta / dgamma, then one atomic per channel and block
+        float* shg = shc + (do_cs ? C : 0);           // [2][C]
         __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            const float v = shc[i];
-            if (cs_per_img) atomicAdd(cs_per_img + (long long)b * cs_ld + i, v);
-            if (cs_total) atomicAdd(cs_total + i, v);
-            if (cs_total2) atomicAdd(cs_total2 + i, v);
-        }
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shg[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(&shg[c + e], sdb[e]); atomicAdd(&shg[C + c + e], sdg[e]); }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(a.dbeta + i, shg[i]); atomicAdd(a.dgamma + i, shg[C + i]); }
     }
 }
 

@@ -7,6 +7,7 @@
 // Roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2-5 = epilogue (TMEM -> regs -> global).
 #pragma once
 #include "ptx.cuh"
+#include "gn_epilogue.cuh"
 
 namespace ddpm {
 
@@ -62,6 +63,7 @@ struct GemmParams {
     int rowvec_ld, rows_per_vec;
     const __nv_bfloat16* residual; int ldr;   // [M][ldr] or null
     float alpha;
+    GnEpi gn; int gn_hw;      // KK: GroupNorm epilogue fusions (gn_epilogue.cuh); rows are NHWC pixels, gn_hw = H*W (multiple of 32)
 };
 
 // A pipeline stage holds KSTEPS K-slabs of 64 (KSTEPS x {A 16 KB, B BLOCK_N x 128 B}).  One producer/consumer handshake costs
@@ -93,9 +95,9 @@ __device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& 
 //   t -> (m_tile fastest, n_tile, z) so that CTAs running concurrently share the same weight (B) tile in L2.
 // TMEM holds TWO accumulator buffers (2 x BLOCK_N columns): the epilogue warps drain buffer i while the MMA warp already
 // accumulates tile i+1 into the other one; the TMA producer runs ahead across tile boundaries.
-// CLUSTER > 1 (KK only): CLUSTER CTAs with consecutive m_tiles (same weight tile) form a thread-block cluster; each loads
-// 1/CLUSTER of the B tile and multicasts it to all of them, so the weight traffic out of L2 drops by CLUSTER.
-template <int BLOCK_N, int MODE, int STAGES, int CLUSTER, int KSTEPS>
+// (TMA multicast of the weight tile over 2/4-CTA clusters was built and measured no faster in round 1 - L2 traffic is not the
+// limiter - and has been removed.)
+template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -140,19 +142,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         return kb1 > kb0 ? kb1 - kb0 : 0;
     };
 
-    static_assert(CLUSTER == 1 || MODE == GEMM_KK, "multicast clusters are implemented for the KK mode only");
-    const uint32_t crank = CLUSTER > 1 ? cluster_ctarank() : 0;
-    constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], gemm_epi_warps(MODE)); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
-    if (CLUSTER > 1) cluster_sync_all();            // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
     pdl_wait();                                     // prologue above overlapped the previous kernel's tail; its data is visible from here
     const uint32_t tmem_base = *tmem_slot;
@@ -205,13 +203,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 if (!st) break;
                                 if (p.dbg & 4) { asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(fb)), "r"((uint32_t)SM::SLAB_BYTES) : "memory"); commit_slab(); continue; }
                                 tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
-                                if (CLUSTER == 1) {
-                                    tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
-                                } else {
-                                    constexpr int ROWS = BLOCK_N / CLUSTER;        // this CTA's slice of the weight tile
-                                    tma_load_3d_mc(st + SM::A_BYTES + crank * ROWS * 128, &tmB, fb, p.b_k_base + kcount * 64,
-                                                   n_tile * BLOCK_N + crank * ROWS, z * p.b_z, CMASK);
-                                }
+                                tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
                                 commit_slab();
                             }
                         }
@@ -288,7 +280,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             if (!(p.dbg & 2)) umma_bf16(d_tmem, da, db, idesc, (i | sb | k) != 0);
                         }
                     }
-                    if (CLUSTER == 1) umma_commit(&empty_bar[st]); else umma_commit_mc(&empty_bar[st], CMASK);
+                    umma_commit(&empty_bar[st]);
                 }
                 if (ok) umma_commit(&tmem_full[acc]);
             }
@@ -372,6 +364,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         f[2 * e] += t2.x; f[2 * e + 1] += t2.y;
                     }
                 }
+                if (MODE == GEMM_KK) {
+                    // GroupNorm fusions (warp-uniform: the 32 rows of a warp lie in one image, M % 32 == 0)
+                    const int n_img = (row_ok && (p.gn.qstats || p.gn.K)) ? row / p.gn_hw : 0;
+                    if (p.gn.qstats) epi_quad_stats(f, row_ok, p.gn.qstats + ((long long)n_img * (p.N >> 2) + (col >> 2)) * 2, lane);
+                    if (p.gn.K) {
+                        const int gnC = p.gn.C0 + p.gn.C1;
+                        uint32_t rs[16]; uint32_t keep = 0xffffffffu;
+                        if (row_ok) {
+                            const __nv_bfloat16* xp = col < p.gn.C0 ? p.gn.x0 + (long long)row * p.gn.C0 + col : p.gn.x1 + (long long)row * p.gn.C1 + (col - p.gn.C0);
+                            ld_row64B(xp, rs);
+                            if (p.gn.mask) keep = __ldg(reinterpret_cast<const unsigned int*>(p.gn.mask + (long long)row * (gnC >> 3) + (col >> 3)));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) rs[e] = 0u;
+                        }
+                        const float* Kn = p.gn.K + (long long)n_img * 4 * p.N + col;
+                        float* gsd = p.gn.gs + ((long long)n_img * (p.N >> 2) + (col >> 2)) * 2;
+                        if (p.gn.mask) epi_gn_bwd<false, true>(f, row_ok, rs, keep, p.gn.keep_scale, p.gn.silu, 0u, 0, Kn, Kn + p.N, p.gn.gamma + col, p.gn.beta + col, gsd, lane);
+                        else           epi_gn_bwd<false, false>(f, row_ok, rs, keep, p.gn.keep_scale, p.gn.silu, 0u, 0, Kn, Kn + p.N, p.gn.gamma + col, p.gn.beta + col, gsd, lane);
+                    }
+                }
                 if (tma_out && NGRP == 2) {
                     // registers -> 128B-swizzled staging slab (row r, 16-byte chunk j at physical chunk j ^ (r & 7))
                     uint8_t* buf = out_stage + (slab_ctr & 1) * SM::OUT_STAGE_BYTES + r * 128;
@@ -429,7 +442,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
-    if (CLUSTER > 1) cluster_sync_all();            // no peer may still multicast data / arrivals into this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);

@@ -14,11 +14,15 @@ namespace ddpm {
 
 struct ParamInfo { std::string name; int nd; int dims[4]; long long numel; long long off; };
 struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
+            long long qs = -1;    // workspace offset of the producer-written quad statistics [B][C/4][2] fp64 (-1: none)
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
 enum { OP_TEMB = 1 };
 struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; int tag = 0; };
 struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; unsigned char* mask; };
+// backward of one GroupNorm, planned BEFORE the data-gradient conv that produces dy so that the conv's epilogue can take over
+// the reduce pass (gn_epilogue.cuh); `fused` is set by conv_op when the chosen kernel supports it
+struct GnBwdPlan { GnSaved sv; float* cs = nullptr; bool fused = false; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 static inline int oct_threads(int C) { const int oct = C / 8; return oct <= 256 ? (256 / oct) * oct : 0; }
@@ -129,8 +133,36 @@ struct UnetEngine {
         const bf16* wp = nullptr; long long ldw = 0; bool has_skip = false; Src skip_in;
         const float* bias = nullptr; const float* rowvec = nullptr; int rowvec_ld = 0; const bf16* residual = nullptr;
         T4 out; float* out_nchw = nullptr; int Co = 0; int Ho = 0, Wo = 0; bool accumulate = false;
+        bool want_qstats = false;          // forward: the output feeds a GroupNorm -> statistics in the epilogue when the kernel can
+        GnBwdPlan* gnb = nullptr;          // backward: the output is dy of this GroupNorm -> dn + column sums in the epilogue
     };
-    void conv_op(std::vector<Op>& L, const ConvSpec& c, double* flops_acc) {
+    // epilogue fusions of a conv: fills `gn` and returns the workspace offset of the quad statistics (-1: none)
+    long long conv_gn_epi(const ConvSpec& c, ddpm_gn_epi& gn) {
+        memset(&gn, 0, sizeof gn);
+        long long qs = -1;
+        static const bool no_fuse = getenv("DDPM_NO_GN_EPI") != nullptr;
+        if (no_fuse) return qs;
+        const int Bn = c.in.t0.B, HW = c.Ho * c.Wo;
+        if (c.want_qstats && c.Co % 32 == 0 && HW % 32 == 0) {
+            qs = (long long)zero_fwd((size_t)Bn * (c.Co / 4) * 2 * 8);
+            gn.qstats = at<double>((size_t)qs);
+        }
+        if (c.gnb && HW % 32 == 0) {
+            const GnSaved& sv = c.gnb->sv;
+            const int C = sv.in.C();
+            // C % 128 == 0: groups are whole 4-channel quads (the apply prologue folds the column sums quad-wise)
+            if (C == c.Co && C % 128 == 0 && sv.in.t0.C % 32 == 0 && (!sv.in.two || sv.in.t1.C % 32 == 0)) {
+                gn.gnb_x0 = bp(sv.in.t0); gn.gnb_C0 = sv.in.t0.C;
+                gn.gnb_x1 = sv.in.two ? bp(sv.in.t1) : nullptr; gn.gnb_C1 = sv.in.two ? sv.in.t1.C : 0;
+                gn.gnb_K = sv.K; gn.gnb_gamma = sv.gamma; gn.gnb_beta = sv.beta; gn.gnb_silu = sv.silu;
+                gn.gnb_gs = c.gnb->cs;              // the [B][2][C] column-sum area doubles as the [B][C/4][2] quad-term area
+                gn.gnb_mask = sv.mask; gn.gnb_keep_scale = sv.drop_p > 0.f ? 1.f / (1.f - sv.drop_p) : 1.f;
+                c.gnb->fused = true;
+            }
+        }
+        return qs;
+    }
+    long long conv_op(std::vector<Op>& L, const ConvSpec& c, double* flops_acc) {
         const int Cin = c.in.C(), taps = c.ksize * c.ksize;
         const T4& i0 = c.in.t0;
         const int Bn = i0.B;
@@ -158,12 +190,19 @@ struct UnetEngine {
             }
             h.w = c.wp; h.ldw = c.ldw; h.Ktot = (int)K; h.out = bp(c.out); h.bias = c.bias; h.rowvec = c.rowvec; h.rowvec_ld = c.rowvec_ld;
             h.residual = c.accumulate ? (const void*)bp(c.out) : (const void*)c.residual; h.base_offset_mode = 0;
+            const long long qs = conv_gn_epi(c, h.gn);
             ++n_tc_gemms;
-            if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return; }
+            if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return qs; }
             HaloLaunch g; int rc = build_halo(h, g);
-            if (rc) { plan_error = rc; return; }
+            if (rc) { plan_error = rc; return qs; }
+            if (g.p.gn.mask) {          // dropout is armed per call by a non-zero seed (eval / p = 0 runs see all-ones masks)
+                UnetEngine* self = this;
+                push(L, c.name + "[halo]", fl, [g, self](cudaStream_t st) {
+                    if (self->drop_seed) return launch_halo(g, st);
+                    HaloLaunch gg = g; gg.p.gn.mask = nullptr; gg.p.gn.keep_scale = 1.f; return launch_halo(gg, st); });
+            } else
             push(L, c.name + "[halo]", fl, [g](cudaStream_t st) { return launch_halo(g, st); });
-            return;
+            return qs;
         }
         if (tc) {
             ddpm_gemm_desc d; memset(&d, 0, sizeof d);
@@ -209,20 +248,27 @@ struct UnetEngine {
                 const float* bias = c.bias; const float* rowvec = c.rowvec; const int rvld = c.rowvec_ld, rpv = c.Ho * c.Wo;
                 const bf16* resid = reinterpret_cast<const bf16*>(d.residual); bf16* outp = bp(c.out);
                 const long long M = Pout; const int N = c.Co; const int nfin = grid_for(M * (N / 8));
-                if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }, 2); return; }
+                if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }, 2); return -1; }
                 GemmLaunch g; int rc = build_gemm(ds, g);
-                if (rc) { plan_error = rc; return; }
+                if (rc) { plan_error = rc; return -1; }
                 push(L, c.name + "[splitk]", fl, [=](cudaStream_t st) {
                     const int r2 = launch_gemm(g, st); if (r2) return r2;
                     launch_k(k_splitk_finalize, nfin, 256, 0, st, scratch, bias, rowvec, rvld, rpv, resid, outp, M, N);
                     return (int)cudaGetLastError(); }, 2);
-                return;
+                return -1;
             }
-            if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return; }
+            const long long qs = conv_gn_epi(c, d.gn);
+            if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return qs; }
             GemmLaunch g; int rc = build_gemm(d, g);
-            if (rc) { plan_error = rc; return; }
+            if (rc) { plan_error = rc; return qs; }
+            if (g.p.gn.mask) {
+                UnetEngine* self = this;
+                push(L, c.name, fl, [g, self](cudaStream_t st) {
+                    if (self->drop_seed) return launch_gemm(g, st);
+                    GemmLaunch gg = g; gg.p.gn.mask = nullptr; gg.p.gn.keep_scale = 1.f; return launch_gemm(gg, st); });
+            } else
             push(L, c.name, fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
-            return;
+            return qs;
         }
         ++n_generic;
         ConvG g; memset(&g, 0, sizeof g);
@@ -241,6 +287,7 @@ struct UnetEngine {
             s.bias = nullptr; s.rowvec = nullptr; s.residual = nullptr; s.accumulate = 1;
             push(L, c.name + ".skip[simt]", 0, [s, grid](cudaStream_t st) { launch_k(k_conv_generic, grid, 256, 0, st, s); return (int)cudaGetLastError(); });
         }
+        return -1;
     }
     float* eps_dst = nullptr;   // run-time destination of the final conv (caller buffer or internal eps buffer)
     const float* deps_src = nullptr;   // run-time d(loss)/d(eps), fp32 NCHW (caller buffer or internal buffer)
@@ -320,30 +367,6 @@ struct UnetEngine {
         nblk = (148 * occ) / Bn; if (nblk > HW / 16) nblk = HW / 16; if (nblk < 1) nblk = 1;
         ppb = (HW + nblk - 1) / nblk; nblk = (HW + ppb - 1) / ppb;
     }
-    // fused single-kernel GroupNorm (one thread-block cluster per image, tile kept in shared memory, statistics exchanged
-    // through DSMEM): cluster size such that the image's tile(s) fit; 0 = use the multi-kernel path.
-    // MEASURED SLOWER on B200 (CIFAR bs=128 step 14.3 ms vs 12.6 ms): at 1-2 CTAs per SM the load -> cluster barrier -> apply
-    // phases serialise, while the multi-kernel path overlaps 4-8 blocks per SM.  Kept as an opt-in experiment (DDPM_FUSED_GN=1).
-    static int gn_cluster(int HW, int C, int ntiles, size_t extra) {
-        static const bool on = getenv("DDPM_FUSED_GN") != nullptr;
-        if (!on) return 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            const size_t budget = pass == 0 ? 100 * 1024 : 200 * 1024;
-            for (int cl = 1; cl <= 8; cl <<= 1) {
-                if (HW % cl) continue;
-                if ((size_t)(HW / cl) * C * 2 * ntiles + extra <= budget) return cl;
-            }
-        }
-        return 0;
-    }
-    template <class Kern, class... Args>
-    static int launch_cluster(Kern kern, dim3 grid, int threads, size_t shm, int cl, cudaStream_t st, Args... args) {
-        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = shm; cfg.stream = st;
-        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        return (int)cudaLaunchKernelEx(&cfg, kern, args...);
-    }
     GnSaved gn_fwd(std::vector<Op>& L, const std::string& name, const Src& in, const std::string& pname, const T4& out, int silu, float drop_p) {
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
         GnSaved sv; sv.in = in; sv.silu = silu; sv.drop_p = drop_p; sv.layer = ++layer_counter;   // dropout is armed per call by a non-zero seed
@@ -354,17 +377,19 @@ struct UnetEngine {
         const int thr = oct_threads(C);
         float* K = sv.K; const float* ga = sv.gamma; const float* be = sv.beta;
         sv.mask = (drop_p > 0.f && train) ? at<unsigned char>(alloc((size_t)Bn * HW * (C / 8))) : nullptr;
-        const int cl = gn_cluster(HW, C, 1, 1024);
-        if (cl) {
-            GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
-            const int ppc = HW / cl; const size_t shm = 512 + (size_t)ppc * C * 2;
-            const int thr5 = (512 / (C / 8)) * (C / 8);
-            const dim3 gf(cl, Bn);
+        // statistics delivered by the producers' epilogues (conv_gn_epi): one launch, no pass over the tensor for the stats
+        const bool have_qs = in.t0.qs >= 0 && (!in.two || in.t1.qs >= 0) && (C % 128) == 0;
+        if (have_qs) {
+            static const int ap_occ = getenv("DDPM_GN_APPLY_OCC") ? atoi(getenv("DDPM_GN_APPLY_OCC")) : 4;
+            GnApply a; memset(&a, 0, sizeof a);
+            a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
+            a.qs0 = at<double>((size_t)in.t0.qs); a.qs1 = in.two ? at<double>((size_t)in.t1.qs) : nullptr;
+            a.gamma = ga; a.beta = be; a.eps = 1e-6f; a.Kout = K;
+            int nb2, ppb2; gn_grid(Bn, HW, ap_occ, nb2, ppb2);
+            const dim3 g2(nb2, Bn);
             UnetEngine* self = this;
-            static bool attr_done = false;
-            if (!attr_done && !dry) { cudaFuncSetAttribute(k_gn_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }
-            push(L, name + ".fused", 0, [=](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
-                return launch_cluster(k_gn_fused_fwd, gf, thr5, shm, cl, st, aa, K, ga, be, ppc, 1e-6f); });
+            push(L, name + ".apply[qs]", 0, [a, g2, thr, ppb2, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
+                launch_k(k_gn_apply, g2, thr, 0, st, aa, ppb2); return (int)cudaGetLastError(); });
             return sv;
         }
         static const int st_occ = getenv("DDPM_GN_STATS_OCC") ? atoi(getenv("DDPM_GN_STATS_OCC")) : 4;
@@ -375,7 +400,8 @@ struct UnetEngine {
         push(L, name + ".stats", 0, [=](cudaStream_t st) {
             launch_k(k_gn_stats, g1, thr, 0, st, gs, stats, HW, ppb, fin);
             return (int)cudaGetLastError(); });
-        GnApply a; a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
+        GnApply a; memset(&a, 0, sizeof a);
+        a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
         int nb2, ppb2; gn_grid(Bn, HW, ap_occ, nb2, ppb2);
         const dim3 g2(nb2, Bn);
         UnetEngine* self = this;
@@ -383,14 +409,21 @@ struct UnetEngine {
             launch_k(k_gn_apply, g2, thr, 0, st, aa, ppb2); return (int)cudaGetLastError(); });
         return sv;
     }
+    // call BEFORE the data-gradient conv that produces dy; pass the plan to that conv (ConvSpec::gnb) and then to gn_bwd
+    GnBwdPlan gn_bwd_plan(const GnSaved& sv) {
+        GnBwdPlan p; p.sv = sv;
+        p.cs = at<float>(zero_bwd((size_t)sv.in.t0.B * 2 * sv.in.C() * 4));
+        return p;
+    }
     // dx(in) (=|+=) gn_bwd(dy) + addend ; dgamma/dbeta accumulate into the flat grads
-    void gn_bwd(const std::string& name, const GnSaved& sv, const T4& dy, const bf16* addend,
+    void gn_bwd(const std::string& name, const GnBwdPlan& gp, const T4& dy, const bf16* addend,
                 float* cs_per_img = nullptr, int cs_ld = 0, float* cs_total = nullptr, float* cs_total2 = nullptr) {
+        const GnSaved& sv = gp.sv;
         const Src& in = sv.in;
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
         GnBwd a; memset(&a, 0, sizeof a);
         a.s = gsrc(in); a.dy = bp(dy); a.K = sv.K; a.gamma = sv.gamma;
-        a.cs = at<float>(zero_bwd((size_t)Bn * 2 * C * 4)); a.PQ = at<float>(alloc((size_t)Bn * 2 * C * 4));
+        a.cs = gp.cs; a.gs = gp.cs; a.PQ = at<float>(alloc((size_t)Bn * 2 * C * 4));
         a.dgamma = sv.dgamma; a.dbeta = sv.dbeta;
         bool f0 = true, f1 = true;
         const T4 g0 = grad_of(in.t0, &f0); a.dx0 = bp(g0); a.acc0 = f0 ? 0 : 1;
@@ -400,26 +433,6 @@ struct UnetEngine {
         static const bool no_dn = getenv("DDPM_GN_NO_DN") != nullptr;
         a.dn_inplace = (sv.silu && !no_dn) ? 1 : 0;
         const int thr = oct_threads(C);
-        {
-            const size_t extra = (size_t)(5 * C + 64) * 4 + 64;
-            const int cl = gn_cluster(HW, C, 2, extra);
-            if (cl) {
-                const int ppc = HW / cl; const size_t shm = (((size_t)(5 * C + 64) * 4 + 15) / 16) * 16 + (size_t)2 * ppc * C * 2;
-                const int thr5 = (512 / (C / 8)) * (C / 8);
-                const dim3 gf(cl, Bn);
-                const bool cs = cs_per_img || cs_total || cs_total2;
-                UnetEngine* self = this;
-                static bool attr_done = false;
-                if (!attr_done && !dry) {
-                    cudaFuncSetAttribute(k_gn_fused_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-                    cudaFuncSetAttribute(k_gn_fused_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done = true; }
-                push(bwd_ops, name + ".gn_bwd.fused", 0, [=](cudaStream_t st) {
-                    GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
-                    if (cs) return launch_cluster(k_gn_fused_bwd<true>, gf, thr5, shm, cl, st, aa, ppc, cs_per_img, cs_ld, cs_total, cs_total2);
-                    return launch_cluster(k_gn_fused_bwd<false>, gf, thr5, shm, cl, st, aa, ppc, cs_per_img, cs_ld, cs_total, cs_total2); });
-                return;
-            }
-        }
         // Grid granularity measured on the whole step (bench.py, DDPM_GN_BWD_OCC / _STATS_OCC / _APPLY_OCC sweeps): blocks per
         // image = 148*occ/B; occ 4 is best for all three passes (10.49 ms/step; occ 2: 10.69, 8: 11.04, 16: 11.71) - per-block
         // prologue / atomics cost more than the wave-quantisation they would save.
@@ -430,6 +443,16 @@ struct UnetEngine {
         const size_t shm = (size_t)2 * C * 4;
         const size_t shm2 = (cs_per_img || cs_total || cs_total2) ? (size_t)C * 4 : 0;
         UnetEngine* self = this;
+        if (gp.fused) {     // dy already holds dn and cs is complete: ONE pass (prologue = finalize)
+            a.dn_inplace = 1; a.fin_in_apply = 1;
+            const size_t shm3 = shm2 + (size_t)2 * C * 4;      // + block-level dbeta / dgamma sums
+            push(bwd_ops, name + ".gn_bwd[epi]", 0, [=](cudaStream_t st) {
+                GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
+                if (shm2) launch_k(k_gn_bwd_apply<true>, g1, thr, shm3, st, aa, cs_per_img, cs_ld, cs_total, cs_total2);
+                else      launch_k(k_gn_bwd_apply<false>, g1, thr, shm3, st, aa, cs_per_img, cs_ld, cs_total, cs_total2);
+                return (int)cudaGetLastError(); }, 1);
+            return;
+        }
         push(bwd_ops, name + ".gn_bwd", 0, [=](cudaStream_t st) {
             GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
             launch_k(k_gn_bwd_reduce, g1, thr, shm, st, aa);

@@ -61,7 +61,8 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
     {
         ConvSpec c; c.name = p + ".conv1"; c.in = one(a1); c.wp = w1.fwd; c.ldw = w1.ld_f; c.bias = PP(p + ".conv1.bias");
         c.rowvec = TP + tp_off; c.rowvec_ld = tp_ld; c.out = h1; c.Co = cout; c.Ho = h; c.Wo = w;
-        conv_op(fwd_ops, c, &fwd_flops);
+        c.want_qstats = true;                       // h1 feeds norm2: its statistics come out of this conv's epilogue
+        h1.qs = conv_op(fwd_ops, c, &fwd_flops);
     }
     T4 a2 = newT(Bn, h, w, cout);
     const GnSaved g2 = gn_fwd(fwd_ops, p + ".norm2", one(h1), p + ".norm2", a2, 1, cfg.drop_rate);
@@ -79,15 +80,17 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
         ConvSpec c; c.name = p + ".conv2"; c.in = one(a2); c.wp = w2.fwd; c.ldw = w2.ld_f; c.bias = bias2;
         c.has_skip = has_skip; c.skip_in = x; c.residual = has_skip ? nullptr : bp(x.t0);
         c.out = out; c.Co = cout; c.Ho = h; c.Wo = w;
-        conv_op(fwd_ops, c, &fwd_flops);
+        c.want_qstats = true;                       // block outputs feed the next norm1 / attention norm / out_conv.0 (and, as skips, the up path)
+        out.qs = conv_op(fwd_ops, c, &fwd_flops);
     }
     if (!train) return out;
     tape.push_back([=]() {
         const T4 dOut = grad_of(out, nullptr);
         colsum_op(p + ".conv2.bias", dOut, nullptr, 0, GP(p + ".conv2.bias"), has_skip ? GP(p + ".skip.bias") : nullptr, cout);
         T4 d_a2 = newT(Bn, h, w, cout);
+        GnBwdPlan p2 = gn_bwd_plan(g2);             // norm2's reduce pass rides in conv2.dgrad's epilogue when that kernel can
         { ConvSpec c; c.name = p + ".conv2.dgrad"; c.in = one(dOut); c.wp = w2.dgr; c.ldw = w2.ld_d; c.out = d_a2; c.Co = cout; c.Ho = h; c.Wo = w;
-          conv_op(bwd_ops, c, &bwd_flops); }
+          c.gnb = &p2; conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".conv2.wgrad", dOut, one(a2), 3, 1, MAP_NORMAL, GP(p + ".conv2.weight"), cout);
         T4 dxs;
         if (has_skip) {
@@ -98,13 +101,14 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
         }
         // the column sums of d_h1 (bias gradients of conv1 / fc and the per-image timestep-projection gradient) are
         // accumulated by the same kernel that produces d_h1
-        gn_bwd(p + ".norm2", g2, d_a2, nullptr, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"));
+        gn_bwd(p + ".norm2", p2, d_a2, nullptr, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"));
         const T4 d_h1 = grad_of(h1, nullptr);
         T4 d_a1 = newT(Bn, h, w, cin);
+        GnBwdPlan p1 = gn_bwd_plan(g1);
         { ConvSpec c; c.name = p + ".conv1.dgrad"; c.in = one(d_h1); c.wp = w1.dgr; c.ldw = w1.ld_d; c.out = d_a1; c.Co = cin; c.Ho = h; c.Wo = w;
-          conv_op(bwd_ops, c, &bwd_flops); }
+          c.gnb = &p1; conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".conv1.wgrad", d_h1, one(a1), 3, 1, MAP_NORMAL, GP(p + ".conv1.weight"), cout);
-        gn_bwd(p + ".norm1", g1, d_a1, has_skip ? bp(dxs) : bp(dOut));
+        gn_bwd(p + ".norm1", p1, d_a1, has_skip ? bp(dxs) : bp(dOut));
     });
     return out;
 }
@@ -131,7 +135,7 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     const Packed wout = pack_conv(p + ".project_out", C, C, 1, 0, false, true);
     T4 out = newT(Bn, h, w, C);
     { ConvSpec c; c.name = p + ".project_out"; c.in = one(O); c.ksize = 1; c.wp = wout.fwd; c.ldw = wout.ld_f; c.bias = PP(p + ".project_out.bias");
-      c.residual = bp(x); c.out = out; c.Co = C; c.Ho = h; c.Wo = w; conv_op(fwd_ops, c, &fwd_flops); }
+      c.residual = bp(x); c.out = out; c.Co = C; c.Ho = h; c.Wo = w; c.want_qstats = true; out.qs = conv_op(fwd_ops, c, &fwd_flops); }
     if (!train) return out;
     tape.push_back([=]() {
         const T4 dY = grad_of(out, nullptr);
@@ -152,10 +156,11 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
         bmm(bwd_ops, p + ".dK", 2, dS, T, (long long)T * T, q, ldq, sq, dq + C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         colsum_op(p + ".project_in.bias", dqkv, nullptr, 0, GP(p + ".project_in.bias"), nullptr, 3 * C);
         T4 dxn = newT(Bn, h, w, C);
+        GnBwdPlan pn = gn_bwd_plan(g);
         { ConvSpec c; c.name = p + ".project_in.dgrad"; c.in = one(dqkv); c.ksize = 1; c.wp = win.dgr; c.ldw = win.ld_d; c.out = dxn; c.Co = C; c.Ho = h; c.Wo = w;
-          conv_op(bwd_ops, c, &bwd_flops); }
+          c.gnb = &pn; conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".project_in.wgrad", dqkv, one(xn), 1, 1, MAP_NORMAL, GP(p + ".project_in.weight"), 3 * C);
-        gn_bwd(p + ".norm", g, dxn, bp(dY));
+        gn_bwd(p + ".norm", pn, dxn, bp(dY));
     });
     return out;
 }
@@ -169,7 +174,7 @@ inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
     const Packed pk = pack_conv(p, C, C, 3, 0, /*flip=*/false, true, tc ? 3 : 1);
     T4 out = newT(Bn, h / 2, w / 2, C);
     { ConvSpec c; c.name = p; c.in = one(x); c.stride = 2; c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = h / 2; c.Wo = w / 2;
-      conv_op(fwd_ops, c, &fwd_flops); }
+      c.want_qstats = true; out.qs = conv_op(fwd_ops, c, &fwd_flops); }
     if (!train) return out;
     tape.push_back([=]() {
         const T4 dY = grad_of(out, nullptr);
@@ -219,7 +224,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
     const Packed pk = pack_conv(p, C, C, 3, 0, true, true);
     T4 out = newT(Bn, 2 * h, 2 * w, C);
     { ConvSpec c; c.name = p; c.in = one(up); c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = 2 * h; c.Wo = 2 * w;
-      conv_op(fwd_ops, c, &fwd_flops); }
+      c.want_qstats = true; out.qs = conv_op(fwd_ops, c, &fwd_flops); }
     if (!train) return out;
     tape.push_back([=]() {
         const T4 dY = grad_of(out, nullptr);
@@ -560,6 +565,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             tape.push_back([=]() {
                 float* gw = GP("out_conv.2.weight"); float* gb = GP("out_conv.2.bias");
                 T4 d_a = newT(B, H, W, ch);
+                GnBwdPlan po = gn_bwd_plan(g);
                 bf16* dap = bp(d_a);
                 const size_t shm2 = (size_t)(ch * Cout * 9 + ch) * 4; const int n2 = grid_for((long long)Bn * Hn * Wn / 2, 128);
                 const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
@@ -581,7 +587,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                         return (int)cudaGetLastError(); }, 2);
                     ConvSpec cs; cs.name = "out_conv.2.dgrad"; cs.in = one(E); cs.ksize = 1; cs.wp = w27t; cs.ldw = 64;
                     cs.out = d_a; cs.Co = ch; cs.Ho = H; cs.Wo = W;
-                    conv_op(bwd_ops, cs, nullptr);
+                    cs.gnb = &po; conv_op(bwd_ops, cs, nullptr);
                     float* S = at<float>(zero_bwd((size_t)64 * ch * 4));
                     wgrad_op("out_conv.2.wgrad", E, one(a_out), 1, 1, MAP_NORMAL, S, 64);
                     const int nun = (Cout * ch * 9 + 255) / 256;
@@ -601,7 +607,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                                 launch_k(k_corr3x3<4>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
                     }
                     return (int)cudaGetLastError(); }, 3);
-                gn_bwd("out_conv.0", g, d_a, nullptr);
+                gn_bwd("out_conv.0", po, d_a, nullptr);
             });
         }
     }

@@ -30,6 +30,24 @@ int ddpm_runtime_check(void);
 /* Device-side error flag set by a bounded wait that timed out inside a kernel (0 = none). Synchronises. */
 int ddpm_device_error_flag(void);
 
+/* Optional GroupNorm fusions of a conv / GEMM epilogue (nn.GroupNorm(32, C, eps=1e-6) + SiLU + Dropout of unet.py:18-20,
+ * 83-89; csrc/gn_epilogue.cuh).  All-zero = off.
+ *  qstats   forward: the producer adds per (image, 4-channel quad) {sum, sum of squares} of its OUTPUT to qstats[NB][N/4][2]
+ *           (fp64 atomics, caller zeroes it) - the statistics pass of the consuming GroupNorm disappears.
+ *  gnb_K    backward: the accumulator is dy, the gradient at a = mask*silu(gn(x)); the epilogue stores
+ *           dn = dy * keep * silu'(sc*x + sh) instead and adds per (image, 4-channel quad) the group-level terms
+ *           {sum gamma*dn, sum gamma*dn*xhat} to gnb_gs[NB][N/4][2] (fp32 atomics, caller zeroes it).  gnb_x0/x1: the
+ *           GroupNorm input as a concat of up to two NHWC bf16 tensors with gnb_C0 + gnb_C1 == N channels;
+ *           gnb_K[NB][4][N] = {sc, sh, rstd, mean*rstd}; gnb_gamma / gnb_beta [N]: the norm's affine parameters; gnb_mask:
+ *           dropout keep bits, one byte per 8 channels [pixel][N/8] (or NULL) with gnb_keep_scale = 1/(1-p); gnb_silu: 1 when
+ *           the norm is followed by SiLU. */
+typedef struct ddpm_gn_epi {
+    double* qstats;
+    const void* gnb_x0; const void* gnb_x1; int gnb_C0, gnb_C1;
+    const float* gnb_K; const float* gnb_gamma; const float* gnb_beta; float* gnb_gs;
+    const unsigned char* gnb_mask; float gnb_keep_scale; int gnb_silu;
+} ddpm_gn_epi;
+
 /* ------------------------------------------------------------------------------------------------
  * Low-level operator: one tcgen05 implicit-GEMM launch (used by the parity tests of the engine itself).
  * mode 0 (KK)   A K-major NHWC pixel tiles (+3x3 taps, up to 3 channel segments), B K-major matrix stack
@@ -57,6 +75,7 @@ typedef struct ddpm_gemm_desc {
     int seg_custom[3], seg_cmul[3]; signed char seg_dx[3][9], seg_dy[3][9];
     int o_mul, o_py, o_px;
     int kk_splits;                     /* mode 0: split the K loop over grid_z = kk_splits CTAs per tile (fp32 atomic output) */
+    ddpm_gn_epi gn;                    /* mode 0 only, rows = NHWC pixels with H*W % 32 == 0 */
 } ddpm_gemm_desc;
 int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream);
 
@@ -73,6 +92,7 @@ typedef struct ddpm_halo_desc {
     void* out; const float* bias; const float* rowvec; int rowvec_ld; const void* residual;
     int base_offset_mode;              /* 0 = descriptor base_offset field left 0 (correct on B200); 1 = (addr>>7)&7 (probe) */
     int force_sub;                     /* 0 = auto; 1 / 2 = number of 16x8 sub-tiles per CTA */
+    ddpm_gn_epi gn;
 } ddpm_halo_desc;
 int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream);
 
