@@ -11,9 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libddpm_b200.so")
 
 
 class GnEpi(C.Structure):
-    _fields_ = [("qstats", C.c_void_p), ("gnb_x0", C.c_void_p), ("gnb_x1", C.c_void_p), ("gnb_C0", C.c_int), ("gnb_C1", C.c_int),
-                ("gnb_K", C.c_void_p), ("gnb_gamma", C.c_void_p), ("gnb_beta", C.c_void_p), ("gnb_gs", C.c_void_p),
-                ("gnb_mask", C.c_void_p), ("gnb_keep_scale", C.c_float), ("gnb_silu", C.c_int)]
+    _fields_ = [("qstats", C.c_void_p)]
 
 
 class GemmDesc(C.Structure):
@@ -98,6 +96,7 @@ def lib():
             "ddpm_sampler_setup": ([vp, i32, vp, vp], i32),
             "ddpm_sampler_reset": ([vp, i32, vp], i32),
             "ddpm_sampler_step": ([vp, vp, vp, u64, vp], i32),
+            "ddpm_sampler_step_pred": ([vp, vp, vp, u64, vp, vp], i32),
             "ddpm_unet_plan_stats": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
             "ddpm_unet_launches_per_forward": ([vp], i32),
@@ -117,7 +116,7 @@ EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "d
            "ddpm_unet_create", "ddpm_unet_destroy", "ddpm_unet_num_params", "ddpm_unet_param_info",
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",
-           "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_unet_plan_stats",
+           "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_sampler_step_pred", "ddpm_unet_plan_stats",
            "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts", "ddpm_opt_step", "ddpm_to_uint8_nhwc"]
 
 

@@ -31,7 +31,7 @@ struct HaloParams {
     const float* bias; const float* rowvec; int rowvec_ld;   // rowvec: per-image vector [NB][rowvec_ld]
     const __nv_bfloat16* residual; int ldr;
     int desc_base_offset_mode; // 0 (default, correct): base_offset field = 0 ; 1: (start>>7)&7 (probe knob, wrong on B200)
-    GnEpi gn;                  // GroupNorm fusions of the epilogue (gn_epilogue.cuh); all-null = off
+    GnEpi gn;                  // GroupNorm statistics of the output (gn_epilogue.cuh); null = off
 };
 
 template <int BLOCK_N, int SUB>
@@ -52,8 +52,7 @@ struct HaloCfg {
     static constexpr int NACC = (2 * SUB * BLOCK_N <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * SUB * BLOCK_N <= 128) ? 128 : ((NACC * SUB * BLOCK_N <= 256) ? 256 : 512);
     static constexpr int OUT_STAGE_BYTES = 128 * 128;           // one 64-channel x 128-pixel output slab (TMA store source)
-    static constexpr int TOTAL = NA * A_STRIDE + NB_ST * B_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ +
-                                 3072 /*bias vector + double-buffered GroupNorm vectors of a 64-channel slab*/;
+    static constexpr int TOTAL = NA * A_STRIDE + NB_ST * B_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*bias vector*/;
 };
 constexpr int HALO_EPI_WARPS = 8;                               // two per TMEM lane quarter (see umma_gemm.cuh)
 constexpr int HALO_THREADS = 64 + 32 * HALO_EPI_WARPS;
@@ -85,8 +84,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_vec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_a) + 512);     // [BLOCK_N] bias + per-image vector
     const uint32_t s_vec_u32 = smem_u32(s_vec);
-    float* s_gv = s_vec + 256;                      // [2][4][64] GroupNorm {sc, sh, gamma, beta} of the current / next slab (backward fusion)
-    const uint32_t s_gv_u32 = smem_u32(s_gv);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -212,8 +209,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         constexpr int EPI_T = 32 * HALO_EPI_WARPS;
         constexpr int NSLAB = BLOCK_N / 64;          // Cout % BLOCK_N == 0 (pick_block_n): every slab of every tile is full
         constexpr int NIT = SUB * NSLAB;
-        const bool gnb = p.gn.K != nullptr;          // GroupNorm-backward fusion (gn_epilogue.cuh)
-        const int gnC = p.gn.C0 + p.gn.C1;
         int it = 0;
         uint32_t slab_ctr = 0;                       // staging-buffer parity, continues across tiles
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -222,22 +217,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const int y0 = (rr / p.tiles_x) * 16, x0 = (rr % p.tiles_x) * 8 * SUB;
             const int acc = (CF::NACC == 2) ? (it & 1) : 0;
             const uint32_t acc_ph = (CF::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
-            // x rows (and dropout keep bits) of the GroupNorm input for slab i2 of this tile: issued one slab ahead, the first
-            // one before the accumulator is even complete, so that the HBM latency hides behind the MMAs / the previous slab
-            uint32_t rs_nxt[16]; uint32_t keep_nxt = 0xffffffffu;
-            auto x_prefetch = [&](int i2) {
-                const int sub = i2 / NSLAB, s0 = (i2 % NSLAB) * 64;
-                const long long px = ((long long)n * p.H + y0 + (r >> 3)) * p.W + x0 + 8 * sub + (r & 7);
-                const int cc = n_tile * BLOCK_N + s0 + grp * 32;
-                const __nv_bfloat16* xp = cc < p.gn.C0 ? p.gn.x0 + px * p.gn.C0 + cc : p.gn.x1 + px * p.gn.C1 + (cc - p.gn.C0);
-                ld_row64B(xp, rs_nxt);
-                if (p.gn.mask) keep_nxt = __ldg(reinterpret_cast<const unsigned int*>(p.gn.mask + px * (gnC >> 3) + (cc >> 3)));
-            };
-            if (gnb) x_prefetch(0);
             if (!mbar_wait(&tmem_full[acc], acc_ph, 3)) break;
             tc_fence_after();
-            // bias + per-image timestep vector of this tile, staged once (a patch lies inside one image); with the
-            // GroupNorm-backward fusion also {sc, sh, gamma, beta} of the first 64-channel slab (later slabs are staged one ahead)
+            // bias + per-image timestep vector of this tile, staged once (a patch lies inside one image)
             named_bar_sync(1, EPI_T);
             for (int c = tid_epi; c < BLOCK_N; c += EPI_T) {
                 const int col = n_tile * BLOCK_N + c;
@@ -248,14 +230,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 s_vec[c] = v;
             }
-            auto stage_gn = [&](int i2) {            // EPI_T == 256 == 4 vectors x 64 channels
-                const int vec = tid_epi >> 6, col = n_tile * BLOCK_N + (i2 % NSLAB) * 64 + (tid_epi & 63);
-                float v;
-                if (vec < 2) v = __ldg(p.gn.K + ((long long)n * 4 + vec) * p.N + col);
-                else v = __ldg((vec == 2 ? p.gn.gamma : p.gn.beta) + col);
-                s_gv[(i2 & 1) * 256 + tid_epi] = v;
-            };
-            if (gnb) stage_gn(0);
             named_bar_sync(1, EPI_T);
 #pragma unroll 1
             for (int i2 = 0; i2 < NIT; ++i2) {
@@ -264,13 +238,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * SUB * BLOCK_N + sub * BLOCK_N);
                 const int c0 = s0 + grp * 32;
                 const int col = n_tile * BLOCK_N + c0;
-                uint32_t rs[16]; uint32_t keep = 0xffffffffu;
-                if (gnb) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) rs[e] = rs_nxt[e];
-                    keep = keep_nxt;
-                    if (i2 + 1 < NIT) x_prefetch(i2 + 1);
-                }
                 uint32_t v[32];
                 tmem_ld32(t_addr + (uint32_t)c0, v);
                 tmem_ld_wait();
@@ -291,21 +258,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         f[2 * e] += t2.x; f[2 * e + 1] += t2.y;
                     }
                 }
-                // GroupNorm fusions (warp-uniform branches): statistics of the output / dy -> dn + group terms
+                // GroupNorm statistics of the output for its consumers (warp-uniform branch; gn_epilogue.cuh)
                 if (p.gn.qstats) epi_quad_stats(f, true, p.gn.qstats + ((long long)n * (p.N >> 2) + (col >> 2)) * 2, lane);
-                if (gnb) {
-                    const uint32_t vs = s_gv_u32 + (uint32_t)((i2 & 1) * 256 + grp * 32) * 4u;
-                    float* gsd = p.gn.gs + ((long long)n * (p.N >> 2) + (col >> 2)) * 2;
-                    if (p.gn.mask) epi_gn_bwd<true, true>(f, true, rs, keep, p.gn.keep_scale, p.gn.silu, vs, 64, nullptr, nullptr, nullptr, nullptr, gsd, lane);
-                    else           epi_gn_bwd<true, false>(f, true, rs, keep, p.gn.keep_scale, p.gn.silu, vs, 64, nullptr, nullptr, nullptr, nullptr, gsd, lane);
-                }
                 // registers -> 128B-swizzled staging slab (row r = pixel, 16-byte chunk j at physical chunk j ^ (r & 7))
                 uint8_t* buf = out_stage + (slab_ctr & 1) * CF::OUT_STAGE_BYTES + r * 128;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     st_shared_v4(buf + (((grp * 4 + j) ^ (r & 7)) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                  pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                if (gnb && i2 + 1 < NIT) stage_gn(i2 + 1);      // published by the slab barrier below
                 // one barrier per slab: before it the issuing thread has waited until the previous store finished reading its
                 // buffer (the one the next slab overwrites); after it all 128 pixel rows of this slab are staged
                 fence_proxy_async_smem();
@@ -352,8 +312,6 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
     p.N = d.Cout; p.out = d.out; p.ldo = d.Cout; p.bias = d.bias; p.rowvec = d.rowvec; p.rowvec_ld = d.rowvec_ld;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual); p.ldr = d.Cout; p.desc_base_offset_mode = d.base_offset_mode;
     p.gn = gn_epi_from_abi(d.gn);
-    if (p.gn.K && (p.gn.C0 + p.gn.C1 != d.Cout || p.gn.C0 % 32 || p.gn.C1 % 32 || !p.gn.gs || !p.gn.x0 || !p.gn.gamma || !p.gn.beta))
-        return fail(-12, "halo conv: bad GroupNorm-backward epilogue description");
     p.nseg = d.nseg;
     const int P = 8 * sub + 2;
     int rc;

@@ -137,10 +137,13 @@ int ddpm_train_forward(ddpm_unet* h, const float* x0, const int64_t* t, const fl
     const int per_img = e.cfg.in_channels * e.H * e.W;
     const long long total = (long long)e.B * per_img;
     float* xt = e.at<float>(e.xt_off); float* eps = e.at<float>(e.eps_off);
-    launch_k(k_qsample, grid_for(total), 256, 0, st, x0, noise, reinterpret_cast<const long long*>(t), tab_a, tab_s, xt, per_img, total);
-    DDPM_CUDA_OK(cudaGetLastError());
-    e.x_in = xt; e.t_in = reinterpret_cast<const long long*>(t); e.eps_dst = eps; e.drop_seed = dropout_seed;
+    (void)per_img; (void)total;
+    // q_sample (diffusion.py:92-97) is in_conv's load prologue: x_t is formed on the fly (and stored once, for the backward)
+    e.qs_pro = QsamplePro{noise, reinterpret_cast<const long long*>(t), tab_a, tab_s, xt};
+    e.x_in = x0; e.t_in = reinterpret_cast<const long long*>(t); e.eps_dst = eps; e.drop_seed = dropout_seed;
     const int rc = e.run_list(e.fwd_ops, st);
+    e.qs_pro = QsamplePro{};
+    e.x_in = xt;                                       // what the backward pass reads as the network input
     if (rc) return rc;
     h->train_target = noise;
     launch_k(k_mse, e.B, 256, 0, st, eps, noise, losses, e.cfg.out_channels * e.H * e.W);
@@ -179,6 +182,9 @@ int ddpm_sampler_reset(ddpm_unet* h, int first_step, void* stream) {
     return 0;
 }
 int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, void* stream) {
+    return ddpm_sampler_step_pred(h, x, z, seed, nullptr, stream);
+}
+int ddpm_sampler_step_pred(ddpm_unet* h, float* x, const float* z, uint64_t seed, float* pred_x0, void* stream) {
     NEED_PLAN(h);
     if (!h->d_coef) return fail(-33, "ddpm_sampler_setup has not been called");
     UnetEngine& e = h->e;
@@ -189,12 +195,19 @@ int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, voi
     e.x_in = x; e.t_in = tbuf; e.eps_dst = eps; e.drop_seed = 0;
     static const bool no_uni = getenv("DDPM_NO_UNIFORM_T") != nullptr;
     e.uniform_t = !no_uni;                                // the whole batch is at the same timestep (diffusion.py:166)
+    // the alpha/beta update of diffusion.py:107-158 rides in the epilogue of the final conv (k_out_gather): eps never reaches
+    // memory and the step has no tail launch.  (Plans whose out_conv is not on the tensor-core path keep the separate tail.)
+    const bool fused = e.gather_fused_tail;
+    if (fused) { e.ps_epi.x = x; e.ps_epi.z = z; e.ps_epi.coef = cc; e.ps_epi.seed = (unsigned long long)seed; e.ps_epi.pred = pred_x0; }
     const int rc = e.run_list(e.fwd_ops, st);
     e.uniform_t = false;
+    e.ps_epi = PsampleEpi{nullptr, nullptr, nullptr, 0, nullptr};
     if (rc) return rc;
-    const long long total = (long long)e.B * e.cfg.out_channels * e.H * e.W;
-    launch_k(k_psample_tail, grid_for(total), 256, 0, st, eps, x, z, cc, (unsigned long long)seed, total);
-    DDPM_CUDA_OK(cudaGetLastError());
+    if (!fused) {
+        const long long total = (long long)e.B * e.cfg.out_channels * e.H * e.W;
+        launch_k(k_psample_tail, grid_for(total), 256, 0, st, eps, x, z, cc, (unsigned long long)seed, total, pred_x0);
+        DDPM_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 int ddpm_opt_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, long long n,

@@ -67,6 +67,23 @@ __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint3
     return m;
 }
 
+// Sampler epilogue of the final conv (diffusion.py:107-158): when `ps.x` is set the gathered eps never reaches memory - the
+// thread that owns pixel (b, y, x) applies the alpha/beta update to its C_out values of x_t in place (same fp32 operation order
+// as k_psample_tail / the reference).
+struct PsampleEpi { float* x; const float* z; const float* coef; unsigned long long seed; float* pred; /* optional: clipped x0 prediction (p_sample_progressive) */ };
+__device__ __forceinline__ float psample_update(float xt, float eps, float zz, float c0, float c1, float c2, float c3, float nzsg, float* pred) {
+    float x0 = __fsub_rn(__fmul_rn(c0, xt), __fmul_rn(c1, eps));
+    x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    if (pred) *pred = x0;
+    const float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, xt));
+    return __fadd_rn(mean, __fmul_rn(nzsg, zz));
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t step, long long i) {
+    const uint4 r = philox4x32((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)seed ^ (step * 0x9E3779B1u), (uint32_t)(seed >> 32));
+    const float u1 = ((float)r.x + 1.f) * 2.3283064365386963e-10f, u2 = (float)r.y * 2.3283064365386963e-10f;
+    return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
 // ============================================================================ timestep embedding (functions.py:10-26)
 __global__ void k_timestep_embedding(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
     pdl_entry();
@@ -342,6 +359,63 @@ __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_pe
     }
 }
 
+// Small feature maps (H*W <= 64: the 4x4 / 8x8 levels, whose producers are split-K finalizers without a statistics epilogue):
+// ONE block per image computes the group statistics and applies the norm in the same launch (the image is 8-32 KB and is
+// re-read from L1/L2), instead of a statistics launch + an apply launch.  blockDim.x = (256/oct)*oct as for k_gn_apply.
+__global__ void __launch_bounds__(256) k_gn_small(const GnApply a) {
+    pdl_entry();
+    const int C = a.s.C0 + a.s.C1, oct = C >> 3, cg = C >> 5;
+    const int b = blockIdx.x;
+    __shared__ float sh[64];                      // [32][2]
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int o = threadIdx.x % oct, lp = threadIdx.x / oct, pstep = blockDim.x / oct;
+    const int c = o * 8;
+    const bool first = c < a.s.C0;
+    const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
+    const int sstride = first ? a.s.C0 : a.s.C1;
+    float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q = lp; q < a.HW; q += pstep) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { su[e] += f[e]; sq[e] = fmaf(f[e], f[e], sq[e]); }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const int g = (c + e) / cg; atomicAdd(&sh[2 * g], su[e]); atomicAdd(&sh[2 * g + 1], sq[e]); }
+    __syncthreads();
+    const float inv_n = 1.f / ((float)a.HW * (float)cg);
+    float sc[8], shf[8];
+    float* Kb = a.Kout + (long long)b * 4 * C + c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c + e) / cg;
+        const float m = sh[2 * g] * inv_n;
+        float var = sh[2 * g + 1] * inv_n - m * m; if (var < 0.f) var = 0.f;
+        const float r = rsqrtf(var + a.eps);
+        sc[e] = r * __ldg(a.gamma + c + e); shf[e] = __ldg(a.beta + c + e) - m * sc[e];
+        if (lp == 0) { Kb[e] = sc[e]; Kb[C + e] = shf[e]; Kb[2 * C + e] = r; Kb[3 * C + e] = m * r; }
+    }
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    bf16* dst = a.y + (long long)b * a.HW * C + c;
+    for (int q = lp; q < a.HW; q += pstep) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(src + (long long)q * sstride)), f);
+        uint32_t keep = 0xffu;
+        if (a.drop_p > 0.f) {
+            keep = dropout_keep8(a.seed, a.layer, (unsigned long long)(((long long)b * a.HW + q) * oct + o) * 8, a.drop_p);
+            if (a.mask) a.mask[((long long)b * a.HW + q) * oct + o] = (unsigned char)keep;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float y = fmaf(f[e], sc[e], shf[e]);
+            if (a.silu) y *= sigmoid_fast(y);
+            f[e] = ((keep >> e) & 1u) ? y * keep_scale : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst + (long long)q * C) = pack8(f);
+    }
+}
+
 // ---- backward of y = act(gn(x))*mask.  With dn = dy * mask * act'(y):
 //   pass 1 (reduce):  cs[b][c] = { sum_p dn , sum_p dn*xh }                      (per image, per channel; fp32 atomics)
 //   finalize:         S1[b,g] = sum_{c in g} gamma_c cs0 ; S2 = sum gamma_c cs1 ; dgamma_c += sum_b cs1 ; dbeta_c += sum_b cs0
@@ -356,10 +430,6 @@ struct GnBwd {
     const unsigned char* mask;    // keep bits saved by the forward pass (drop_p > 0)
     int* ticket;                  // [B] arrival counters (zeroed per pass): the last reduce block of an image runs the finalize
     int dn_inplace;               // reduce pass overwrites dy with dn = mask*dy*silu'(y); apply pass reads it back as-is
-    int fin_in_apply;             // the data-gradient conv's epilogue already stored dn and filled gs (gn_epilogue.cuh): there is
-                                  // no reduce pass; the apply pass folds the quad terms into P, Q in its prologue and
-                                  // accumulates dgamma / dbeta (per-channel sums of dn*xh / dn) on the fly
-    const float* gs;              // [B][C/4][2] {sum gamma*dn, sum gamma*dn*xh} per (image, quad)
 };
 __global__ void __launch_bounds__(256, 2) k_gn_bwd_reduce(const GnBwd a) {
     pdl_entry();   // grid (pixel blocks, B), blockDim.x = (256/oct)*oct
@@ -460,28 +530,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
     const float* PQb = a.PQ + (long long)b * 2 * C + c;
     float sc[8], sh[8], P[8], Q[8];
     ld8(Kb, sc); ld8(Kb + C, sh);
-    float rr[2] = {0.f, 0.f}, mr[2] = {0.f, 0.f};
-    if (a.fin_in_apply) {
-        // S1[g] = sum_{c in g} gamma*dn, S2[g] = sum gamma*dn*xh: whole quads of the dgrad epilogue's gs (C % 128 == 0)
-        const int cg = C >> 5, nq = cg >> 2;
-        const float* gsb = a.gs + (long long)b * (C >> 2) * 2;
-        const float* Kall = a.K + (long long)b * 4 * C;
-        const float inv_n = 1.f / ((float)a.HW * (float)cg);
-        float k2[2], k3[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ch0 = c + 4 * h, g = ch0 / cg;
-            if (h == 1 && c / cg == g) { k2[1] = k2[0]; k3[1] = k3[0]; rr[1] = rr[0]; mr[1] = mr[0]; continue; }
-            const float r = Kall[2 * C + ch0], m_r = Kall[3 * C + ch0];
-            float S1 = 0.f, S2 = 0.f;
-            for (int qd = g * nq; qd < (g + 1) * nq; ++qd) { S1 += gsb[2 * qd]; S2 += gsb[2 * qd + 1]; }
-            k2[h] = r * S1 * inv_n; k3[h] = r * S2 * inv_n; rr[h] = r; mr[h] = m_r;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { P[e] = k3[e >> 2] * rr[e >> 2]; Q[e] = k2[e >> 2] - k3[e >> 2] * mr[e >> 2]; }
-    } else {
-        ld8(PQb, P); ld8(PQb + C, Q);
-    }
+    ld8(PQb, P); ld8(PQb + C, Q);
     const bf16* src = first ? a.s.x0 + (long long)b * a.HW * a.s.C0 + c : a.s.x1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
     const int sstride = first ? a.s.C0 : a.s.C1;
     bf16* dst = first ? a.dx0 + (long long)b * a.HW * a.s.C0 + c : a.dx1 + (long long)b * a.HW * a.s.C1 + (c - a.s.C0);
@@ -490,7 +539,6 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
     const bf16* adp = a.addend ? a.addend + (long long)b * a.HW * C + c : nullptr;
     const unsigned char* mk = (a.drop_p > 0.f) ? a.mask + (long long)b * a.HW * oct + o : nullptr;
     float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float sdb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sdg[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // per-channel sums of dn and dn*xh (dbeta, dgamma)
     for (int pp = p0 + lp; pp < p1; pp += 2 * pstep) {
         uint4 ux[2], ud[2], ua[2], uo[2]; uint32_t kp[2] = {0xffu, 0xffu};
 #pragma unroll
@@ -523,7 +571,6 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
                 if (adp) v += ad[e];
                 if (acc) v += ov[e];
                 ov[e] = v; if (do_cs) cs[e] += v;
-                if (a.fin_in_apply) { sdb[e] += dn; sdg[e] = fmaf(dn, fmaf(x[e], rr[e >> 2], -mr[e >> 2]), sdg[e]); }
             }
             *reinterpret_cast<uint4*>(dst + (long long)q * sstride) = pack8(ov);
         }
@@ -539,16 +586,6 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
             if (cs_total) atomicAdd(cs_total + i, v);
             if (cs_total2) atomicAdd(cs_total2 + i, v);
         }
-    }
-    if (a.fin_in_apply) {      // block-level sums of dbeta / dgamma, then one atomic per channel and block
-        float* shg = shc + (do_cs ? C : 0);           // [2][C]
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shg[i] = 0.f;
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { atomicAdd(&shg[c + e], sdb[e]); atomicAdd(&shg[C + c + e], sdg[e]); }
-        __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(a.dbeta + i, shg[i]); atomicAdd(a.dgamma + i, shg[C + i]); }
     }
 }
 
@@ -732,10 +769,14 @@ __global__ void __launch_bounds__(256) k_wgrad_generic(const WgradG c) {
 // w layout: [Co][CI*9] fp32 (OIHW), out NHWC bf16.  CI <= 4, Co % 32 == 0.
 // lane <-> pixel (two pixels per lane, 64 per warp); output channels are produced 32 at a time with the weights fetched as
 // warp-broadcast 16-byte shared-memory reads, so one fetch feeds 64 pixels (the per-octet version was shared-memory bound).
+// q_sample prologue (diffusion.py:92-97): with `noise` set, the kernel's input is x_t = sqrt_ab[t_b]*x + sqrt_1mab[t_b]*noise,
+// formed while the taps are loaded (same two multiplies + add as the reference); the centre tap also stores x_t to `xt_out`
+// (the weight gradient of this conv needs it in the backward pass).
+struct QsamplePro { const float* noise; const long long* t; const float* tab_a; const float* tab_s; float* xt_out; };
 template <int CI>
 __global__ void __launch_bounds__(128) k_in_conv(const float* __restrict__ x, const float* __restrict__ w,
                                                 const float* __restrict__ bias, bf16* __restrict__ out,
-                                                int B, int H, int W, int Co) {
+                                                int B, int H, int W, int Co, double* qstats, const QsamplePro qp) {
     pdl_entry();
     extern __shared__ float sw[];                 // [CI*9][Co] + [Co]
     constexpr int K = CI * 9;
@@ -753,12 +794,23 @@ __global__ void __launch_bounds__(128) k_in_conv(const float* __restrict__ x, co
             pix[u] = base + u * 32 + lane;
             const bool pv = pix[u] < P;
             const int b = pv ? (int)(pix[u] / (H * W)) : 0, r = pv ? (int)(pix[u] % (H * W)) : 0, y = r / W, xx = r % W;
+            float qa = 1.f, qs_ = 0.f;
+            if (qp.noise && pv) { const long long tb = qp.t[b]; qa = __ldg(qp.tab_a + tb); qs_ = __ldg(qp.tab_s + tb); }
 #pragma unroll
             for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
-                    in[u][ci * 9 + t] = (pv && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + (((long long)b * CI + ci) * H + iy) * W + ix) : 0.f;
+                    float v = 0.f;
+                    if (pv && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                        const long long j = (((long long)b * CI + ci) * H + iy) * W + ix;
+                        v = __ldg(x + j);
+                        if (qp.noise) {
+                            v = __fadd_rn(__fmul_rn(qa, v), __fmul_rn(qs_, __ldg(qp.noise + j)));
+                            if (t == 4) qp.xt_out[j] = v;
+                        }
+                    }
+                    in[u][ci * 9 + t] = v;
                 }
         }
         for (int c0 = 0; c0 < Co; c0 += 32) {
@@ -775,6 +827,15 @@ __global__ void __launch_bounds__(128) k_in_conv(const float* __restrict__ x, co
                     acc[0][j4 * 4 + 2] = fmaf(v0, wv.z, acc[0][j4 * 4 + 2]); acc[0][j4 * 4 + 3] = fmaf(v0, wv.w, acc[0][j4 * 4 + 3]);
                     acc[1][j4 * 4] = fmaf(v1, wv.x, acc[1][j4 * 4]); acc[1][j4 * 4 + 1] = fmaf(v1, wv.y, acc[1][j4 * 4 + 1]);
                     acc[1][j4 * 4 + 2] = fmaf(v1, wv.z, acc[1][j4 * 4 + 2]); acc[1][j4 * 4 + 3] = fmaf(v1, wv.w, acc[1][j4 * 4 + 3]);
+                }
+            }
+            if (qstats) {      // GroupNorm statistics of the output (gn_epilogue.cuh): H*W % 32 == 0, so a warp's 32 pixels share an image
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const long long p0w = base + u * 32;                     // warp-uniform
+                    if (p0w >= P) continue;
+                    const int nimg = (int)(p0w / (H * W));
+                    epi_quad_stats(acc[u], pix[u] < P, qstats + ((long long)nimg * (Co >> 2) + (c0 >> 2)) * 2, lane);
                 }
             }
 #pragma unroll
@@ -1100,23 +1161,15 @@ __global__ void k_nchw_f32_to_nhwc_bf16(const float* __restrict__ src, bf16* __r
 //   coef[5] = nonzero flag (t>0) as float, coef[6] = step index (for the built-in noise stream)
 //   z == nullptr and seed != 0: the noise is drawn in-kernel (Philox4x32-10 + Box-Muller; NOT torch's stream)
 __global__ void k_psample_tail(const float* __restrict__ eps, float* __restrict__ x /*in: x_t, out: x_{t-1}*/, const float* __restrict__ z,
-                               const float* __restrict__ coef, unsigned long long seed, long long total) {
+                               const float* __restrict__ coef, unsigned long long seed, long long total, float* pred) {
     pdl_entry();
-    const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], sg = coef[4], nz = coef[5];
+    const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], nzsg = __fmul_rn(coef[5], coef[4]);
     const uint32_t step = (uint32_t)coef[6];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const float xt = x[i];
-        float x0 = __fsub_rn(__fmul_rn(c0, xt), __fmul_rn(c1, eps[i]));
-        x0 = fminf(fmaxf(x0, -1.f), 1.f);
-        const float mean = __fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, xt));
         float zz = 0.f;
         if (z) zz = z[i];
-        else if (seed) {
-            const uint4 r = philox4x32((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)seed ^ (step * 0x9E3779B1u), (uint32_t)(seed >> 32));
-            const float u1 = ((float)r.x + 1.f) * 2.3283064365386963e-10f, u2 = (float)r.y * 2.3283064365386963e-10f;
-            zz = sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
-        }
-        x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sg), zz));
+        else if (seed) zz = philox_normal(seed, step, i);
+        x[i] = psample_update(x[i], eps[i], zz, c0, c1, c2, c3, nzsg, pred ? pred + i : nullptr);
     }
 }
 // generate.py:129  (x * 127.5 + 127.5).round().clamp(0, 255).to(uint8).permute(0, 2, 3, 1): NCHW fp32 -> NHWC uint8.
@@ -1197,9 +1250,11 @@ __global__ void k_unpack_tap(const float* __restrict__ S, float* __restrict__ gw
 }
 template <int CO>
 __global__ void __launch_bounds__(256) k_out_gather(const float* __restrict__ T /*[P][32]*/, const float* __restrict__ bias, float* __restrict__ out /*NCHW*/,
-                                                   int B, int H, int W) {
+                                                   int B, int H, int W, const PsampleEpi ps) {
     pdl_entry();
     const long long P = (long long)B * H * W;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, nzsg = 0.f; uint32_t step = 0;
+    if (ps.x) { c0 = ps.coef[0]; c1 = ps.coef[1]; c2 = ps.coef[2]; c3 = ps.coef[3]; nzsg = __fmul_rn(ps.coef[5], ps.coef[4]); step = (uint32_t)ps.coef[6]; }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W), y = (int)((i / W) % H); const long long b = i / ((long long)W * H);
         float acc[CO];
@@ -1212,6 +1267,17 @@ __global__ void __launch_bounds__(256) k_out_gather(const float* __restrict__ T 
             const float* r = T + ((b * H + yy) * W + xx) * 32 + t * CO;
 #pragma unroll
             for (int co = 0; co < CO; ++co) acc[co] += __ldg(r + co);
+        }
+        if (ps.x) {
+#pragma unroll
+            for (int co = 0; co < CO; ++co) {
+                const long long j = ((b * CO + co) * H + y) * W + x;
+                float zz = 0.f;
+                if (ps.z) zz = ps.z[j];
+                else if (ps.seed) zz = philox_normal(ps.seed, step, j);
+                ps.x[j] = psample_update(ps.x[j], acc[co], zz, c0, c1, c2, c3, nzsg, ps.pred ? ps.pred + j : nullptr);
+            }
+            continue;
         }
 #pragma unroll
         for (int co = 0; co < CO; ++co) out[((b * CO + co) * H + y) * W + x] = acc[co];

@@ -63,7 +63,7 @@ struct GemmParams {
     int rowvec_ld, rows_per_vec;
     const __nv_bfloat16* residual; int ldr;   // [M][ldr] or null
     float alpha;
-    GnEpi gn; int gn_hw;      // KK: GroupNorm epilogue fusions (gn_epilogue.cuh); rows are NHWC pixels, gn_hw = H*W (multiple of 32)
+    GnEpi gn; int gn_hw;      // KK: GroupNorm statistics of the output (gn_epilogue.cuh); rows are NHWC pixels, gn_hw = H*W (multiple of 32)
 };
 
 // A pipeline stage holds KSTEPS K-slabs of 64 (KSTEPS x {A 16 KB, B BLOCK_N x 128 B}).  One producer/consumer handshake costs
@@ -364,26 +364,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         f[2 * e] += t2.x; f[2 * e + 1] += t2.y;
                     }
                 }
-                if (MODE == GEMM_KK) {
-                    // GroupNorm fusions (warp-uniform: the 32 rows of a warp lie in one image, M % 32 == 0)
-                    const int n_img = (row_ok && (p.gn.qstats || p.gn.K)) ? row / p.gn_hw : 0;
-                    if (p.gn.qstats) epi_quad_stats(f, row_ok, p.gn.qstats + ((long long)n_img * (p.N >> 2) + (col >> 2)) * 2, lane);
-                    if (p.gn.K) {
-                        const int gnC = p.gn.C0 + p.gn.C1;
-                        uint32_t rs[16]; uint32_t keep = 0xffffffffu;
-                        if (row_ok) {
-                            const __nv_bfloat16* xp = col < p.gn.C0 ? p.gn.x0 + (long long)row * p.gn.C0 + col : p.gn.x1 + (long long)row * p.gn.C1 + (col - p.gn.C0);
-                            ld_row64B(xp, rs);
-                            if (p.gn.mask) keep = __ldg(reinterpret_cast<const unsigned int*>(p.gn.mask + (long long)row * (gnC >> 3) + (col >> 3)));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) rs[e] = 0u;
-                        }
-                        const float* Kn = p.gn.K + (long long)n_img * 4 * p.N + col;
-                        float* gsd = p.gn.gs + ((long long)n_img * (p.N >> 2) + (col >> 2)) * 2;
-                        if (p.gn.mask) epi_gn_bwd<false, true>(f, row_ok, rs, keep, p.gn.keep_scale, p.gn.silu, 0u, 0, Kn, Kn + p.N, p.gn.gamma + col, p.gn.beta + col, gsd, lane);
-                        else           epi_gn_bwd<false, false>(f, row_ok, rs, keep, p.gn.keep_scale, p.gn.silu, 0u, 0, Kn, Kn + p.N, p.gn.gamma + col, p.gn.beta + col, gsd, lane);
-                    }
+                if (MODE == GEMM_KK && p.gn.qstats) {
+                    // GroupNorm statistics of the output (warp-uniform: the 32 rows of a warp lie in one image, M % 32 == 0;
+                    // with the output-row scatter of the sub-pixel convs the image index is still that of the A-grid row)
+                    const int n_img = row_ok ? row / p.gn_hw : 0;
+                    epi_quad_stats(f, row_ok, p.gn.qstats + ((long long)n_img * (p.N >> 2) + (col >> 2)) * 2, lane);
                 }
                 if (tma_out && NGRP == 2) {
                     // registers -> 128B-swizzled staging slab (row r, 16-byte chunk j at physical chunk j ^ (r & 7))

@@ -20,9 +20,6 @@ struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t
 enum { OP_TEMB = 1 };
 struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; int tag = 0; };
 struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; unsigned char* mask; };
-// backward of one GroupNorm, planned BEFORE the data-gradient conv that produces dy so that the conv's epilogue can take over
-// the reduce pass (gn_epilogue.cuh); `fused` is set by conv_op when the chosen kernel supports it
-struct GnBwdPlan { GnSaved sv; float* cs = nullptr; bool fused = false; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
 static inline int oct_threads(int C) { const int oct = C / 8; return oct <= 256 ? (256 / oct) * oct : 0; }
@@ -133,10 +130,9 @@ struct UnetEngine {
         const bf16* wp = nullptr; long long ldw = 0; bool has_skip = false; Src skip_in;
         const float* bias = nullptr; const float* rowvec = nullptr; int rowvec_ld = 0; const bf16* residual = nullptr;
         T4 out; float* out_nchw = nullptr; int Co = 0; int Ho = 0, Wo = 0; bool accumulate = false;
-        bool want_qstats = false;          // forward: the output feeds a GroupNorm -> statistics in the epilogue when the kernel can
-        GnBwdPlan* gnb = nullptr;          // backward: the output is dy of this GroupNorm -> dn + column sums in the epilogue
+        bool want_qstats = false;          // the output feeds a GroupNorm -> statistics in the epilogue when the kernel can
     };
-    // epilogue fusions of a conv: fills `gn` and returns the workspace offset of the quad statistics (-1: none)
+    // epilogue fusion of a conv: fills `gn` and returns the workspace offset of the quad statistics (-1: none)
     long long conv_gn_epi(const ConvSpec& c, ddpm_gn_epi& gn) {
         memset(&gn, 0, sizeof gn);
         long long qs = -1;
@@ -146,19 +142,6 @@ struct UnetEngine {
         if (c.want_qstats && c.Co % 32 == 0 && HW % 32 == 0) {
             qs = (long long)zero_fwd((size_t)Bn * (c.Co / 4) * 2 * 8);
             gn.qstats = at<double>((size_t)qs);
-        }
-        if (c.gnb && HW % 32 == 0) {
-            const GnSaved& sv = c.gnb->sv;
-            const int C = sv.in.C();
-            // C % 128 == 0: groups are whole 4-channel quads (the apply prologue folds the column sums quad-wise)
-            if (C == c.Co && C % 128 == 0 && sv.in.t0.C % 32 == 0 && (!sv.in.two || sv.in.t1.C % 32 == 0)) {
-                gn.gnb_x0 = bp(sv.in.t0); gn.gnb_C0 = sv.in.t0.C;
-                gn.gnb_x1 = sv.in.two ? bp(sv.in.t1) : nullptr; gn.gnb_C1 = sv.in.two ? sv.in.t1.C : 0;
-                gn.gnb_K = sv.K; gn.gnb_gamma = sv.gamma; gn.gnb_beta = sv.beta; gn.gnb_silu = sv.silu;
-                gn.gnb_gs = c.gnb->cs;              // the [B][2][C] column-sum area doubles as the [B][C/4][2] quad-term area
-                gn.gnb_mask = sv.mask; gn.gnb_keep_scale = sv.drop_p > 0.f ? 1.f / (1.f - sv.drop_p) : 1.f;
-                c.gnb->fused = true;
-            }
         }
         return qs;
     }
@@ -195,12 +178,6 @@ struct UnetEngine {
             if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return qs; }
             HaloLaunch g; int rc = build_halo(h, g);
             if (rc) { plan_error = rc; return qs; }
-            if (g.p.gn.mask) {          // dropout is armed per call by a non-zero seed (eval / p = 0 runs see all-ones masks)
-                UnetEngine* self = this;
-                push(L, c.name + "[halo]", fl, [g, self](cudaStream_t st) {
-                    if (self->drop_seed) return launch_halo(g, st);
-                    HaloLaunch gg = g; gg.p.gn.mask = nullptr; gg.p.gn.keep_scale = 1.f; return launch_halo(gg, st); });
-            } else
             push(L, c.name + "[halo]", fl, [g](cudaStream_t st) { return launch_halo(g, st); });
             return qs;
         }
@@ -261,12 +238,6 @@ struct UnetEngine {
             if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return qs; }
             GemmLaunch g; int rc = build_gemm(d, g);
             if (rc) { plan_error = rc; return qs; }
-            if (g.p.gn.mask) {
-                UnetEngine* self = this;
-                push(L, c.name, fl, [g, self](cudaStream_t st) {
-                    if (self->drop_seed) return launch_gemm(g, st);
-                    GemmLaunch gg = g; gg.p.gn.mask = nullptr; gg.p.gn.keep_scale = 1.f; return launch_gemm(gg, st); });
-            } else
             push(L, c.name, fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
             return qs;
         }
@@ -290,6 +261,9 @@ struct UnetEngine {
         return -1;
     }
     float* eps_dst = nullptr;   // run-time destination of the final conv (caller buffer or internal eps buffer)
+    PsampleEpi ps_epi = {nullptr, nullptr, nullptr, 0, nullptr};   // run-time: sampler update fused into the final gather (x != null)
+    QsamplePro qs_pro = {};           // run-time: q_sample fused into in_conv's loads (ddpm_train_forward)
+    bool gather_fused_tail = false;   // plan property: the final conv ends in k_out_gather (tensor-core out_conv path)
     const float* deps_src = nullptr;   // run-time d(loss)/d(eps), fp32 NCHW (caller buffer or internal buffer)
     int plan_error = 0;
 
@@ -392,6 +366,15 @@ struct UnetEngine {
                 launch_k(k_gn_apply, g2, thr, 0, st, aa, ppb2); return (int)cudaGetLastError(); });
             return sv;
         }
+        if (HW <= 64 && !getenv("DDPM_NO_GN_EPI")) {       // tiny maps: statistics + apply in ONE launch, one block per image
+            GnApply a; memset(&a, 0, sizeof a);
+            a.s = gs; a.K = K; a.y = bp(out); a.HW = HW; a.silu = silu; a.drop_p = sv.drop_p; a.seed = 0; a.layer = sv.layer; a.mask = sv.mask;
+            a.gamma = ga; a.beta = be; a.eps = 1e-6f; a.Kout = K;
+            UnetEngine* self = this;
+            push(L, name + ".small", 0, [a, Bn, thr, self](cudaStream_t st) { GnApply aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
+                launch_k(k_gn_small, Bn, thr, 0, st, aa); return (int)cudaGetLastError(); });
+            return sv;
+        }
         static const int st_occ = getenv("DDPM_GN_STATS_OCC") ? atoi(getenv("DDPM_GN_STATS_OCC")) : 4;
         static const int ap_occ = getenv("DDPM_GN_APPLY_OCC") ? atoi(getenv("DDPM_GN_APPLY_OCC")) : 4;
         int nblk, ppb; gn_grid(Bn, HW, st_occ, nblk, ppb);
@@ -409,21 +392,14 @@ struct UnetEngine {
             launch_k(k_gn_apply, g2, thr, 0, st, aa, ppb2); return (int)cudaGetLastError(); });
         return sv;
     }
-    // call BEFORE the data-gradient conv that produces dy; pass the plan to that conv (ConvSpec::gnb) and then to gn_bwd
-    GnBwdPlan gn_bwd_plan(const GnSaved& sv) {
-        GnBwdPlan p; p.sv = sv;
-        p.cs = at<float>(zero_bwd((size_t)sv.in.t0.B * 2 * sv.in.C() * 4));
-        return p;
-    }
     // dx(in) (=|+=) gn_bwd(dy) + addend ; dgamma/dbeta accumulate into the flat grads
-    void gn_bwd(const std::string& name, const GnBwdPlan& gp, const T4& dy, const bf16* addend,
+    void gn_bwd(const std::string& name, const GnSaved& sv, const T4& dy, const bf16* addend,
                 float* cs_per_img = nullptr, int cs_ld = 0, float* cs_total = nullptr, float* cs_total2 = nullptr) {
-        const GnSaved& sv = gp.sv;
         const Src& in = sv.in;
         const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
         GnBwd a; memset(&a, 0, sizeof a);
         a.s = gsrc(in); a.dy = bp(dy); a.K = sv.K; a.gamma = sv.gamma;
-        a.cs = gp.cs; a.gs = gp.cs; a.PQ = at<float>(alloc((size_t)Bn * 2 * C * 4));
+        a.cs = at<float>(zero_bwd((size_t)Bn * 2 * C * 4)); a.PQ = at<float>(alloc((size_t)Bn * 2 * C * 4));
         a.dgamma = sv.dgamma; a.dbeta = sv.dbeta;
         bool f0 = true, f1 = true;
         const T4 g0 = grad_of(in.t0, &f0); a.dx0 = bp(g0); a.acc0 = f0 ? 0 : 1;
@@ -443,16 +419,6 @@ struct UnetEngine {
         const size_t shm = (size_t)2 * C * 4;
         const size_t shm2 = (cs_per_img || cs_total || cs_total2) ? (size_t)C * 4 : 0;
         UnetEngine* self = this;
-        if (gp.fused) {     // dy already holds dn and cs is complete: ONE pass (prologue = finalize)
-            a.dn_inplace = 1; a.fin_in_apply = 1;
-            const size_t shm3 = shm2 + (size_t)2 * C * 4;      // + block-level dbeta / dgamma sums
-            push(bwd_ops, name + ".gn_bwd[epi]", 0, [=](cudaStream_t st) {
-                GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
-                if (shm2) launch_k(k_gn_bwd_apply<true>, g1, thr, shm3, st, aa, cs_per_img, cs_ld, cs_total, cs_total2);
-                else      launch_k(k_gn_bwd_apply<false>, g1, thr, shm3, st, aa, cs_per_img, cs_ld, cs_total, cs_total2);
-                return (int)cudaGetLastError(); }, 1);
-            return;
-        }
         push(bwd_ops, name + ".gn_bwd", 0, [=](cudaStream_t st) {
             GnBwd aa = a; aa.seed = self->drop_seed; if (!aa.seed) aa.drop_p = 0.f;
             launch_k(k_gn_bwd_reduce, g1, thr, shm, st, aa);

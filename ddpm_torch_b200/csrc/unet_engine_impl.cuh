@@ -88,9 +88,8 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
         const T4 dOut = grad_of(out, nullptr);
         colsum_op(p + ".conv2.bias", dOut, nullptr, 0, GP(p + ".conv2.bias"), has_skip ? GP(p + ".skip.bias") : nullptr, cout);
         T4 d_a2 = newT(Bn, h, w, cout);
-        GnBwdPlan p2 = gn_bwd_plan(g2);             // norm2's reduce pass rides in conv2.dgrad's epilogue when that kernel can
         { ConvSpec c; c.name = p + ".conv2.dgrad"; c.in = one(dOut); c.wp = w2.dgr; c.ldw = w2.ld_d; c.out = d_a2; c.Co = cout; c.Ho = h; c.Wo = w;
-          c.gnb = &p2; conv_op(bwd_ops, c, &bwd_flops); }
+          conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".conv2.wgrad", dOut, one(a2), 3, 1, MAP_NORMAL, GP(p + ".conv2.weight"), cout);
         T4 dxs;
         if (has_skip) {
@@ -101,14 +100,13 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
         }
         // the column sums of d_h1 (bias gradients of conv1 / fc and the per-image timestep-projection gradient) are
         // accumulated by the same kernel that produces d_h1
-        gn_bwd(p + ".norm2", p2, d_a2, nullptr, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"));
+        gn_bwd(p + ".norm2", g2, d_a2, nullptr, dTP + tp_off, tp_ld, GP(p + ".conv1.bias"), GP(p + ".fc.bias"));
         const T4 d_h1 = grad_of(h1, nullptr);
         T4 d_a1 = newT(Bn, h, w, cin);
-        GnBwdPlan p1 = gn_bwd_plan(g1);
         { ConvSpec c; c.name = p + ".conv1.dgrad"; c.in = one(d_h1); c.wp = w1.dgr; c.ldw = w1.ld_d; c.out = d_a1; c.Co = cin; c.Ho = h; c.Wo = w;
-          c.gnb = &p1; conv_op(bwd_ops, c, &bwd_flops); }
+          conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".conv1.wgrad", d_h1, one(a1), 3, 1, MAP_NORMAL, GP(p + ".conv1.weight"), cout);
-        gn_bwd(p + ".norm1", p1, d_a1, has_skip ? bp(dxs) : bp(dOut));
+        gn_bwd(p + ".norm1", g1, d_a1, has_skip ? bp(dxs) : bp(dOut));
     });
     return out;
 }
@@ -156,11 +154,10 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
         bmm(bwd_ops, p + ".dK", 2, dS, T, (long long)T * T, q, ldq, sq, dq + C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         colsum_op(p + ".project_in.bias", dqkv, nullptr, 0, GP(p + ".project_in.bias"), nullptr, 3 * C);
         T4 dxn = newT(Bn, h, w, C);
-        GnBwdPlan pn = gn_bwd_plan(g);
         { ConvSpec c; c.name = p + ".project_in.dgrad"; c.in = one(dqkv); c.ksize = 1; c.wp = win.dgr; c.ldw = win.ld_d; c.out = dxn; c.Co = C; c.Ho = h; c.Wo = w;
-          c.gnb = &pn; conv_op(bwd_ops, c, &bwd_flops); }
+          conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".project_in.wgrad", dqkv, one(xn), 1, 1, MAP_NORMAL, GP(p + ".project_in.weight"), 3 * C);
-        gn_bwd(p + ".norm", pn, dxn, bp(dY));
+        gn_bwd(p + ".norm", g, dxn, bp(dY));
     });
     return out;
 }
@@ -244,7 +241,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     B = B_; H = H_; W = W_; train = train_; dry = dry_;
     cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); grads.clear(); once_list.clear();
     tp_table_host.clear(); tp_uni_table_host.clear(); fc_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
-    layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0;
+    layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0; gather_fused_tail = false;
     const size_t zf_total = zf_cursor, zb_total = zb_cursor;   // sizes learned by the preceding dry pass
     zf_cursor = zb_cursor = 0;
     zero_fwd_bytes = dry ? 0 : zf_total; zero_bwd_bytes = dry ? 0 : zb_total;
@@ -431,12 +428,16 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         const float* wi = PP("in_conv.weight"); const float* bi = PP("in_conv.bias"); bf16* o = bp(h0);
         const size_t shm = (size_t)(ch * Cin * 9 + ch) * 4; const int n = grid_for((long long)B * H * W / 2, 128);
         const int Bn = B, Hn = H, Wn = W;
+        // h0 feeds the first norm1 and (as the last skip) the final up block's norm1: its statistics come out of this kernel
+        double* qs0 = nullptr;
+        if (ch % 32 == 0 && (H * W) % 32 == 0 && !getenv("DDPM_NO_GN_EPI")) { h0.qs = (long long)zero_fwd((size_t)B * (ch / 4) * 2 * 8); qs0 = at<double>((size_t)h0.qs); }
         push(fwd_ops, "in_conv", 2.0 * B * H * W * ch * Cin * 9, [=](cudaStream_t st) {
+            const QsamplePro qp = self->qs_pro;       // training: x_t = q_sample(x0, t, noise) is formed while the taps are loaded
             switch (Cin) {
-                case 1: launch_k(k_in_conv<1>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                case 2: launch_k(k_in_conv<2>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                case 3: launch_k(k_in_conv<3>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
-                default: launch_k(k_in_conv<4>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch); break;
+                case 1: launch_k(k_in_conv<1>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch, qs0, qp); break;
+                case 2: launch_k(k_in_conv<2>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch, qs0, qp); break;
+                case 3: launch_k(k_in_conv<3>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch, qs0, qp); break;
+                default: launch_k(k_in_conv<4>, n, 128, shm, st, self->x_in, wi, bi, o, Bn, Hn, Wn, ch, qs0, qp); break;
             }
             return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
@@ -542,11 +543,12 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 if (rc) return rc;
                 push(fwd_ops, "out_conv.2", fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
             } else push(fwd_ops, "out_conv.2", fl, [](cudaStream_t) { return 0; });
+            gather_fused_tail = true;             // the sampler's alpha/beta update rides in this kernel (ddpm_sampler_step)
             push(fwd_ops, "out_conv.2.gather", 0, [=](cudaStream_t st) {
                 switch (Cout) {
-                    case 1: launch_k(k_out_gather<1>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn); break;
-                    case 2: launch_k(k_out_gather<2>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn); break;
-                    default: launch_k(k_out_gather<3>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn); break;
+                    case 1: launch_k(k_out_gather<1>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn, self->ps_epi); break;
+                    case 2: launch_k(k_out_gather<2>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn, self->ps_epi); break;
+                    default: launch_k(k_out_gather<3>, nblk, 256, 0, st, T, bo, self->eps_dst, Bn, Hn, Wn, self->ps_epi); break;
                 }
                 return (int)cudaGetLastError(); });
         } else
@@ -565,7 +567,6 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             tape.push_back([=]() {
                 float* gw = GP("out_conv.2.weight"); float* gb = GP("out_conv.2.bias");
                 T4 d_a = newT(B, H, W, ch);
-                GnBwdPlan po = gn_bwd_plan(g);
                 bf16* dap = bp(d_a);
                 const size_t shm2 = (size_t)(ch * Cout * 9 + ch) * 4; const int n2 = grid_for((long long)Bn * Hn * Wn / 2, 128);
                 const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
@@ -587,7 +588,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                         return (int)cudaGetLastError(); }, 2);
                     ConvSpec cs; cs.name = "out_conv.2.dgrad"; cs.in = one(E); cs.ksize = 1; cs.wp = w27t; cs.ldw = 64;
                     cs.out = d_a; cs.Co = ch; cs.Ho = H; cs.Wo = W;
-                    cs.gnb = &po; conv_op(bwd_ops, cs, nullptr);
+                    conv_op(bwd_ops, cs, nullptr);
                     float* S = at<float>(zero_bwd((size_t)64 * ch * 4));
                     wgrad_op("out_conv.2.wgrad", E, one(a_out), 1, 1, MAP_NORMAL, S, 64);
                     const int nun = (Cout * ch * 9 + 255) / 256;
@@ -597,17 +598,17 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                     const float* de = self->deps_src;
                     launch_k(k_chansum_nchw, dim3(64, Cout), 256, 0, st, de, gb, Bn, Cout, Hn * Wn);
                     switch (Cout) {
-                        case 1: launch_k(k_in_conv<1>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        case 1: launch_k(k_in_conv<1>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch, (double*)nullptr, QsamplePro{});
                                 launch_k(k_corr3x3<1>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        case 2: launch_k(k_in_conv<2>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        case 2: launch_k(k_in_conv<2>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch, (double*)nullptr, QsamplePro{});
                                 launch_k(k_corr3x3<2>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        case 3: launch_k(k_in_conv<3>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        case 3: launch_k(k_in_conv<3>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch, (double*)nullptr, QsamplePro{});
                                 launch_k(k_corr3x3<3>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
-                        default: launch_k(k_in_conv<4>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch);
+                        default: launch_k(k_in_conv<4>, n2, 128, shm2, st, de, wt, nullptr, dap, Bn, Hn, Wn, ch, (double*)nullptr, QsamplePro{});
                                 launch_k(k_corr3x3<4>, nb, ch, 0, st, ap, de, gw, 9, (long long)ch * 9, 1, 1, nullptr, Bn, Hn, Wn, ch, ppb); break;
                     }
                     return (int)cudaGetLastError(); }, 3);
-                gn_bwd("out_conv.0", po, d_a, nullptr);
+                gn_bwd("out_conv.0", g, d_a, nullptr);
             });
         }
     }
@@ -623,13 +624,13 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         if (!unpack_table_host.empty()) {
             const PackEntry* tab = at<PackEntry>(unpack_table_off); const int n = (int)unpack_table_host.size();
             // on the side stream too: ordered after every wgrad GEMM there; the list's final join publishes the flat gradients
-            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(32, n), 256, 0, st, tab); return (int)cudaGetLastError(); }, 1, true);
+            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(128, n), 256, 0, st, tab); return (int)cudaGetLastError(); }, 1, true);
         }
     }
     pack_table_off = alloc(sizeof(PackEntry) * (pack_table_host.size() + 1));
     if (!pack_table_host.empty()) {
         const PackEntry* tab = at<PackEntry>(pack_table_off); const int n = (int)pack_table_host.size();
-        push(pack_ops, "pack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(32, n), 256, 0, st, tab); return (int)cudaGetLastError(); });
+        push(pack_ops, "pack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(128, n), 256, 0, st, tab); return (int)cudaGetLastError(); });
     }
     if (plan_error) return plan_error;
     return 0;

@@ -210,13 +210,40 @@ class GaussianDiffusion:
 
     @torch.inference_mode()
     def p_sample_progressive(self, denoise_fn, shape, device=torch.device("cpu"), noise=None, pred_freq=10, seed=None):
+        """diffusion.py:176-198.  Native path: every step is the engine's sampler step, which also writes the clipped x_0
+        prediction (ddpm_sampler_step_pred); predictions are copied out every ``pred_freq`` steps exactly as the reference does."""
         B = (shape or noise.shape)[0]
-        t = torch.empty(B, dtype=torch.int64, device=device)
         gen = torch.Generator(device).manual_seed(seed) if seed is not None else None
         x_t = torch.empty(shape, device=device).normal_(generator=gen) if noise is None else noise.to(device)
         n = self.timesteps // pred_freq
         preds = torch.zeros((n, B) + tuple(shape[1:]), dtype=torch.float32)
         idx = n
+        model = self._fast_ok(denoise_fn)
+        if model is not None and x_t.is_cuda:
+            L = _lib.lib()
+            dev = model.flat_params.device
+            x_t = x_t.contiguous().float().clone()
+            _, _, H, W = x_t.shape
+            was_training = model.training
+            model.eval()
+            try:
+                with torch.cuda.device(dev):
+                    h = model.prepare(B, H, W, training=False, force_repack=True)
+                    coef, tmod = self._coef_rows(), self._model_timesteps().contiguous()
+                    _lib.check(L.ddpm_sampler_setup(h, coef.shape[0], tmod.data_ptr(), coef.data_ptr()), "sampler_setup")
+                    _lib.check(L.ddpm_sampler_reset(h, self.timesteps - 1, _lib.stream_ptr(dev)), "sampler_reset")
+                    z, pred = torch.empty_like(x_t), torch.empty_like(x_t)
+                    for ti in range(self.timesteps - 1, -1, -1):
+                        z.normal_(generator=gen)
+                        _lib.check(L.ddpm_sampler_step_pred(h, x_t.data_ptr(), z.data_ptr(), 0, pred.data_ptr(), _lib.stream_ptr(dev)), "sampler_step")
+                        if (ti + 1) % pred_freq == 0:
+                            idx -= 1
+                            preds[idx] = pred.cpu()
+            finally:
+                if was_training:
+                    model.train()
+            return x_t.cpu(), preds
+        t = torch.empty(B, dtype=torch.int64, device=device)
         fn = self._wrap_denoise(denoise_fn, device)
         for ti in range(self.timesteps - 1, -1, -1):
             t.fill_(ti)
@@ -342,7 +369,8 @@ def _ddp_allreduce(wrapper, model):
 
 
 def _native_sample_loop(diffusion, model, x, gen, rng, seed, use_graph, split=None):
-    """T sampler steps on the engine: per step {prep, UNet forward, alpha/beta tail}; captured once, replayed T times.
+    """T sampler steps on the engine: per step {noise draw, step-table fetch, UNet forward with the alpha/beta update in the final
+    conv's epilogue}; captured once, replayed T times - one graph launch per timestep.
 
     ``split=2`` (opt-in; DDPM_SAMPLER_SPLIT overrides the default of 1 - measured on B200 at bs=256: 5.46 vs 5.47 ms per step, no gain, since half-batch kernels are less efficient): the batch is cut into two
     halves with their own plans, run on two forked streams inside the SAME captured graph, so that one half's HBM-bound
@@ -402,29 +430,35 @@ def _native_sample_loop_on_device(diffusion, model, x, gen, rng, seed, use_graph
         for s_ in forks:
             cur.wait_stream(s_)
 
+    def draw():
+        if z is not None:
+            z.normal_(generator=gen)            # diffusion.py:155 - the reference's stream, drawn on the device
+
     graph = None
     if use_graph:
-        # warm the allocator-free path once outside capture (step 0 of the loop), then capture one step
-        if z is not None:
-            z.normal_(generator=gen)
+        # ONE graph launch per timestep: the captured step holds the noise draw (the generator is registered with the graph, so
+        # every replay advances its Philox offset exactly like an eager normal_ call), the step-table fetch, the UNet forward and
+        # the alpha/beta update fused into the final conv's gather.  Step 0 runs eagerly (allocator warm-up), then one step is
+        # captured and replayed for every remaining timestep.
+        draw()
         step()
         done = 1
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
         if done < S:
+            graph = torch.cuda.CUDAGraph()
+            if gen is not None and z is not None:
+                graph.register_generator_state(gen)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 with torch.cuda.graph(graph, stream=side):
+                    draw()
                     step()
             torch.cuda.current_stream().wait_stream(side)
             # capture does not execute: the captured step is replayed below for every remaining timestep
             for _ in range(done, S):
-                if z is not None:
-                    z.normal_(generator=gen)
                 graph.replay()
     else:
         for _ in range(S):
-            if z is not None:
-                z.normal_(generator=gen)
+            draw()
             step()
     return x

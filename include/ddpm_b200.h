@@ -30,22 +30,11 @@ int ddpm_runtime_check(void);
 /* Device-side error flag set by a bounded wait that timed out inside a kernel (0 = none). Synchronises. */
 int ddpm_device_error_flag(void);
 
-/* Optional GroupNorm fusions of a conv / GEMM epilogue (nn.GroupNorm(32, C, eps=1e-6) + SiLU + Dropout of unet.py:18-20,
- * 83-89; csrc/gn_epilogue.cuh).  All-zero = off.
- *  qstats   forward: the producer adds per (image, 4-channel quad) {sum, sum of squares} of its OUTPUT to qstats[NB][N/4][2]
- *           (fp64 atomics, caller zeroes it) - the statistics pass of the consuming GroupNorm disappears.
- *  gnb_K    backward: the accumulator is dy, the gradient at a = mask*silu(gn(x)); the epilogue stores
- *           dn = dy * keep * silu'(sc*x + sh) instead and adds per (image, 4-channel quad) the group-level terms
- *           {sum gamma*dn, sum gamma*dn*xhat} to gnb_gs[NB][N/4][2] (fp32 atomics, caller zeroes it).  gnb_x0/x1: the
- *           GroupNorm input as a concat of up to two NHWC bf16 tensors with gnb_C0 + gnb_C1 == N channels;
- *           gnb_K[NB][4][N] = {sc, sh, rstd, mean*rstd}; gnb_gamma / gnb_beta [N]: the norm's affine parameters; gnb_mask:
- *           dropout keep bits, one byte per 8 channels [pixel][N/8] (or NULL) with gnb_keep_scale = 1/(1-p); gnb_silu: 1 when
- *           the norm is followed by SiLU. */
+/* Optional GroupNorm fusion of a conv / GEMM epilogue (nn.GroupNorm(32, C, eps=1e-6) of unet.py:18-20; csrc/gn_epilogue.cuh).
+ *  qstats   the producer adds per (image, 4-channel quad) {sum, sum of squares} of its OUTPUT to qstats[NB][N/4][2]
+ *           (fp64 atomics, caller zeroes it) - the statistics pass of the consuming GroupNorm disappears.  NULL = off. */
 typedef struct ddpm_gn_epi {
     double* qstats;
-    const void* gnb_x0; const void* gnb_x1; int gnb_C0, gnb_C1;
-    const float* gnb_K; const float* gnb_gamma; const float* gnb_beta; float* gnb_gs;
-    const unsigned char* gnb_mask; float gnb_keep_scale; int gnb_silu;
 } ddpm_gn_epi;
 
 /* ------------------------------------------------------------------------------------------------
@@ -137,10 +126,14 @@ int ddpm_train_backward(ddpm_unet* h, const float* gscale, void* stream);
  * coef[S][6] = {sqrt_recip_ab, sqrt_recip_m1_ab, post_c1, post_c2, exp(.5*logvar), t>0}; both HOST pointers.
  * reset(step) arms the device-side step counter; each step() call then consumes one step (counter decrements),
  * x f32[B,C,H,W] is updated in place; z = per-step N(0,1) draw (device) or NULL (+seed != 0: built-in Philox stream).
- * A step() is a fixed launch sequence with no host-side arguments that change -> capturable once, replayable T times. */
+ * A step() is a fixed launch sequence with no host-side arguments that change -> capturable once, replayable T times.
+ * The alpha/beta update runs in the epilogue of the UNet's final conv (eps never reaches memory; no tail launch). */
 int ddpm_sampler_setup(ddpm_unet* h, int S, const int64_t* t_model_host, const float* coef_host);
 int ddpm_sampler_reset(ddpm_unet* h, int first_step, void* stream);
 int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, void* stream);
+/* Same step, additionally writing the clipped x_0 prediction of diffusion.py:122,130 to pred_x0 f32[B,C,H,W] (NULL = skip):
+ * GaussianDiffusion.p_sample_progressive (diffusion.py:176-198, p_sample_step(..., return_pred=True)). */
+int ddpm_sampler_step_pred(ddpm_unet* h, float* x, const float* z, uint64_t seed, float* pred_x0, void* stream);
 /* Introspection for tests / bench: op counts and algorithmic FLOPs of the compiled plan. */
 int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd_ops, int* n_bwd_ops, int* n_tensorcore_ops, int* n_generic_ops,
                          double* fwd_flops, double* bwd_flops);

@@ -300,3 +300,36 @@ def test_gradient_accumulation_matches_reference_semantics(golden):
     print(f"\n[grad accumulation] flat_grads vs sum of single passes rel-L2 {r:.3e}; p.grad vs flat views {rel(pg, views):.3e}")
     assert r < 1e-2 and rel(pg, views) < 1e-2 and rel(acc, singles[1]) > 0.1
     flag_ok()
+
+
+def test_native_p_sample_progressive(golden):
+    """diffusion.py:176-198 on the engine (ddpm_sampler_step_pred): final sample and the x_0 predictions every pred_freq steps
+    against the generic torch loop of the same class driven by the oracle network, same seed (same CUDA noise stream)."""
+    import ddpm_torch_b200 as D
+    fx = golden("unet_tiny.pt")
+    cfg = fx["cfg"]
+    m, sd = build(cfg, fx["seed"])
+    T = 12
+    d = D.GaussianDiffusion(D.get_beta_schedule("linear", 1e-4, 0.02, T), "eps", "fixed-large", "mse")
+    shape = tuple(fx["noise"].shape)
+    xs, preds = d.p_sample_progressive(m, shape, device=torch.device(DEV), pred_freq=3, seed=5)
+    with torch.no_grad():
+        xr, pr = d.p_sample_progressive(lambda a, q: R.unet_forward(sd, cfg, a, q), shape, device=torch.device(DEV), pred_freq=3, seed=5)
+    e1, e2 = (xs - xr).abs().max().item(), (preds - pr).abs().max().item()
+    print(f"\n[progressive T={T}] final Linf {e1:.3e}; x0-prediction Linf {e2:.3e}; preds shape {tuple(preds.shape)}")
+    assert preds.shape == pr.shape == (T // 3,) + shape and e1 < 5e-2 and e2 < 5e-2
+    flag_ok()
+
+
+CELEBA64_CFG = dict(in_channels=3, hid_channels=128, out_channels=3, ch_multipliers=(1, 2, 2, 2), num_res_blocks=2,
+                    apply_attn=(False, False, True, False), drop_rate=0.0)          # configs/celeba.json
+
+
+def test_celeba64_config_fwd_bwd():
+    """configs/celeba.json (CelebA 64x64, attention at the 16x16 level = level 2): loss and all gradients at bs=8."""
+    m, sd = build(CELEBA64_CFG, 77, train=True)
+    g = torch.Generator(DEV).manual_seed(64)
+    x0 = torch.rand(8, 3, 64, 64, device=DEV, generator=g) * 2 - 1
+    t = torch.randint(1000, (8,), device=DEV, generator=g)
+    noise = torch.randn(8, 3, 64, 64, device=DEV, generator=g)
+    grads_vs_oracle(m, sd, CELEBA64_CFG, x0, t, noise, "celeba 64x64 bs=8 train", chunk=4)

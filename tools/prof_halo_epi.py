@@ -1,5 +1,5 @@
 """Isolated timing of the haloed 3x3 conv with the GroupNorm epilogue fusions (gn_epilogue.cuh), rotating buffers > L2.
-usage: python tools/prof_halo_epi.py [variant ...]   variants: plain qstats gnb gnb_mask   (default: all)
+usage: python tools/prof_halo_epi.py [variant ...]   variants: plain qstats   (default: both)
 Under ncu pass ONE variant and --once (a single launch after warm-up is bracketed by cudaProfilerStart/Stop)."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,19 +7,15 @@ import torch
 from ddpm_torch_b200 import _lib
 
 once = "--once" in sys.argv
-variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain", "qstats", "gnb", "gnb_mask"]
+variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain", "qstats"]
 B, H, W = 128, 32, 32
 L = _lib.lib(); st = _lib.stream_ptr()
 for (ci, co) in ((128, 128), (128, 384), (256, 256)):
     nbuf = 6
     xs = [torch.randn(B, H, W, ci, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     ys = [torch.empty(B, H, W, co, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
-    gx = [torch.randn(B, H, W, co, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     w = (torch.randn(co, 9 * ci, device="cuda") * 0.03).to(torch.bfloat16); bias = torch.zeros(co, device="cuda")
-    K = torch.randn(B, 4, co, device="cuda"); cs = torch.zeros(B, co // 4, 2, device="cuda")
-    gamma = torch.randn(co, device="cuda"); beta = torch.randn(co, device="cuda")
     qs = torch.zeros(B, co // 4, 2, device="cuda", dtype=torch.float64)
-    mask = torch.randint(0, 256, (B, H, W, co // 8), device="cuda", dtype=torch.uint8)
     for var in variants:
         ds = []
         for i in range(nbuf):
@@ -31,12 +27,6 @@ for (ci, co) in ((128, 128), (128, 384), (256, 256)):
                 d.bias = bias.data_ptr()
             if var == "qstats":
                 d.gn.qstats = qs.data_ptr()
-            if var.startswith("gnb"):
-                d.gn.gnb_x0 = gx[i].data_ptr(); d.gn.gnb_C0 = co; d.gn.gnb_K = K.data_ptr(); d.gn.gnb_gs = cs.data_ptr()
-                d.gn.gnb_gamma = gamma.data_ptr(); d.gn.gnb_beta = beta.data_ptr()
-                d.gn.gnb_silu = 1; d.gn.gnb_keep_scale = 1.0
-                if var == "gnb_mask":
-                    d.gn.gnb_mask = mask.data_ptr(); d.gn.gnb_keep_scale = 1.0 / 0.9
             ds.append(d)
         for d in ds:
             _lib.check(L.ddpm_conv_halo_run(C.byref(d), st))
