@@ -44,11 +44,13 @@ struct HaloCfg {
     // producer -> issuer -> commit round trip costs ~300 cycles of the single issuing thread, whatever the stage holds; with
     // one tap per stage (256 MMA cycles at N=128) the tensor pipe starves at 65 %.  Three taps (one ky row) per stage = 768
     // MMA cycles per round trip.
-    static constexpr int TPS = (BLOCK_N == 256 || SUB != 1) ? 1 : 3;
+    static constexpr int TPS = (BLOCK_N == 256) ? 1 : 3;
     static constexpr int TAP_BYTES = BLOCK_N * 128;
     static constexpr int B_BYTES = TAP_BYTES * TPS;
     static constexpr int NA = 2;
-    static constexpr int NB_ST = (TPS == 3) ? ((BLOCK_N == 128) ? 3 : 6) : ((BLOCK_N == 256) ? ((SUB == 1) ? 4 : 3) : ((SUB == 1) ? 8 : 6));
+    // SUB = 2: every weight slab feeds two sub-tiles (256 pixels), i.e. half the weight traffic out of L2 per FLOP and 1536 MMA
+    // cycles per stage; two 48 KB stages (3072 cycles in flight) then cover the TMA round trip.
+    static constexpr int NB_ST = (TPS == 3) ? ((BLOCK_N == 128) ? ((SUB == 1) ? 3 : 2) : ((SUB == 1) ? 6 : 4)) : ((SUB == 1) ? 4 : 3);
     static constexpr int NACC = (2 * SUB * BLOCK_N <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * SUB * BLOCK_N <= 128) ? 128 : ((NACC * SUB * BLOCK_N <= 256) ? 256 : 512);
     static constexpr int OUT_STAGE_BYTES = 128 * 128;           // one 64-channel x 128-pixel output slab (TMA store source)
@@ -293,7 +295,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct HaloLaunch { CUtensorMap a[3], b, o; HaloParams p; int block_n, sub; int tiles; double flops; };
+struct HaloLaunch { CUtensorMap a[3], b, o; HaloParams p; int block_n, sub; int tiles; double flops; int pair; /* CTA-pair kernel (conv_halo2.cuh) */ };
 
 typedef ddpm_halo_desc HaloDesc;   // the C-ABI struct doubles as the internal description
 
@@ -305,6 +307,11 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
     g.block_n = pick_block_n(d.Cout);
     int sub = 1;   // measured on B200 (tools/dbg_dominant.py): one 16x8 sub-tile per CTA beats two (1089 vs 1012 TFLOP/s at N=128)
     if (d.force_sub == 1 || d.force_sub == 2) sub = d.force_sub;
+    // CTA-pair kernel (cta_group::2): force_sub = 3 forces it, 1 / 2 force the single-CTA kernel, 0 = policy below
+    static const int pair_policy = getenv("DDPM_HALO_PAIR") ? atoi(getenv("DDPM_HALO_PAIR")) : 1;
+    const bool pair_ok = g.block_n >= 128 && (((long long)d.NB * (d.H / 16) * (d.W / 8)) % 2) == 0;
+    g.pair = (d.force_sub == 3 || (d.force_sub == 0 && pair_policy)) && pair_ok ? 1 : 0;
+    if (d.force_sub == 3 && !pair_ok) return fail(-12, "halo conv: the CTA-pair kernel needs Cout %% 128 == 0 and an even number of 16x8 tiles");
     if (sub == 2 && d.W % 16) return fail(-12, "halo conv: SUB=2 needs W %% 16 == 0");
     g.sub = sub;
     HaloParams& p = g.p;
@@ -322,7 +329,7 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
         else                    { if ((rc = make_tmap_4d(&g.a[m], d.a_ptr[m], d.a_C[m], d.W, d.H, d.NB, d.a_ld[m], 64, 8 * sub, 16, 1))) return rc; }
     }
     for (int i = 0; i < 3; ++i) { bool used = false; for (int s = 0; s < d.nseg; ++s) used |= d.seg_map[s] == i; if (!used) g.a[i] = g.a[d.seg_map[0]]; }
-    if ((rc = make_tmap_3d(&g.b, d.w, d.Ktot, d.Cout, 1, d.ldw, 0, 64, g.block_n))) return rc;
+    if ((rc = make_tmap_3d(&g.b, d.w, d.Ktot, d.Cout, 1, d.ldw, 0, 64, g.pair ? g.block_n / 2 : g.block_n))) return rc;   // pair: each CTA loads half of the weight rows
     if ((rc = make_tmap_4d(&g.o, d.out, d.Cout, d.W, d.H, d.NB, d.Cout, 64, 8, 16, 1))) return rc;      // output slab = 64 ch x (8 x 16) px
     g.tiles = d.NB * p.tiles_x * p.tiles_y * p.n_tiles;
     g.flops = 2.0 * d.NB * d.H * d.W * (double)d.Cout * d.Ktot;
@@ -343,7 +350,9 @@ inline int launch_halo_inst(const HaloLaunch& g, cudaStream_t st) {
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }
+inline int launch_halo2(const HaloLaunch& g, cudaStream_t st);      // conv_halo2.cuh
 inline int launch_halo(const HaloLaunch& g, cudaStream_t st) {
+    if (g.pair) return launch_halo2(g, st);
     if (g.block_n == 64 && g.sub == 1) return launch_halo_inst<64, 1>(g, st);
     if (g.block_n == 64 && g.sub == 2) return launch_halo_inst<64, 2>(g, st);
     if (g.block_n == 128 && g.sub == 1) return launch_halo_inst<128, 1>(g, st);

@@ -8,6 +8,7 @@
 #include <vector>
 #include "gemm_build.cuh"
 #include "conv_halo.cuh"
+#include "conv_halo2.cuh"
 #include "kernels_simt.cuh"
 
 namespace ddpm {

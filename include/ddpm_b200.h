@@ -80,7 +80,7 @@ typedef struct ddpm_halo_desc {
     const void* w; long long ldw; int Ktot;
     void* out; const float* bias; const float* rowvec; int rowvec_ld; const void* residual;
     int base_offset_mode;              /* 0 = descriptor base_offset field left 0 (correct on B200); 1 = (addr>>7)&7 (probe) */
-    int force_sub;                     /* 0 = auto; 1 / 2 = number of 16x8 sub-tiles per CTA */
+    int force_sub;                     /* 0 = auto; 1 / 2 = single-CTA kernel with that many 16x8 sub-tiles per CTA; 3 = CTA-pair kernel (cta_group::2) */
     ddpm_gn_epi gn;
 } ddpm_halo_desc;
 int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream);

@@ -285,8 +285,9 @@ def _halo_run(d):
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 16), (1, 64, 64), (2, 16, 8)])
-@pytest.mark.parametrize("Cout,sub", [(64, 1), (64, 2), (128, 1), (128, 2), (256, 1), (256, 2)])
+@pytest.mark.parametrize("Cout,sub", [(64, 1), (64, 2), (128, 1), (128, 2), (256, 1), (256, 2), (128, 3), (256, 3), (384, 3)])
 def test_conv_halo_concat_skip(B, H, W, Cout, sub):
+    """sub = 1 / 2: single-CTA kernel with one / two 16x8 sub-tiles; sub = 3: the CTA-pair kernel (tcgen05 cta_group::2)."""
     from ddpm_torch_b200._lib import HaloDesc
     if sub == 2 and W % 16:
         pytest.skip("SUB=2 needs W % 16 == 0")
@@ -341,7 +342,7 @@ def test_conv_halo_base_offset_probe():
 
 # ---------------------------------------------------------------------------- GroupNorm fusions of the epilogues (csrc/gn_epilogue.cuh)
 @pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 16)])
-@pytest.mark.parametrize("Cout,sub", [(128, 1), (256, 1), (128, 2), (64, 1)])
+@pytest.mark.parametrize("Cout,sub", [(128, 1), (256, 1), (128, 2), (64, 1), (128, 3), (256, 3)])
 def test_conv_halo_quad_stats_epilogue(B, H, W, Cout, sub):
     """forward fusion: per (image, 4-channel quad) {sum, sum of squares} of the conv output, fp64 atomics."""
     from ddpm_torch_b200._lib import HaloDesc

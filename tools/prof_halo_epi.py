@@ -7,10 +7,10 @@ import torch
 from ddpm_torch_b200 import _lib
 
 once = "--once" in sys.argv
-variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain", "qstats"]
+variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain", "plain_pair", "qstats_pair"]
 B, H, W = 128, 32, 32
 L = _lib.lib(); st = _lib.stream_ptr()
-for (ci, co) in ((128, 128), (128, 384), (256, 256)):
+for (ci, co) in ((128, 128), (128, 384), (384, 128), (256, 256), (512, 256)):
     nbuf = 6
     xs = [torch.randn(B, H, W, ci, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     ys = [torch.empty(B, H, W, co, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
@@ -23,10 +23,15 @@ for (ci, co) in ((128, 128), (128, 384), (256, 256)):
             d.a_ptr[0] = xs[i].data_ptr(); d.a_C[0] = ci; d.a_ld[0] = ci
             d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = ci // 64
             d.w = w.data_ptr(); d.ldw = 9 * ci; d.Ktot = 9 * ci; d.out = ys[i].data_ptr()
-            if var in ("plain", "qstats"):
-                d.bias = bias.data_ptr()
-            if var == "qstats":
+            d.bias = bias.data_ptr()
+            if var.startswith("qstats"):
                 d.gn.qstats = qs.data_ptr()
+            if var.endswith("_sub2"):
+                d.force_sub = 2
+            elif var.endswith("_pair"):
+                d.force_sub = 3
+            else:
+                d.force_sub = 1
             ds.append(d)
         for d in ds:
             _lib.check(L.ddpm_conv_halo_run(C.byref(d), st))
