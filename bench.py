@@ -8,7 +8,8 @@ mode, synthetic 3x32x32) on N B200s, plus p_sample-loop images/sec (bs=256) at N
 One JSON line on stdout (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same step
 driven through the public Python API with the batch coming from pinned host memory and the loss read back.
 A "step" = weight re-pack + q_sample + UNet forward + MSE + full backward (grads of all 304 tensors)
-(+ one NCCL all-reduce (mean) of the flat gradient buffer when N > 1).  Optimiser/EMA are outside the metric.
+(+ the NCCL all-reduce (mean) of the flat gradient buffer when N > 1, issued chunk by chunk on a communication stream as the
+backward pass completes each level group).  Optimiser/EMA are outside the metric.
 Extra keys at every N (BASELINE configs 3-5): `sampler` (CIFAR bs=256 per GPU, DDIM-50 + ancestral-1000), `hq_train`
 (celebahq.json 3x256x256, 4 images per GPU, incl. the 455 MB all-reduce), `hq_ddim100` (8 images per GPU, no collective);
 at N=1 also `vs_stock_cuda` (the unmodified reference's torch-CUDA step on the same B200 - north_star's >=10x denominator).
@@ -124,7 +125,7 @@ def dist_setup(n):
 
 def workload_config(world, B):
     return {"workload": "CIFAR-10 UNet (configs/cifar10.json, 35.7M params, drop 0.1 active) training step: repack + q_sample + fwd + MSE + bwd"
-                        + (" + NCCL all-reduce(mean) of the flat fp32 grads" if world > 1 else ""),
+                        + (" + NCCL all-reduce(mean) of the flat fp32 grads, overlapped with the backward chunk by chunk" if world > 1 else ""),
             "per_gpu_batch": B, "global_batch": B * world, "resolution": "3x32x32", "parallelism": f"dp{world}",
             "l2": "4 rotating input batches; activations (2.2 GB fwd) exceed the 126 MB L2"}
 
@@ -357,7 +358,7 @@ def main():
                                         losses.data_ptr(), 1000 + i, sp))
         _lib.check(L.ddpm_train_backward(h, gscale.data_ptr(), sp))
         if world > 1:
-            D.parallel.allreduce_mean_(model.flat_grads)
+            D.parallel.allreduce_grads_overlapped_(model)
 
     def barrier():
         if world > 1:
@@ -400,7 +401,7 @@ def main():
         loss = diff.train_losses(model, x, t, nz).mean()
         loss.backward()
         if world > 1:
-            D.parallel.allreduce_mean_(model.flat_grads)
+            D.parallel.allreduce_grads_overlapped_(model)
         return loss.item()
 
     for i in range(args.warmup):
@@ -565,7 +566,7 @@ def bench_hq(D, _lib, dev, rank, world, barrier, maxr, pk, train_bs=4, sample_bs
         _lib.check(L.ddpm_train_forward(h, x0.data_ptr(), t.data_ptr(), nz.data_ptr(), ta.data_ptr(), tsb.data_ptr(), losses.data_ptr(), 0, sp))
         _lib.check(L.ddpm_train_backward(h, gs.data_ptr(), sp))
         if world > 1:
-            D.parallel.allreduce_mean_(model.flat_grads)
+            D.parallel.allreduce_grads_overlapped_(model)
     for i in range(warmup):
         step(i)
     barrier()

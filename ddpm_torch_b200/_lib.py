@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
         ("seg_custom", C.c_int * 3), ("seg_cmul", C.c_int * 3),
         ("seg_dx", (C.c_byte * 9) * 3), ("seg_dy", (C.c_byte * 9) * 3),
         ("o_mul", C.c_int), ("o_py", C.c_int), ("o_px", C.c_int), ("kk_splits", C.c_int),
-        ("gn", GnEpi),
+        ("gn", GnEpi), ("cta_pair", C.c_int),
     ]
 
 
@@ -97,6 +97,8 @@ def lib():
             "ddpm_sampler_reset": ([vp, i32, vp], i32),
             "ddpm_sampler_step": ([vp, vp, vp, u64, vp], i32),
             "ddpm_sampler_step_pred": ([vp, vp, vp, u64, vp, vp], i32),
+            "ddpm_unet_grad_chunks": ([vp, i32, C.POINTER(i64), C.POINTER(i64)], i32),
+            "ddpm_unet_wait_grad_chunk": ([vp, i32, vp], i32),
             "ddpm_unet_plan_stats": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
             "ddpm_unet_launches_per_forward": ([vp], i32),
@@ -116,7 +118,7 @@ EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "d
            "ddpm_unet_create", "ddpm_unet_destroy", "ddpm_unet_num_params", "ddpm_unet_param_info",
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",
-           "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_sampler_step_pred", "ddpm_unet_plan_stats",
+           "ddpm_sampler_setup", "ddpm_sampler_reset", "ddpm_sampler_step", "ddpm_sampler_step_pred", "ddpm_unet_grad_chunks", "ddpm_unet_wait_grad_chunk", "ddpm_unet_plan_stats",
            "ddpm_unet_launches_per_forward", "ddpm_unet_launch_counts", "ddpm_opt_step", "ddpm_to_uint8_nhwc"]
 
 

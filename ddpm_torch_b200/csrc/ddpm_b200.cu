@@ -73,6 +73,7 @@ void ddpm_unet_destroy(ddpm_unet* h) {
     if (h->d_tmodel) cudaFree(h->d_tmodel);
     if (h->d_coef) cudaFree(h->d_coef);
     if (h->e.side_stream) { cudaStreamDestroy(h->e.side_stream); cudaEventDestroy(h->e.ev_fork); cudaEventDestroy(h->e.ev_join); }
+    for (auto& c : h->e.chunks) if (c.ev) cudaEventDestroy(c.ev);
     if (h->e.hp_stream) { cudaStreamDestroy(h->e.hp_stream); cudaEventDestroy(h->e.ev_hp_fork); cudaEventDestroy(h->e.ev_hp_join); }
     delete h;
 }
@@ -254,6 +255,18 @@ int ddpm_to_uint8_nhwc(const float* x, uint8_t* out, int B, int C, int H, int W,
         default: launch_k(k_to_uint8_nhwc<4>, grid, 256, 0, st, x, out, npix, H * W); break;
     }
     DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int ddpm_unet_grad_chunks(const ddpm_unet* h, int max_n, long long* lo, long long* hi) {
+    if (!h || !h->e.planned || !h->e.train) return fail(-33, "ddpm_unet_grad_chunks: no training plan");
+    const int n = (int)h->e.chunks.size();
+    for (int i = 0; i < n && i < max_n; ++i) { if (lo) lo[i] = h->e.chunks[i].lo; if (hi) hi[i] = h->e.chunks[i].hi; }
+    return n;
+}
+int ddpm_unet_wait_grad_chunk(ddpm_unet* h, int i, void* stream) {
+    NEED_PLAN(h);
+    if (i < 0 || i >= (int)h->e.chunks.size() || !h->e.chunks[i].ev) return fail(-30, "gradient chunk index out of range");
+    DDPM_CUDA_OK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->e.chunks[i].ev, 0));
     return 0;
 }
 int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd, int* n_bwd, int* n_tc, int* n_gen, double* ff, double* bf) {

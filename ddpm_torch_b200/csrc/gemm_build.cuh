@@ -59,11 +59,28 @@ inline int build_gemm(const ddpm_gemm_desc& d, GemmLaunch& g) {
             if (!d.a_ptr[i]) { g.a[i] = g.a[0]; continue; }
             if ((rc = make_tmap_4d(&g.a[i], d.a_ptr[i], d.a_C[i], d.W * aes, d.H * aes, d.NB, d.a_ld[i], 64, p.w_t, p.h_t, p.n_t, aes))) return rc;
         }
-        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.block_n))) return rc;
+        // CTA-pair kernel (cta_group::2): two consecutive m_tiles share one M = 256 MMA, each CTA loads half of the weight rows
+        // Policy (cta_pair = 0), measured on B200 (profiles/r02_pair_ab.txt): in the single-stream sampler the pair kernel wins
+        // (4.74 -> 4.65 ms per step); in the training step, where the weight-gradient GEMMs of the side stream run next to the
+        // main chain, 2-CTA clusters of 227 KB CTAs schedule worse than independent CTAs (9.47 -> 9.68 ms) - so pairs are used by
+        // inference plans only (gemm_pair_hint(), set by UnetEngine::plan).  DDPM_GEMM_PAIR overrides (bit 0 KK, bit 1 MN-major).
+        static const int pair_env = getenv("DDPM_GEMM_PAIR") ? atoi(getenv("DDPM_GEMM_PAIR")) : -1;
+        const int pair_policy = pair_env >= 0 ? pair_env : (gemm_pair_hint() ? 1 : 0);
+        const bool pair_ok = g.block_n >= 128 && (m_tiles % 2) == 0;
+        g.pair = (d.cta_pair >= 2 || (d.cta_pair == 0 && (pair_policy & 1))) && pair_ok ? 1 : 0;
+        if (d.cta_pair == 2 && !pair_ok) return fail(-11, "KK: the CTA-pair kernel needs N %% 128 == 0 and an even number of 128-row tiles");
+        if ((rc = make_tmap_3d(&g.b, d.b_ptr, d.b_K, d.b_rows, d.b_batch > 0 ? d.b_batch : 1, d.b_ld, d.b_bs, 64, g.pair ? g.block_n / 2 : g.block_n))) return rc;
         g.flops = 2.0 * d.M * d.N * 64.0 * slabs * gz;
     } else if (d.mode == GEMM_MNMN) {
         if (!pick_box(d.W, d.H, 64, p.wk_t, p.hk_t, p.nk_t)) return fail(-11, "MNMN: unsupported geometry W=%d H=%d", d.W, d.H);
         if (d.M % 64) return fail(-11, "MNMN: M must be a multiple of 64");
+        {   // CTA pairs along M (two 128-row tiles of output channels per M = 256 MMA), each CTA holding half of the N columns
+            // measured slower inside the training step (9.47 -> 9.67 ms, see the K-major policy below): off unless asked for
+            static const int pair_env = getenv("DDPM_GEMM_PAIR") ? atoi(getenv("DDPM_GEMM_PAIR")) : 0;
+            const bool pair_ok = g.block_n >= 128 && (m_tiles % 2) == 0 && (d.M % 128) == 0;
+            g.pair = (d.cta_pair >= 2 || (d.cta_pair == 0 && (pair_env & 2))) && pair_ok ? 1 : 0;
+            if (d.cta_pair == 2 && !pair_ok) return fail(-11, "MNMN: the CTA-pair kernel needs M %% 256 == 0 and N %% 128 == 0");
+        }
         if ((rc = make_tmap_4d(&g.a[0], d.a_ptr[0], d.a_C[0], d.W, d.H, d.NB, d.a_ld[0], 64, p.wk_t, p.hk_t, p.nk_t))) return rc;
         g.a[1] = g.a[2] = g.a[0];
         if ((rc = make_tmap_4d(&g.b, d.b_ptr, d.b_K, d.W * bes, d.H * bes, d.NB, d.b_ld, 64, p.wk_t, p.hk_t, p.nk_t, bes))) return rc;

@@ -85,10 +85,32 @@ struct GemmLaunch {
     GemmParams p;
     dim3 grid;
     int mode, block_n;
+    int pair;               // KK: CTA-pair kernel (cta_group::2); the B map's box then holds block_n / 2 rows
     double flops;
 };
 template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
+inline int launch_gemm_pair(const GemmLaunch& g, cudaStream_t st) {
+    using SM = GemmSmem<BLOCK_N / 2, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
+    auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES, KSTEPS, 1>;
+    static bool attr_done = false;
+    if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL)); attr_done = true; }
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    int pairs = (int)g.grid.x / 2; if (pairs > num_sms / 2) pairs = num_sms / 2;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(gemm_threads(MODE)); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    bool pdl = pdl_enabled();
+    if (pdl) { cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone; if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone && !getenv("DDPM_PDL_GRAPH")) pdl = false; }
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+    DDPM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, g.a[0], g.a[1], g.a[2], g.b, g.o, g.p));
+    return 0;
+}
+template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
 inline int launch_gemm_inst2(const GemmLaunch& g, cudaStream_t st) {
+    if constexpr (MODE != GEMM_KMN && BLOCK_N >= 128) { if (g.pair) return launch_gemm_pair<BLOCK_N, MODE, STAGES, KSTEPS>(g, st); }
     using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
     auto kern = umma_gemm_kernel<BLOCK_N, MODE, STAGES, KSTEPS>;
     static bool attr_done = false;
@@ -122,6 +144,9 @@ inline int launch_gemm(const GemmLaunch& g, cudaStream_t st) {
 #undef DDPM_GEMM_CASE
     return fail(-6, "unsupported gemm variant block_n=%d mode=%d", g.block_n, g.mode);
 }
+
+// K-major GEMMs built with cta_pair = 0 use the CTA-pair kernel when this is non-zero (inference plans; see build_gemm)
+inline int& gemm_pair_hint() { static thread_local int v = 1; return v; }
 
 inline int pick_block_n(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); }
 

@@ -97,13 +97,18 @@ __device__ __forceinline__ void pix_decompose(int p, int W, int H, int& n, int& 
 // accumulates tile i+1 into the other one; the TMA producer runs ahead across tile boundaries.
 // (TMA multicast of the weight tile over 2/4-CTA clusters was built and measured no faster in round 1 - L2 traffic is not the
 // limiter - and has been removed.)
-template <int BLOCK_N, int MODE, int STAGES, int KSTEPS>
+// PAIR (KK mode): two CTAs of a cluster (tcgen05 cta_group::2) take m_tiles 2j and 2j+1 of the same (n_tile, z): each loads its
+// own A rows and HALF of the B tile, the even CTA issues M = 256 MMAs for both (see conv_halo2.cuh for the protocol and why:
+// at M = 128 the MMA operand reads saturate the SM's shared-memory bandwidth).  B_ROWS = weight rows held per CTA.
+template <int BLOCK_N, int MODE, int STAGES, int KSTEPS, int PAIR = 0>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
     pdl_trigger();                                  // dependents may be scheduled; they block in their own pdl_wait()
-    using SM = GemmSmem<BLOCK_N, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
+    static_assert(!PAIR || MODE != GEMM_KMN, "CTA pairs are implemented for the K-major and the MN-major (weight-gradient) modes");
+    constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;
+    using SM = GemmSmem<B_ROWS, STAGES, KSTEPS, (MODE == GEMM_MNMN ? 0 : 1)>;
     constexpr int A_MN = (MODE == GEMM_MNMN) ? 1 : 0;
     constexpr int B_MN = (MODE == GEMM_KK) ? 0 : 1;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
@@ -121,8 +126,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_tiles = p.m_tiles, n_tiles = p.n_tiles;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader of the pair
+    // tile walk: single CTA: t -> (m_tile fastest, n_tile, z); pair: t indexes PAIRS of m_tiles (m_tile = 2*(t % m_pairs) + rank)
+    const int m_tiles = PAIR ? (p.m_tiles >> 1) : p.m_tiles, n_tiles = p.n_tiles;
     const int total_tiles = m_tiles * n_tiles * p.grid_z;
+    const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cta_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     // K slabs of a tile (uniform across roles)
     int kk_slabs = 0;
@@ -145,12 +153,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], gemm_epi_warps(MODE)); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (PAIR ? 2 : 1) * gemm_epi_warps(MODE)); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                   // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     pdl_wait();                                     // prologue above overlapped the previous kernel's tail; its data is visible from here
     const uint32_t tmem_base = *tmem_slot;
@@ -179,10 +188,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // after the loads of a slab were issued: arm the barrier when the stage is complete (or the tile ends)
             auto commit_slab = [&]() {
                 ++sub; --left;
-                if (sub == KSTEPS || left == 0) { mbar_expect_tx(fb, (uint32_t)(sub * SM::SLAB_BYTES)); sub = 0; ++stg; }
+                if (sub == KSTEPS || left == 0) { if (crank == 0) mbar_expect_tx(fb, (uint32_t)((PAIR ? 2 : 1) * sub * SM::SLAB_BYTES)); sub = 0; ++stg; }
             };
-            for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-                const int m_tile = t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
+            for (int t = cta_id; t < total_tiles && ok; t += cta_step) {
+                const int m_tile = PAIR ? (t % m_tiles) * 2 + (int)crank : t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
                 left = slabs_of(z); sub = 0;
                 if (MODE == GEMM_KK) {
                     int n0, y0, x0;
@@ -202,8 +211,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 uint8_t* st = acquire(0);
                                 if (!st) break;
                                 if (p.dbg & 4) { asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(fb)), "r"((uint32_t)SM::SLAB_BYTES) : "memory"); commit_slab(); continue; }
-                                tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
-                                tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+                                if (PAIR) {
+                                    tma_load_4d_2cta(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
+                                    tma_load_3d_2cta(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N + (int)crank * B_ROWS, z * p.b_z);
+                                } else {
+                                    tma_load_4d(st, mA, fb, sg.c_base + kc * 64, xc, yc, n0);
+                                    tma_load_3d(st + SM::A_BYTES, &tmB, fb, p.b_k_base + kcount * 64, n_tile * BLOCK_N, z * p.b_z);
+                                }
                                 commit_slab();
                             }
                         }
@@ -220,13 +234,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         int n0, y0, x0;
                         pix_decompose((kb0 + i) * 64, p.W, p.H, n0, y0, x0);
                         n0 += batch;
+                        if (PAIR) {      // own 128 rows of M, own half of the N columns; bytes complete on the leader's barrier
 #pragma unroll
-                        for (int b = 0; b < 2; ++b)
-                            tma_load_4d(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
+                            for (int b = 0; b < 2; ++b)
+                                tma_load_4d_2cta(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
 #pragma unroll
-                        for (int b = 0; b < BLOCK_N / 64; ++b)
-                            tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64,
-                                        x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
+                            for (int b = 0; b < B_ROWS / 64; ++b)
+                                tma_load_4d_2cta(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + (int)crank * B_ROWS + b * 64,
+                                                 x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < 2; ++b)
+                                tma_load_4d(st + b * 8192, &tmA0, fb, p.a_c_base + m_tile * 128 + b * 64, x0, y0, n0);
+#pragma unroll
+                            for (int b = 0; b < BLOCK_N / 64; ++b)
+                                tma_load_4d(st + SM::A_BYTES + b * 8192, &tmB, fb, p.b_c_base + n_tile * BLOCK_N + b * 64,
+                                            x0 * p.b_cmul + dx, y0 * p.b_cmul + dy, n0);
+                        }
                         commit_slab();
                     }
                 } else {  // GEMM_KMN
@@ -247,11 +271,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc(128, BLOCK_N, A_MN, B_MN);
+        if (crank == 0 && elect_one()) {             // pair: the leader issues for both CTAs
+            constexpr uint32_t idesc = umma_idesc(PAIR ? 256 : 128, BLOCK_N, A_MN, B_MN);
             int stg = 0, it = 0;
             bool ok = true;
-            for (int t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++it) {
+            for (int t = cta_id; t < total_tiles && ok; t += cta_step, ++it) {
                 const int z = t / (m_tiles * n_tiles);
                 const int ns = slabs_of(z);
                 const int acc = it & 1;
@@ -277,12 +301,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                                      : umma_smem_desc(a_addr + k * 32, 16, 1024);
                             const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                                      : umma_smem_desc(b_addr + k * 32, 16, 1024);
-                            if (!(p.dbg & 2)) umma_bf16(d_tmem, da, db, idesc, (i | sb | k) != 0);
+                            if (!(p.dbg & 2)) { if (PAIR) umma_bf16_2cta(d_tmem, da, db, idesc, (i | sb | k) != 0); else umma_bf16(d_tmem, da, db, idesc, (i | sb | k) != 0); }
                         }
                     }
-                    umma_commit(&empty_bar[st]);
+                    if (PAIR) umma_commit_2cta(&empty_bar[st], 3); else umma_commit(&empty_bar[st]);
                 }
-                if (ok) umma_commit(&tmem_full[acc]);
+                if (ok) { if (PAIR) umma_commit_2cta(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]); }
             }
         }
     } else {
@@ -293,8 +317,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int r = q * 32 + lane;                 // accumulator row
         int it = 0;
         uint32_t slab_ctr = 0;                       // staging-buffer parity of the TMA-store path, continues across tiles
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            const int m_tile = t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
+        for (int t = cta_id; t < total_tiles; t += cta_step, ++it) {
+            const int m_tile = PAIR ? (t % m_tiles) * 2 + (int)crank : t % m_tiles, n_tile = (t / m_tiles) % n_tiles, z = t / (m_tiles * n_tiles);
             const int ns = slabs_of(z);
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
@@ -420,16 +444,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // hand the accumulator buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }   // pair: on the leader's barrier
         }
         if (threadIdx.x == 64) bulk_wait_group0();  // outstanding TMA stores read this CTA's shared memory
     }
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                   // no arrival / MMA read may still target the peer's shared memory or TMEM
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 

@@ -19,7 +19,14 @@ struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
             long long pix() const { return (long long)B * H * W; } long long numel() const { return pix() * C; } };
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
 enum { OP_TEMB = 1 };
-struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; int tag = 0; };
+struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; int tag = 0;
+            int chunk = -1;   // >= 0: gradient-chunk boundary of the backward list (see UnetEngine::chunks)
+};
+// A contiguous range [lo, hi) of the flat gradient buffer that is FINAL once `ev` has fired (recorded by the backward pass on the
+// side stream, after the last weight-gradient GEMM / gradient unpack / main-chain reduction that writes into it).  Chunks are
+// listed in the order the backward completes them, so a data-parallel caller can start the all-reduce of a chunk while the
+// rest of the backward is still running (utils/train.py:149-153 does this with DDP's buckets).
+struct GradChunk { long long lo = 0, hi = 0; int unpack_lo = 0, unpack_hi = 0; cudaEvent_t ev = nullptr; };
 struct GnSaved { Src in; float* K; const float* gamma; const float* beta; float* dgamma; float* dbeta; int silu; float drop_p; uint32_t layer; unsigned char* mask; };
 
 static inline int grid_for(long long n, int threads = 256) { long long g = (n + threads - 1) / threads; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1; return (int)g; }
@@ -37,6 +44,9 @@ struct UnetEngine {
     int B = 0, H = 0, W = 0; bool train = false; bool dry = true; size_t cursor = 0; bool planned = false;
     std::vector<Op> pack_ops, fwd_ops, bwd_ops;
     std::vector<std::function<void()>> tape;
+    std::vector<std::string> tape_tag; std::string cur_tag = "late";       // gradient-chunk group of every tape entry
+    void tape_push(std::function<void()> f) { tape.push_back(std::move(f)); tape_tag.push_back(cur_tag); }
+    std::vector<GradChunk> chunks;
     std::map<long long, std::pair<T4, bool>> grads;     // fwd tensor offset -> (grad tensor, written?)
     size_t zero_fwd_off = 0, zero_fwd_bytes = 0, zero_bwd_off = 0, zero_bwd_bytes = 0;   // per-pass zeroed regions
     size_t once_zero_off = 0, once_zero_bytes = 0;                                       // zeroed at plan time only
@@ -96,6 +106,30 @@ struct UnetEngine {
             if (i != 0) reg_conv(p + "." + std::to_string(nrb + 1) + ".1", cur, cur, 3);
         }
         reg_gn("out_conv.0", ch); reg_conv("out_conv.2", ch, cfg.out_channels, 3);
+        layout_params();
+    }
+    // Memory layout of the flat buffers: registration order, EXCEPT that the tensors whose gradients only exist at the very end
+    // of the backward pass (the embedding MLP and the per-block timestep projections fc.weight, unet.py:122-126,77) are moved
+    // behind everything else ("late region"), so that the rest forms contiguous per-level ranges that complete one after the
+    // other.  The parameter LIST (state_dict order) is unchanged - only the offsets differ.
+    static bool is_late(const std::string& n) { return n.rfind("embed.", 0) == 0 || (n.size() > 10 && n.compare(n.size() - 10, 10, ".fc.weight") == 0); }
+    long long main_elems = 0;
+    void layout_params() {
+        long long off = 0;
+        for (auto& p : params) if (!is_late(p.name)) { p.off = off; off += (p.numel + 63) / 64 * 64; }
+        main_elems = off;
+        for (auto& p : params) if (is_late(p.name)) { p.off = off; off += (p.numel + 63) / 64 * 64; }
+        flat_elems = off;
+    }
+    // group of a parameter / tape entry for the gradient chunks: d<i> (in_conv + down level i), mid, u<i> (+ out_conv), late
+    std::string group_of(const std::string& n) const {
+        if (is_late(n)) return "late";
+        if (n.rfind("in_conv", 0) == 0) return "d0";
+        if (n.rfind("out_conv", 0) == 0) return "u" + std::to_string(cfg.levels - 1);
+        if (n.rfind("middle", 0) == 0) return "mid";
+        const size_t k = n.find("level_");
+        if (k != std::string::npos) return std::string(n[0] == 'd' ? "d" : "u") + std::to_string(atoi(n.c_str() + k + 6));
+        return "late";
     }
     const ParamInfo& pinfo(const std::string& n) const { return params[pidx.at(n)]; }
     float* PP(const std::string& n) const { return P + pinfo(n).off; }
@@ -504,6 +538,18 @@ struct UnetEngine {
             ++oi;
             if (skip_temb && o.tag == OP_TEMB) {
                 if (o.name == "temb.sin") for (auto& u : temb_uni_ops) { rc = u.run(st); if (rc) return fail(-20, "op '%s' failed: %s", u.name.c_str(), cudaGetErrorString((cudaError_t)rc)); }
+                if (!tev.empty()) cudaEventRecord(tev[oi], st);
+                continue;
+            }
+            if (o.chunk >= 0) {
+                // gradient-chunk boundary: everything the main chain has written so far is joined into the side stream (which
+                // carries the weight-gradient GEMMs), the chunk's gradient unpack runs there, then the chunk's event is recorded
+                cudaStream_t cs_ = (side_stream && !dbg && !no_side) ? side_stream : st;
+                rc = 0;
+                if (cs_ != st) { rc = (int)cudaEventRecord(ev_fork, st); if (!rc) rc = (int)cudaStreamWaitEvent(cs_, ev_fork, 0); main_since_fork = 0; forked = true; }
+                if (!rc) rc = o.run(cs_);
+                if (!rc && chunks[o.chunk].ev) rc = (int)cudaEventRecord(chunks[o.chunk].ev, cs_);
+                if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc));
                 if (!tev.empty()) cudaEventRecord(tev[oi], st);
                 continue;
             }

@@ -84,7 +84,7 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
         out.qs = conv_op(fwd_ops, c, &fwd_flops);
     }
     if (!train) return out;
-    tape.push_back([=]() {
+    tape_push([=]() {
         const T4 dOut = grad_of(out, nullptr);
         colsum_op(p + ".conv2.bias", dOut, nullptr, 0, GP(p + ".conv2.bias"), has_skip ? GP(p + ".skip.bias") : nullptr, cout);
         T4 d_a2 = newT(Bn, h, w, cout);
@@ -135,7 +135,7 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     { ConvSpec c; c.name = p + ".project_out"; c.in = one(O); c.ksize = 1; c.wp = wout.fwd; c.ldw = wout.ld_f; c.bias = PP(p + ".project_out.bias");
       c.residual = bp(x); c.out = out; c.Co = C; c.Ho = h; c.Wo = w; c.want_qstats = true; out.qs = conv_op(fwd_ops, c, &fwd_flops); }
     if (!train) return out;
-    tape.push_back([=]() {
+    tape_push([=]() {
         const T4 dY = grad_of(out, nullptr);
         colsum_op(p + ".project_out.bias", dY, nullptr, 0, GP(p + ".project_out.bias"), nullptr, C);
         T4 dO = newT(Bn, h, w, C);
@@ -173,7 +173,7 @@ inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
     { ConvSpec c; c.name = p; c.in = one(x); c.stride = 2; c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = h / 2; c.Wo = w / 2;
       c.want_qstats = true; out.qs = conv_op(fwd_ops, c, &fwd_flops); }
     if (!train) return out;
-    tape.push_back([=]() {
+    tape_push([=]() {
         const T4 dY = grad_of(out, nullptr);
         colsum_op(p + ".bias", dY, nullptr, 0, GP(p + ".bias"), nullptr, C);
         bool first = true; const T4 dx = grad_of(x, &first);
@@ -223,7 +223,7 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
     { ConvSpec c; c.name = p; c.in = one(up); c.wp = pk.fwd; c.ldw = pk.ld_f; c.bias = PP(p + ".bias"); c.out = out; c.Co = C; c.Ho = 2 * h; c.Wo = 2 * w;
       c.want_qstats = true; out.qs = conv_op(fwd_ops, c, &fwd_flops); }
     if (!train) return out;
-    tape.push_back([=]() {
+    tape_push([=]() {
         const T4 dY = grad_of(out, nullptr);
         colsum_op(p + ".bias", dY, nullptr, 0, GP(p + ".bias"), nullptr, C);
         T4 dUp = newT(Bn, 2 * h, 2 * w, C);
@@ -239,7 +239,9 @@ inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
 
 inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     B = B_; H = H_; W = W_; train = train_; dry = dry_;
-    cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); grads.clear(); once_list.clear();
+    gemm_pair_hint() = train ? 0 : 1;               // CTA-pair GEMM kernels: inference plans only (measured, gemm_build.cuh)
+    cursor = 0; pack_ops.clear(); fwd_ops.clear(); bwd_ops.clear(); tape.clear(); tape_tag.clear(); cur_tag = "late"; grads.clear(); once_list.clear();
+    { std::vector<GradChunk> keep; keep.swap(chunks); for (auto& c : keep) if (c.ev) cudaEventDestroy(c.ev); }
     tp_table_host.clear(); tp_uni_table_host.clear(); fc_table_host.clear(); tpw_table_host.clear(); tpd_table_host.clear(); pack_table_host.clear(); unpack_table_host.clear();
     layer_counter = 0; fwd_flops = bwd_flops = 0; n_tc_gemms = n_generic = 0; plan_error = 0; gather_fused_tail = false;
     const size_t zf_total = zf_cursor, zb_total = zb_cursor;   // sizes learned by the preceding dry pass
@@ -363,7 +365,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     };
     if (train) {
         // adjoint of the embedding MLP; registered first so it runs after every block has deposited its dTP slice
-        tape.push_back([=]() {
+        tape_push([=]() {
             const SgemmParams* tw = at<SgemmParams>(tpw_table_off); const SgemmParams* td = at<SgemmParams>(tpd_table_off);
             const dim3 gw((maxc + 63) / 64, (E + 63) / 64, nblocks), gd((E + 63) / 64, (B + 63) / 64, nblocks);
             if (tc_temb) {
@@ -423,6 +425,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     }
 
     // ---- in_conv (unet.py:127,210): NCHW fp32 -> NHWC bf16
+    cur_tag = "d0";
     T4 h0 = newT(B, H, W, ch);
     {
         const float* wi = PP("in_conv.weight"); const float* bi = PP("in_conv.bias"); bf16* o = bp(h0);
@@ -441,7 +444,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             }
             return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
-        if (train) tape.push_back([=]() {
+        if (train) tape_push([=]() {
             const T4 dY = grad_of(h0, nullptr);
             float* gw = GP("in_conv.weight"); float* gb = GP("in_conv.bias"); const bf16* d = bp(dY);
             const long long P = (long long)Bn * Hn * Wn; const int ppb = 256; const int nb = (int)((P + ppb - 1) / ppb);
@@ -487,17 +490,20 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     };
     for (int i = 0; i < L; ++i) {
         const std::string p = "downsamples.level_" + std::to_string(i);
+        cur_tag = "d" + std::to_string(i);
         for (int j = 0; j < nrb; ++j) hs.push_back(block(p + "." + std::to_string(j), one(hs.back()), chs(i), cfg.attn[i] != 0));
         if (i != L - 1) hs.push_back(down_conv(p + "." + std::to_string(nrb) + ".1", hs.back()));
     }
     // ---- middle (unet.py:132-136,221)
     T4 h = hs.back();
+    cur_tag = "mid";
     { const int off = tp_entry("middle.0", chs(L - 1)); h = res_block("middle.0", one(h), chs(L - 1), off, tp_ld, TP, dTP); }
     h = attn_block("middle.1", h);
     { const int off = tp_entry("middle.2", chs(L - 1)); h = res_block("middle.2", one(h), chs(L - 1), off, tp_ld, TP, dTP); }
     // ---- up path (unet.py:224-230): cat([h, hs.pop()]) is never materialised
     for (int i = L - 1; i >= 0; --i) {
         const std::string p = "upsamples.level_" + std::to_string(i);
+        cur_tag = "u" + std::to_string(i);
         for (int j = 0; j <= nrb; ++j) {
             Src s; s.t0 = h; s.t1 = hs.back(); s.two = true; hs.pop_back();
             h = block(p + "." + std::to_string(j), s, chs(i), cfg.attn[i] != 0);
@@ -506,6 +512,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
     }
     if (blk != nblocks) return fail(-31, "internal: block count mismatch %d vs %d", blk, nblocks);
     // ---- out_conv (unet.py:138-142,232): GN -> SiLU -> conv3x3 (C -> Cout<=4) -> NCHW fp32
+    cur_tag = "u" + std::to_string(L - 1);           // its parameters sit right behind upsamples.level_{L-1} in the flat buffer
     {
         if (ch > 256) return fail(-30, "hid_channels > 256 unsupported by the narrow out_conv kernels");
         T4 a_out = newT(B, H, W, ch);
@@ -564,7 +571,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             // data gradient = a 3x3 "in_conv" Cout -> ch over d_eps with flipped / transposed fp32 weights
             float* wt = at<float>(alloc((size_t)ch * Cout * 9 * 4));
             { PackEntry e; memset(&e, 0, sizeof e); e.kind = PK_FLIP_T; e.Co = Cout; e.Ci = ch; e.taps = 9; e.w = wo; e.fout = wt; pack_table_host.push_back(e); }
-            tape.push_back([=]() {
+            tape_push([=]() {
                 float* gw = GP("out_conv.2.weight"); float* gb = GP("out_conv.2.bias");
                 T4 d_a = newT(B, H, W, ch);
                 bf16* dap = bp(d_a);
@@ -618,14 +625,49 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         push(bwd_ops, "zero.bwd", 0, [=](cudaStream_t st) {
             if (n) { const cudaError_t e = cudaMemsetAsync(z, 0, n, st); if (e) return (int)e; }
             return (int)cudaMemsetAsync(Gp, 0, gbytes, st); }, 0);
-        for (int i = (int)tape.size() - 1; i >= 0; --i) tape[i]();
-        tape.clear();
-        unpack_table_off = alloc(sizeof(PackEntry) * (unpack_table_host.size() + 1));
-        if (!unpack_table_host.empty()) {
-            const PackEntry* tab = at<PackEntry>(unpack_table_off); const int n = (int)unpack_table_host.size();
-            // on the side stream too: ordered after every wgrad GEMM there; the list's final join publishes the flat gradients
-            push(bwd_ops, "wgrad.unpack_all", 0, [=](cudaStream_t st) { launch_k(k_pack_table, dim3(128, n), 256, 0, st, tab); return (int)cudaGetLastError(); }, 1, true);
+        // the tape in reverse; whenever every entry of a level group has run, its slice of the flat gradient buffer is final:
+        // groups are merged into chunks of >= 4 M gradients (16 MB) as long as they stay contiguous, and every chunk boundary
+        // becomes an op that unpacks the chunk's weight gradients on the side stream and records the chunk's event
+        std::map<std::string, std::pair<long long, long long>> range;
+        for (auto& pr : params) {
+            const std::string g = group_of(pr.name);
+            const long long lo = pr.off, hi = pr.off + (pr.numel + 63) / 64 * 64;
+            auto it = range.find(g);
+            if (it == range.end()) range[g] = {lo, hi}; else { if (lo < it->second.first) it->second.first = lo; if (hi > it->second.second) it->second.second = hi; }
         }
+        std::map<std::string, int> remaining;
+        for (auto& tg : tape_tag) ++remaining[tg];
+        // the table must exist before the ops are built: its size is only known after the tape ran, so reserve the worst case
+        const size_t max_unpack = 2 * params.size() + 8;
+        unpack_table_off = alloc(sizeof(PackEntry) * max_unpack);
+        const PackEntry* tab = at<PackEntry>(unpack_table_off);
+        long long pend_lo = -1, pend_hi = -1; int unpack_done = 0;
+        auto emit = [&]() {
+            if (pend_lo < 0) return;
+            GradChunk c; c.lo = pend_lo; c.hi = pend_hi; c.unpack_lo = unpack_done; c.unpack_hi = (int)unpack_table_host.size();
+            unpack_done = c.unpack_hi;
+            const int idx = (int)chunks.size();
+            chunks.push_back(c);
+            const int n = c.unpack_hi - c.unpack_lo; const PackEntry* t0 = tab + c.unpack_lo;
+            Op o; o.name = "grad.chunk" + std::to_string(idx); o.flops = 0; o.launches = n > 0 ? 1 : 0; o.chunk = idx;
+            o.run = [=](cudaStream_t st) { if (n > 0) { launch_k(k_pack_table, dim3(128, n), 256, 0, st, t0); return (int)cudaGetLastError(); } return 0; };
+            bwd_ops.push_back(std::move(o));
+            pend_lo = pend_hi = -1;
+        };
+        for (int i = (int)tape.size() - 1; i >= 0; --i) {
+            tape[i]();
+            const std::string& tg = tape_tag[i];
+            if (--remaining[tg] > 0) continue;
+            auto it = range.find(tg);
+            if (it == range.end()) continue;
+            const long long lo = it->second.first, hi = it->second.second;
+            if (pend_lo >= 0 && !(lo == pend_hi || hi == pend_lo)) emit();          // not adjacent: close the pending chunk first
+            if (pend_lo < 0) { pend_lo = lo; pend_hi = hi; } else { if (lo < pend_lo) pend_lo = lo; if (hi > pend_hi) pend_hi = hi; }
+            if (pend_hi - pend_lo >= (4 << 20) || tg == "late") emit();
+        }
+        emit();
+        if (unpack_table_host.size() > max_unpack) return fail(-31, "internal: gradient unpack table overflow");
+        tape.clear();
     }
     pack_table_off = alloc(sizeof(PackEntry) * (pack_table_host.size() + 1));
     if (!pack_table_host.empty()) {
@@ -660,6 +702,8 @@ inline int UnetEngine::build() {
         if (cudaStreamCreateWithPriority(&hp_stream, cudaStreamNonBlocking, greatest) || cudaEventCreateWithFlags(&ev_hp_fork, cudaEventDisableTiming) ||
             cudaEventCreateWithFlags(&ev_hp_join, cudaEventDisableTiming)) return fail(-2, "priority stream creation failed");
     }
+    for (auto& c : chunks)
+        if (!c.ev && cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming)) return fail(-2, "gradient-chunk event creation failed");
     planned = true;
     return 0;
 }

@@ -364,8 +364,8 @@ def _ddp_allreduce(wrapper, model):
         return
     if not hasattr(wrapper, "process_group") and not hasattr(wrapper, "module"):
         return
-    from .parallel import allreduce_mean_
-    allreduce_mean_(model._grads, group=getattr(wrapper, "process_group", None))
+    from .parallel import allreduce_grads_overlapped_
+    allreduce_grads_overlapped_(model, group=getattr(wrapper, "process_group", None))     # chunk-wise, overlapped with the backward's tail
 
 
 def _native_sample_loop(diffusion, model, x, gen, rng, seed, use_graph, split=None):

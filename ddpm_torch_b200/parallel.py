@@ -38,3 +38,46 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
 def rank_seeds(rank: int):
     """utils/train.py:115-117: per-rank generator seeds for (t, noise) and for preview sampling."""
     return 8191 + rank, 131071 + rank
+
+
+def grad_chunks(model):
+    """[(lo, hi)] element ranges of the model's flat gradient buffer in the order the backward pass completes them."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    lo, hi = (C.c_longlong * 64)(), (C.c_longlong * 64)()
+    n = L.ddpm_unet_grad_chunks(model._h, 64, lo, hi)
+    if n < 0:
+        _lib.check(n, "grad_chunks")
+    return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+
+def allreduce_grads_overlapped_(model, group=None):
+    """Mean all-reduce of the flat gradient buffer, chunk by chunk, OVERLAPPED with the tail of the backward pass: call it right
+    after the (asynchronous) backward launch.  Every chunk is reduced on a communication stream that waits only for that chunk's
+    completion event inside the engine's backward (ddpm_unet_wait_grad_chunk); the current stream finally waits for the
+    communication stream.  This is what DDP's bucketed reducer does for the reference (train.py:110), with the engine's own
+    level-group chunks as buckets and the flat buffer as the message."""
+    from . import _lib
+    flat = model._grads
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or flat is None:
+        return flat
+    if model._acc_pending:                      # gradient accumulation in flight: reduce the folded buffer in one piece
+        return allreduce_mean_(model.flat_grads, group)
+    L = _lib.lib()
+    dev = flat.device
+    chunks = getattr(model, "_grad_chunks", None)
+    if chunks is None or model._grad_chunks_key != model._plan_key:
+        chunks = model._grad_chunks = grad_chunks(model)
+        model._grad_chunks_key = model._plan_key
+        assert sum(h - l for l, h in chunks) == flat.numel() and min(l for l, _ in chunks) == 0
+    comm = getattr(model, "_comm_stream", None)
+    if comm is None or comm.device != dev:
+        comm = model._comm_stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.device(dev):
+        for i, (lo, hi) in enumerate(chunks):
+            _lib.check(L.ddpm_unet_wait_grad_chunk(model._h, i, comm.cuda_stream), "wait_grad_chunk")
+            with torch.cuda.stream(comm):
+                allreduce_mean_(flat[lo:hi], group)
+        torch.cuda.current_stream(dev).wait_stream(comm)
+    return flat

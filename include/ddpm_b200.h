@@ -65,6 +65,8 @@ typedef struct ddpm_gemm_desc {
     int o_mul, o_py, o_px;
     int kk_splits;                     /* mode 0: split the K loop over grid_z = kk_splits CTAs per tile (fp32 atomic output) */
     ddpm_gn_epi gn;                    /* mode 0 only, rows = NHWC pixels with H*W % 32 == 0 */
+    int cta_pair;                      /* modes 0 / 1: 0 = library policy, 1 = single-CTA kernel, 2 = CTA-pair kernel (tcgen05 cta_group::2,
+                                        * M = 256; error when the shape is not eligible), 3 = CTA-pair kernel when eligible */
 } ddpm_gemm_desc;
 int ddpm_gemm_run(const ddpm_gemm_desc* d, void* stream);
 
@@ -134,6 +136,13 @@ int ddpm_sampler_step(ddpm_unet* h, float* x, const float* z, uint64_t seed, voi
 /* Same step, additionally writing the clipped x_0 prediction of diffusion.py:122,130 to pred_x0 f32[B,C,H,W] (NULL = skip):
  * GaussianDiffusion.p_sample_progressive (diffusion.py:176-198, p_sample_step(..., return_pred=True)). */
 int ddpm_sampler_step_pred(ddpm_unet* h, float* x, const float* z, uint64_t seed, float* pred_x0, void* stream);
+/* Data-parallel training (train.py:110 DDP, utils/train.py:149-153): the backward pass finishes the flat gradient buffer in
+ * contiguous CHUNKS, level group by level group, and records a CUDA event per chunk.  grad_chunks returns their number and
+ * fills lo/hi (element offsets into the flat buffer, in completion order; together they tile it exactly); wait_grad_chunk makes
+ * `stream` wait for chunk i of the most recent ddpm_unet_backward / ddpm_train_backward, so that the caller can all-reduce that
+ * chunk on a communication stream while the rest of the backward is still running.  Needs a training plan. */
+int ddpm_unet_grad_chunks(const ddpm_unet* h, int max_n, long long* lo, long long* hi);
+int ddpm_unet_wait_grad_chunk(ddpm_unet* h, int i, void* stream);
 /* Introspection for tests / bench: op counts and algorithmic FLOPs of the compiled plan. */
 int ddpm_unet_plan_stats(const ddpm_unet* h, int* n_fwd_ops, int* n_bwd_ops, int* n_tensorcore_ops, int* n_generic_ops,
                          double* fwd_flops, double* bwd_flops);

@@ -74,16 +74,25 @@ def test_param_inventory_is_the_reference_state_dict(L, cfg, n_params):
     h = _handle(L, cfg)
     shapes = R.param_shapes(cfg)
     assert L.ddpm_unet_num_params(h) == len(shapes)
-    total, prev_end = 0, 0
+    total, ranges = 0, []
     for i, (k, s) in enumerate(shapes.items()):
         nm, nd, dims, off = C.c_char_p(), C.c_int(), (C.c_int * 4)(), C.c_longlong()
         assert L.ddpm_unet_param_info(h, i, C.byref(nm), C.byref(nd), C.byref(dims), C.byref(off)) == 0
-        assert nm.value.decode() == k and tuple(dims[:nd.value]) == tuple(s)
-        assert off.value >= prev_end and off.value % 64 == 0
-        prev_end = off.value + math.prod(s); total += math.prod(s)
+        assert nm.value.decode() == k and tuple(dims[:nd.value]) == tuple(s)           # the LIST is the reference's state_dict order
+        assert off.value % 64 == 0
+        ranges.append((off.value, off.value + math.prod(s), k)); total += math.prod(s)
     if n_params:
         assert total == n_params
-    assert L.ddpm_unet_flat_elems(h) >= prev_end
+    # memory placement: registration order, except that the embedding MLP and the fc.weight tensors (whose gradients only exist
+    # at the very end of the backward pass) sit behind everything else, so the rest completes in contiguous per-level chunks
+    ranges.sort()
+    for (a0, a1, _), (b0, b1, _) in zip(ranges, ranges[1:]):
+        assert a1 <= b0
+    assert L.ddpm_unet_flat_elems(h) >= ranges[-1][1]
+    late = [k for _, _, k in ranges if k.startswith("embed.") or k.endswith(".fc.weight")]
+    assert [k for _, _, k in ranges][-len(late):] == late
+    main = [k for _, _, k in ranges][:-len(late)]
+    assert main == [k for k in shapes if k not in set(late)]
     L.ddpm_unet_destroy(h)
 
 

@@ -333,3 +333,38 @@ def test_celeba64_config_fwd_bwd():
     t = torch.randint(1000, (8,), device=DEV, generator=g)
     noise = torch.randn(8, 3, 64, 64, device=DEV, generator=g)
     grads_vs_oracle(m, sd, CELEBA64_CFG, x0, t, noise, "celeba 64x64 bs=8 train", chunk=4)
+
+
+def test_gradient_chunks_tile_the_flat_buffer(golden):
+    """data-parallel seam: the backward completes the flat gradient buffer in contiguous chunks (ddpm_unet_grad_chunks) that
+    tile it exactly; waiting for a chunk's event on another stream and reading the chunk there sees the final gradients."""
+    import ddpm_torch_b200 as D
+    from ddpm_torch_b200 import _lib, parallel
+    fx = golden("unet_cifar10_bs4.pt")
+    m, sd = build(fx["cfg"], fx["seed"], train=True)
+    diff = D.GaussianDiffusion(D.get_beta_schedule("linear", 1e-4, 0.02, 1000), "eps", "fixed-large", "mse")
+    x0, t, noise = fx["x0"].to(DEV), fx["t"].to(DEV), fx["noise"].to(DEV)
+    diff.train_losses(m, x0, t, noise).mean().backward()
+    ref = m.flat_grads.clone()
+    chunks = parallel.grad_chunks(m)
+    print(f"\n[grad chunks] {len(chunks)} chunks: " + ", ".join(f"[{lo / 1e6:.2f}M, {hi / 1e6:.2f}M)" for lo, hi in chunks))
+    assert len(chunks) >= 3
+    cover = sorted(chunks)
+    assert cover[0][0] == 0 and cover[-1][1] == m.flat_grads.numel() and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    # second backward: copy every chunk out on a side stream as soon as its event fires
+    m.zero_grad()
+    L = _lib.lib()
+    loss = diff.train_losses(m, x0, t, noise).mean()
+    got = torch.zeros_like(ref)
+    loss.backward()
+    side = torch.cuda.Stream()
+    for i, (lo, hi) in enumerate(chunks):
+        _lib.check(L.ddpm_unet_wait_grad_chunk(m._h, i, side.cuda_stream))
+        with torch.cuda.stream(side):
+            got[lo:hi].copy_(m._grads[lo:hi])
+    side.synchronize()
+    torch.cuda.synchronize()
+    r = rel(got, ref)
+    print(f"[grad chunks] chunk-wise copy vs first backward rel-L2 {r:.3e}")
+    assert r < 1e-2
+    flag_ok()

@@ -26,11 +26,24 @@ def bf(*shape, scale=1.0, seed=0):
     return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
 
 
+_PAIR = 0
+
+
+@pytest.fixture(autouse=True, params=["single", "pair"])
+def pairmode(request):
+    """every engine test runs on the single-CTA kernels (cta_pair = 1) and on the tcgen05 cta_group::2 CTA-pair kernels wherever
+    the shape is eligible (cta_pair = 3: N % 128 == 0 and an even number of 128-row tiles; K-major and MN-major modes)"""
+    global _PAIR
+    _PAIR = 1 if request.param == "single" else 3
+    yield
+
+
 def new_desc():
     from ddpm_torch_b200._lib import GemmDesc
     d = GemmDesc()
     d.alpha = 1.0
     d.grid_z = 1
+    d.cta_pair = _PAIR
     return d
 
 
