@@ -46,7 +46,7 @@ class HaloDesc(C.Structure):
         ("w", C.c_void_p), ("ldw", C.c_longlong), ("Ktot", C.c_int),
         ("out", C.c_void_p), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int), ("residual", C.c_void_p),
         ("base_offset_mode", C.c_int), ("force_sub", C.c_int),
-        ("gn", GnEpi),
+        ("gn", GnEpi), ("xf_K", C.c_void_p), ("xf_silu", C.c_int),
     ]
 
 

@@ -32,6 +32,8 @@ struct HaloParams {
     const __nv_bfloat16* residual; int ldr;
     int desc_base_offset_mode; // 0 (default, correct): base_offset field = 0 ; 1: (start>>7)&7 (probe knob, wrong on B200)
     GnEpi gn;                  // GroupNorm statistics of the output (gn_epilogue.cuh); null = off
+    const float* xfK; int xfC, xf_silu;   // CTA-pair kernel only (conv_halo2.cuh): GroupNorm(+SiLU) of the 3x3 input applied in shared memory;
+                                          // xfK [NB][4][xfC] = {sc, sh, ..} per (image, input channel), null = off
 };
 
 template <int BLOCK_N, int SUB>
@@ -319,6 +321,8 @@ inline int build_halo(const HaloDesc& d, HaloLaunch& g) {
     p.N = d.Cout; p.out = d.out; p.ldo = d.Cout; p.bias = d.bias; p.rowvec = d.rowvec; p.rowvec_ld = d.rowvec_ld;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual); p.ldr = d.Cout; p.desc_base_offset_mode = d.base_offset_mode;
     p.gn = gn_epi_from_abi(d.gn);
+    p.xfK = d.xf_K; p.xfC = d.a_C[d.seg_map[0]]; p.xf_silu = d.xf_silu;
+    if (p.xfK && !(g.pair && d.seg_taps[0] == 9 && d.seg_map[0] == 0)) return fail(-12, "halo conv: the fused GroupNorm input transform needs the CTA-pair kernel and a 3x3 first segment on map 0");
     p.nseg = d.nseg;
     const int P = 8 * sub + 2;
     int rc;

@@ -33,8 +33,17 @@ struct Halo2Cfg {
     static constexpr int TOTAL = NA * A_STRIDE + NB_ST * B_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*bias vector*/;
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+// XF = 1 (inference plans): the 3x3 segment's input is the RAW GroupNorm input x; four extra "transform" warps rewrite every
+// haloed A tile in shared memory between its TMA landing and the MMAs: y = silu(sc*x + sh) with the per-(image, channel)
+// constants K = {sc, sh} of the norm (out-of-image halo pixels stay zero = the conv's padding of the NORMALISED tensor).
+// The elementwise rewrite keeps the 128-byte swizzle (it is in place), so the UMMA descriptors are unchanged.  This removes the
+// GroupNorm-apply pass (read x + write a, 4 B/element) and the `a` tensor of unet.py:83-89 from the sampler's forward.
+// Protocol: with XF each CTA's A box completes on its OWN full_a barrier; its transform warps wait there, rewrite, fence the
+// generic-proxy writes for the async proxy and arrive on the LEADER's ready_a barrier (2 CTAs x 4 warps), which the MMA thread
+// waits on instead of full_a.
+constexpr int HALO_XF_WARPS = 8;       // 4 warps rewrote a 23 KB tile in ~2600 cycles > the 2304 MMA cycles of an N=128 chunk (measured: conv 2x slower)
+template <int BLOCK_N, int XF>
+__global__ void __launch_bounds__(HALO_THREADS + 32 * HALO_XF_WARPS * XF, 1)
 conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                      const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const HaloParams p) {
@@ -52,7 +61,8 @@ conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     uint64_t* empty_b = full_b + CF::NB_ST;
     uint64_t* tmem_full = empty_b + CF::NB_ST;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]  (the LEADER's copy collects the arrivals of both CTAs)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* ready_a = tmem_empty + 2;             // [NA]  XF: "tile rewritten by the transform warps of both CTAs" (leader's copy)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_a + CF::NA);
     float* s_vec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_a) + 512);
     const uint32_t s_vec_u32 = smem_u32(s_vec);
 
@@ -66,7 +76,7 @@ conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmB);
-        for (int s = 0; s < CF::NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < CF::NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); mbar_init(&ready_a[s], 2 * HALO_XF_WARPS); }
         for (int s = 0; s < CF::NB_ST; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * HALO_EPI_WARPS); }
         fence_mbar_init();
@@ -98,9 +108,15 @@ conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
                             const int sa = ia % CF::NA; const uint32_t ph = (ia / CF::NA) & 1;
                             if (!mbar_wait(&empty_a[sa], ph ^ 1, 5)) { ok = false; break; }
                             const uint32_t bytes = (sg.taps == 9) ? (uint32_t)CF::A_BYTES : (uint32_t)(16 * 8 * 128);
-                            if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * bytes);       // both CTAs' boxes complete here
-                            if (sg.taps == 9) tma_load_4d_2cta(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0 - 1, y0 - 1, n);
-                            else              tma_load_4d_2cta(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
+                            if (XF) {            // own barrier: the local transform warps pick the tile up
+                                mbar_expect_tx(&full_a[sa], bytes);
+                                if (sg.taps == 9) tma_load_4d(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0 - 1, y0 - 1, n);
+                                else              tma_load_4d(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
+                            } else {
+                                if (rank == 0) mbar_expect_tx(&full_a[sa], 2 * bytes);       // both CTAs' boxes complete here
+                                if (sg.taps == 9) tma_load_4d_2cta(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0 - 1, y0 - 1, n);
+                                else              tma_load_4d_2cta(smA + sa * CF::A_STRIDE, mA, &full_a[sa], sg.c_base + kc * 64, x0, y0, n);
+                            }
                             ++ia;
                         }
                         for (int tp = 0; tp < sg.taps; tp += CF::TPS) {
@@ -135,7 +151,7 @@ conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
                     const HaloSeg sg = p.seg[s];
                     for (int kc = 0; kc < sg.kchunks && ok; ++kc) {
                         const int sa = ia % CF::NA; const uint32_t pha = (ia / CF::NA) & 1;
-                        if (!mbar_wait(&full_a[sa], pha, 7)) { ok = false; break; }
+                        if (!mbar_wait(XF ? &ready_a[sa] : &full_a[sa], pha, 7)) { ok = false; break; }
                         const uint32_t a_base = smem_u32(smA + sa * CF::A_STRIDE);
                         for (int tp0 = 0; tp0 < sg.taps; tp0 += CF::TPS) {
                             const int nt = (sg.taps - tp0 < CF::TPS) ? sg.taps - tp0 : CF::TPS;
@@ -166,6 +182,62 @@ conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
                     }
                 }
                 if (ok) umma_commit_2cta(&tmem_full[acc], 3);
+            }
+        }
+    } else if (XF && warp >= 2 + HALO_EPI_WARPS) {
+        // ======================= transform warps (both CTAs): GroupNorm + SiLU on the landed A tile =======================
+        const int tid_x = (warp - 2 - HALO_EPI_WARPS) * 32 + lane;      // 0..255
+        constexpr int XROWS = 4 * HALO_XF_WARPS;                        // tile rows covered per pass (8 threads per 128-byte row)
+        const int c = tid_x & 7, r0 = tid_x >> 3;                      // logical 16-byte chunk (8 channels), first tile row
+        int ia = 0;
+        bool ok = true;
+        for (int t = pair_id; t < total_pairs && ok; t += n_pairs_grid) {
+            const int m_tile = (t % m_pairs) * 2 + (int)rank;
+            const int n = m_tile / tiles_per_img, r = m_tile % tiles_per_img;
+            const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+            for (int s = 0; s < p.nseg && ok; ++s) {
+                const HaloSeg sg = p.seg[s];
+                const bool do_xf = sg.taps == 9 && sg.map == 0 && p.xfK != nullptr;
+                for (int kc = 0; kc < sg.kchunks && ok; ++kc, ++ia) {
+                    const int sa = ia % CF::NA; const uint32_t ph = (ia / CF::NA) & 1;
+                    float sc[8], sh[8];
+                    if (do_xf) {         // the tile's image and this thread's 8 channels: issued before the wait (hides behind the TMA)
+                        const float* Kn = p.xfK + (long long)n * 4 * p.xfC + sg.c_base + kc * 64 + c * 8;
+                        const float4 a0 = __ldg(reinterpret_cast<const float4*>(Kn)), a1 = __ldg(reinterpret_cast<const float4*>(Kn) + 1);
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(Kn + p.xfC)), b1 = __ldg(reinterpret_cast<const float4*>(Kn + p.xfC) + 1);
+                        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+                        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+                    }
+                    if (!mbar_wait(&full_a[sa], ph, 8)) { ok = false; break; }
+                    if (do_xf && !(p.xf_silu & 4)) {          // (bit 2: experiment knob - protocol only, no rewrite)
+                        uint8_t* base = smA + sa * CF::A_STRIDE;
+#pragma unroll
+                        for (int rr = r0; rr < 18 * P; rr += XROWS) {
+                            const int yy = rr / P, xx = rr - yy * P;
+                            const int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+                            if (gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;      // zero padding of the normalised tensor
+                            uint4* ptr = reinterpret_cast<uint4*>(base + rr * 128 + ((c ^ (rr & 7)) << 4));
+                            uint4 u = *ptr;
+                            __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 v = __bfloat1622float2(hp[e]);
+                                float y0f = fmaf(v.x, sc[2 * e], sh[2 * e]), y1f = fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1]);
+                                if (p.xf_silu & 1) {
+                                    float t0, t1;
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0f));
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1f));
+                                    y0f *= fmaf(0.5f, t0, 0.5f); y1f *= fmaf(0.5f, t1, 0.5f);
+                                }
+                                hp[e] = __floats2bfloat162_rn(y0f, y1f);
+                            }
+                            *ptr = u;
+                        }
+                        if (!(p.xf_silu & 8)) fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&ready_a[sa], 0);
+                }
             }
         }
     } else {
@@ -264,10 +336,10 @@ inline bool halo_pair_eligible(int NB, int H, int W, int Cout) {
     return bn >= 128 && (m_tiles % 2) == 0;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int XF>
 inline int launch_halo2_inst(const HaloLaunch& g, cudaStream_t st) {
     using CF = Halo2Cfg<BLOCK_N>;
-    auto kern = conv3x3_halo2_kernel<BLOCK_N>;
+    auto kern = conv3x3_halo2_kernel<BLOCK_N, XF>;
     static_assert(CF::TOTAL <= 232448, "halo pair conv: shared memory budget (227 KB) exceeded");
     static bool attr_done = false;
     if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::TOTAL)); attr_done = true; }
@@ -276,7 +348,7 @@ inline int launch_halo2_inst(const HaloLaunch& g, cudaStream_t st) {
     const int pairs_total = g.tiles / 2;
     int pairs = num_sms / 2; if (pairs > pairs_total) pairs = pairs_total;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(HALO_THREADS); cfg.dynamicSmemBytes = CF::TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(HALO_THREADS + 32 * HALO_XF_WARPS * XF); cfg.dynamicSmemBytes = CF::TOTAL; cfg.stream = st;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
@@ -287,8 +359,13 @@ inline int launch_halo2_inst(const HaloLaunch& g, cudaStream_t st) {
     return 0;
 }
 inline int launch_halo2(const HaloLaunch& g, cudaStream_t st) {
-    if (g.block_n == 128) return launch_halo2_inst<128>(g, st);
-    if (g.block_n == 256) return launch_halo2_inst<256>(g, st);
+    if (g.p.xfK) {
+        if (g.block_n == 128) return launch_halo2_inst<128, 1>(g, st);
+        if (g.block_n == 256) return launch_halo2_inst<256, 1>(g, st);
+    } else {
+        if (g.block_n == 128) return launch_halo2_inst<128, 0>(g, st);
+        if (g.block_n == 256) return launch_halo2_inst<256, 0>(g, st);
+    }
     return fail(-6, "unsupported halo pair conv variant");
 }
 

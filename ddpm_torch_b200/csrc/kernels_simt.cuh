@@ -359,6 +359,20 @@ __global__ void __launch_bounds__(256, 4) k_gn_apply(const GnApply a, int pix_pe
     }
 }
 
+// Per-(image, channel) GroupNorm constants K from the producers' quad statistics WITHOUT a pass over the tensor: inference plans
+// whose consumer conv applies the norm in its operand path (conv_halo2.cuh, XF).  grid = B, one thread per channel.
+__global__ void __launch_bounds__(256) k_gn_prep(const GnApply a) {
+    pdl_entry();
+    const int C = a.s.C0 + a.s.C1, cg = C >> 5, b = blockIdx.x;
+    float* Kb = a.Kout + (long long)b * 4 * C;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        float m, r;
+        gn_group_from_quads(a, b, ch, cg, m, r);
+        const float sc = r * __ldg(a.gamma + ch);
+        Kb[ch] = sc; Kb[C + ch] = __ldg(a.beta + ch) - m * sc; Kb[2 * C + ch] = r; Kb[3 * C + ch] = m * r;
+    }
+}
+
 // Small feature maps (H*W <= 64: the 4x4 / 8x8 levels, whose producers are split-K finalizers without a statistics epilogue):
 // ONE block per image computes the group statistics and applies the norm in the same launch (the image is 8-32 KB and is
 // re-read from L1/L2), instead of a statistics launch + an apply launch.  blockDim.x = (256/oct)*oct as for k_gn_apply.

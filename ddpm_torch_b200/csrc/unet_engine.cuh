@@ -166,7 +166,34 @@ struct UnetEngine {
         const float* bias = nullptr; const float* rowvec = nullptr; int rowvec_ld = 0; const bf16* residual = nullptr;
         T4 out; float* out_nchw = nullptr; int Co = 0; int Ho = 0, Wo = 0; bool accumulate = false;
         bool want_qstats = false;          // the output feeds a GroupNorm -> statistics in the epilogue when the kernel can
+        const float* xfK = nullptr; int xf_silu = 0;   // inference: `in` is the RAW GroupNorm input, the conv applies act(sc*x + sh) in its
+                                                       // operand path (CTA-pair haloed kernel only; see xf_ok / gn_prep_xf)
     };
+    // GroupNorm(+SiLU) folded into the consumer 3x3 conv's operand path (conv_halo2.cuh XF): inference plans, single-source input with
+    // producer statistics, and a conv that takes the CTA-pair haloed kernel.
+    // OPT-IN (DDPM_XF=1, read at plan time): measured on B200 (profiles/r02_halo_xf_experiment.txt) the rewrite of the landed tile
+    // costs the conv +46 % in isolation (+17 % for the extra barrier hop alone, the rest for the rewrite competing for the shared-memory
+    // bandwidth the MMAs already saturate) against the ~40 % of a conv that the removed apply pass takes - break-even at best, and
+    // the whole sampler step got slower (4.68 -> 5.09 ms at bs=256).  Kept, with unit and network parity tests, for hardware /
+    // configurations where the balance differs.
+    bool xf_ok(const Src& x, int Co, int h, int w) const {
+        const char* on = getenv("DDPM_XF");
+        const bool off = !on || atoi(on) == 0 || getenv("DDPM_NO_GN_EPI") != nullptr || getenv("DDPM_NO_HALO") != nullptr ||
+                         (getenv("DDPM_HALO_PAIR") && atoi(getenv("DDPM_HALO_PAIR")) == 0);
+        if (off || train || x.two || x.t0.qs < 0 || x.t0.C % 128 || Co % 128) return false;
+        if (!halo_eligible(h, w, Co) || !tc_ok_geom(h, w)) return false;
+        return (((long long)x.t0.B * (h / 16) * (w / 8)) % 2) == 0;
+    }
+    float* gn_prep_xf(std::vector<Op>& L, const std::string& name, const Src& in, const std::string& pname) {
+        const int C = in.C(), Bn = in.t0.B, HW = in.t0.H * in.t0.W;
+        float* K = at<float>(alloc((size_t)Bn * 4 * C * 4));
+        GnApply a; memset(&a, 0, sizeof a);
+        a.s = gsrc(in); a.HW = HW; a.qs0 = at<double>((size_t)in.t0.qs); a.qs1 = nullptr;
+        a.gamma = PP(pname + ".weight"); a.beta = PP(pname + ".bias"); a.eps = 1e-6f; a.Kout = K;
+        const int thr = C < 256 ? C : 256;
+        push(L, name + ".prep", 0, [a, Bn, thr](cudaStream_t st) { launch_k(k_gn_prep, Bn, thr, 0, st, a); return (int)cudaGetLastError(); });
+        return K;
+    }
     // epilogue fusion of a conv: fills `gn` and returns the workspace offset of the quad statistics (-1: none)
     long long conv_gn_epi(const ConvSpec& c, ddpm_gn_epi& gn) {
         memset(&gn, 0, sizeof gn);
@@ -209,6 +236,7 @@ struct UnetEngine {
             h.w = c.wp; h.ldw = c.ldw; h.Ktot = (int)K; h.out = bp(c.out); h.bias = c.bias; h.rowvec = c.rowvec; h.rowvec_ld = c.rowvec_ld;
             h.residual = c.accumulate ? (const void*)bp(c.out) : (const void*)c.residual; h.base_offset_mode = 0;
             const long long qs = conv_gn_epi(c, h.gn);
+            if (c.xfK) { h.xf_K = c.xfK; h.xf_silu = c.xf_silu; h.force_sub = 3; }
             ++n_tc_gemms;
             if (dry) { push(L, c.name, fl, [](cudaStream_t) { return 0; }); return qs; }
             HaloLaunch g; int rc = build_halo(h, g);
@@ -216,6 +244,7 @@ struct UnetEngine {
             push(L, c.name + "[halo]", fl, [g](cudaStream_t st) { return launch_halo(g, st); });
             return qs;
         }
+        if (c.xfK) { plan_error = fail(-31, "internal: conv '%s' was planned with a fused GroupNorm input but did not take the CTA-pair haloed kernel", c.name.c_str()); return -1; }
         if (tc) {
             ddpm_gemm_desc d; memset(&d, 0, sizeof d);
             d.mode = GEMM_KK; d.M = (int)Pout; d.N = c.Co; d.W = c.Wo; d.H = c.Ho; d.NB = Bn;

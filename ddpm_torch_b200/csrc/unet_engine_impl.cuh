@@ -54,18 +54,23 @@ inline void UnetEngine::bmm(std::vector<Op>& L, const std::string& name, int for
 inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, int tp_off, int tp_ld, float* TP, float* dTP) {
     const int cin = x.C(), Bn = x.t0.B, h = x.t0.H, w = x.t0.W;
     const bool has_skip = cin != cout;
-    T4 a1 = newT(Bn, h, w, cin);
-    const GnSaved g1 = gn_fwd(fwd_ops, p + ".norm1", x, p + ".norm1", a1, 1, 0.f);
+    // inference plans: norm + SiLU ride in the consumer conv's operand path (no `a` tensor, no apply pass) where the conv can
+    const bool xf1 = xf_ok(x, cout, h, w);
+    T4 a1; GnSaved g1{}; const float* K1 = nullptr;
+    if (xf1) K1 = gn_prep_xf(fwd_ops, p + ".norm1", x, p + ".norm1");
+    else { a1 = newT(Bn, h, w, cin); g1 = gn_fwd(fwd_ops, p + ".norm1", x, p + ".norm1", a1, 1, 0.f); }
     const Packed w1 = pack_conv(p + ".conv1", cout, cin, 3, 0, true, true);
     T4 h1 = newT(Bn, h, w, cout);
     {
-        ConvSpec c; c.name = p + ".conv1"; c.in = one(a1); c.wp = w1.fwd; c.ldw = w1.ld_f; c.bias = PP(p + ".conv1.bias");
+        ConvSpec c; c.name = p + ".conv1"; c.in = xf1 ? x : one(a1); c.xfK = K1; c.xf_silu = 1; c.wp = w1.fwd; c.ldw = w1.ld_f; c.bias = PP(p + ".conv1.bias");
         c.rowvec = TP + tp_off; c.rowvec_ld = tp_ld; c.out = h1; c.Co = cout; c.Ho = h; c.Wo = w;
         c.want_qstats = true;                       // h1 feeds norm2: its statistics come out of this conv's epilogue
         h1.qs = conv_op(fwd_ops, c, &fwd_flops);
     }
-    T4 a2 = newT(Bn, h, w, cout);
-    const GnSaved g2 = gn_fwd(fwd_ops, p + ".norm2", one(h1), p + ".norm2", a2, 1, cfg.drop_rate);
+    const bool xf2 = xf_ok(one(h1), cout, h, w);
+    T4 a2; GnSaved g2{}; const float* K2 = nullptr;
+    if (xf2) K2 = gn_prep_xf(fwd_ops, p + ".norm2", one(h1), p + ".norm2");
+    else { a2 = newT(Bn, h, w, cout); g2 = gn_fwd(fwd_ops, p + ".norm2", one(h1), p + ".norm2", a2, 1, cfg.drop_rate); }
     const Packed w2 = pack_conv(p + ".conv2", cout, cout, 3, has_skip ? cin : 0, true, true);
     bf16* wsd = nullptr; float* bias2 = PP(p + ".conv2.bias");
     if (has_skip) {
@@ -77,7 +82,7 @@ inline T4 UnetEngine::res_block(const std::string& p, const Src& x, int cout, in
     }
     T4 out = newT(Bn, h, w, cout);
     {
-        ConvSpec c; c.name = p + ".conv2"; c.in = one(a2); c.wp = w2.fwd; c.ldw = w2.ld_f; c.bias = bias2;
+        ConvSpec c; c.name = p + ".conv2"; c.in = xf2 ? one(h1) : one(a2); c.xfK = K2; c.xf_silu = 1; c.wp = w2.fwd; c.ldw = w2.ld_f; c.bias = bias2;
         c.has_skip = has_skip; c.skip_in = x; c.residual = has_skip ? nullptr : bp(x.t0);
         c.out = out; c.Co = cout; c.Ho = h; c.Wo = w;
         c.want_qstats = true;                       // block outputs feed the next norm1 / attention norm / out_conv.0 (and, as skips, the up path)

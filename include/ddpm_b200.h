@@ -84,6 +84,10 @@ typedef struct ddpm_halo_desc {
     int base_offset_mode;              /* 0 = descriptor base_offset field left 0 (correct on B200); 1 = (addr>>7)&7 (probe) */
     int force_sub;                     /* 0 = auto; 1 / 2 = single-CTA kernel with that many 16x8 sub-tiles per CTA; 3 = CTA-pair kernel (cta_group::2) */
     ddpm_gn_epi gn;
+    /* force_sub = 3 / CTA-pair kernel only: the 3x3 segment's input (map 0) is the RAW input of a GroupNorm(+SiLU); the kernel
+     * applies y = act(sc*x + sh) to every landed tile in shared memory (unet.py:83-84: conv(act(norm(x)))), xf_K [NB][4][C] holding
+     * {sc, sh, ...} per (image, channel).  NULL = off. */
+    const float* xf_K; int xf_silu;
 } ddpm_halo_desc;
 int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream);
 

@@ -368,3 +368,24 @@ def test_gradient_chunks_tile_the_flat_buffer(golden):
     print(f"[grad chunks] chunk-wise copy vs first backward rel-L2 {r:.3e}")
     assert r < 1e-2
     flag_ok()
+
+
+def test_operand_path_groupnorm_optin(golden, monkeypatch):
+    """DDPM_XF=1 (opt-in, measured slower - profiles/r02_halo_xf_experiment.txt): inference plans fold norm + SiLU into the consumer
+    conv's operand path (transform warps of the CTA-pair kernel).  Same parity bar as the default path."""
+    monkeypatch.setenv("DDPM_XF", "1")
+    fx = golden("unet_cifar10_bs4.pt")
+    cfg = fx["cfg"]
+    m, sd = build(cfg, fx["seed"])
+    g = torch.Generator(DEV).manual_seed(3)
+    x = torch.randn(8, 3, 32, 32, device=DEV, generator=g); t = torch.randint(1000, (8,), device=DEV, generator=g)
+    with torch.no_grad():
+        eps = m(x, t)
+        ref = R.unet_forward(sd, cfg, x, t)
+    n_fwd = C.c_int()
+    from ddpm_torch_b200 import _lib
+    _lib.lib().ddpm_unet_launch_counts(m._h, C.byref(n_fwd), None, None)
+    r = rel(eps, ref)
+    print(f"\n[DDPM_XF=1] eps rel-L2 {r:.3e}; launches per forward {n_fwd.value}")
+    assert r < 1e-2 and n_fwd.value < 150
+    flag_ok()

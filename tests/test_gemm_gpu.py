@@ -406,3 +406,39 @@ def test_kk_gemm_quad_stats_epilogue(B, H, W, N):
     want = torch.stack([r4.sum(dim=(1, 3)), (r4 * r4).sum(dim=(1, 3))], dim=-1)
     assert rel(out.float().view(B, H, W, N), ref) < 4e-3
     assert rel(qs[..., 1], want[..., 1]) < 1e-5 and (qs[..., 0] - want[..., 0]).abs().max().item() < 1e-3 * want[..., 1].sqrt().max().item()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 16), (2, 16, 8)])
+@pytest.mark.parametrize("Cin,Cout,skip", [(128, 128, False), (256, 256, False), (128, 256, True)])
+def test_conv_halo_pair_fused_groupnorm_input(B, H, W, Cin, Cout, skip):
+    """CTA-pair kernel with transform warps: out = conv3x3(silu(sc*x + sh)) (+ fused 1x1 skip over RAW tensors), zero padding applied
+    to the NORMALISED tensor (unet.py:83-84: conv(act(norm(x))))."""
+    from ddpm_torch_b200._lib import HaloDesc
+    x = bf(B, H, W, Cin, seed=1)
+    K = torch.randn(B, 4, Cin, device="cuda") * 0.8
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    parts = [pack_w(w)]
+    C1 = 64
+    x1 = bf(B, H, W, C1, seed=2)
+    ws = torch.randn(Cout, C1, 1, 1, device="cuda") * 0.1
+    if skip:
+        parts.append(pack_w(ws))
+    wp = torch.cat(parts, dim=1).contiguous()
+    bias = torch.randn(Cout, device="cuda")
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = HaloDesc()
+    d.NB, d.H, d.W, d.Cout = B, H, W, Cout
+    d.a_ptr[0] = x.data_ptr(); d.a_C[0] = Cin; d.a_ld[0] = Cin
+    d.nseg = 1; d.seg_map[0] = 0; d.seg_taps[0] = 9; d.seg_kchunks[0] = Cin // 64
+    if skip:
+        d.a_ptr[1] = x1.data_ptr(); d.a_C[1] = C1; d.a_ld[1] = C1
+        d.nseg = 2; d.seg_map[1] = 1; d.seg_taps[1] = 1; d.seg_kchunks[1] = C1 // 64
+    d.w = wp.data_ptr(); d.ldw = wp.shape[1]; d.Ktot = wp.shape[1]; d.out = out.data_ptr(); d.bias = bias.data_ptr()
+    d.force_sub = 3; d.xf_K = K.data_ptr(); d.xf_silu = 1
+    _halo_run(d)
+    torch.backends.cudnn.allow_tf32 = False
+    a = F.silu(x.float() * K[:, 0].view(B, 1, 1, Cin) + K[:, 1].view(B, 1, 1, Cin)).to(torch.bfloat16).float()
+    ref = F.conv2d(a.permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1)
+    if skip:
+        ref = ref + F.conv2d(x1.float().permute(0, 3, 1, 2), ws.to(torch.bfloat16).float())
+    assert rel(out.float().permute(0, 3, 1, 2), ref) < 5e-3

@@ -7,15 +7,16 @@ import torch
 from ddpm_torch_b200 import _lib
 
 once = "--once" in sys.argv
-variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain", "plain_pair", "qstats_pair"]
+variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain_pair", "xf_pair", "xfnomath_pair", "xfnofence_pair"]
 B, H, W = 128, 32, 32
 L = _lib.lib(); st = _lib.stream_ptr()
-for (ci, co) in ((128, 128), (128, 384), (384, 128), (256, 256), (512, 256)):
+for (ci, co) in ((128, 128), (256, 256)):
     nbuf = 6
     xs = [torch.randn(B, H, W, ci, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     ys = [torch.empty(B, H, W, co, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
     w = (torch.randn(co, 9 * ci, device="cuda") * 0.03).to(torch.bfloat16); bias = torch.zeros(co, device="cuda")
     qs = torch.zeros(B, co // 4, 2, device="cuda", dtype=torch.float64)
+    Kx = torch.randn(B, 4, ci, device="cuda")
     for var in variants:
         ds = []
         for i in range(nbuf):
@@ -26,6 +27,8 @@ for (ci, co) in ((128, 128), (128, 384), (384, 128), (256, 256), (512, 256)):
             d.bias = bias.data_ptr()
             if var.startswith("qstats"):
                 d.gn.qstats = qs.data_ptr()
+            if var.startswith("xf"):
+                d.xf_K = Kx.data_ptr(); d.xf_silu = 1 | (4 if "nomath" in var else 0) | (8 if "nofence" in var else 0)
             if var.endswith("_sub2"):
                 d.force_sub = 2
             elif var.endswith("_pair"):
