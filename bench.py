@@ -589,8 +589,7 @@ def bench_hq(D, _lib, dev, rank, world, barrier, maxr, pk, train_bs=4, sample_bs
     model.eval()
     ddim = D.DDIM.from_ddpm(diff, eta=0.0, subsequence=D.get_selection_schedule("linear", 100, 1000))
     n_img = D.parallel.shard_size(sample_bs * world, rank, world)
-    ddim_w = D.DDIM.from_ddpm(diff, eta=0.0, subsequence=D.get_selection_schedule("linear", 4, 1000))
-    ddim_w.p_sample(model, shape=(n_img, 3, 256, 256), device=dev, seed=3 + rank)      # warm-up (plan)
+    ddim.p_sample(model, shape=(n_img, 3, 256, 256), device=dev, seed=3 + rank)        # warm-up (plan, step graph)
     barrier()
     e0.record()
     x = ddim.p_sample(model, shape=(n_img, 3, 256, 256), device=dev, seed=5 + rank)

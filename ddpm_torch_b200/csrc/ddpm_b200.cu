@@ -54,6 +54,13 @@ int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream) {
     return launch_halo(g, static_cast<cudaStream_t>(stream));
 }
 
+int ddpm_attn_fused_run(const void* qkv, void* out, int NB, int T, int C, void* stream) {
+    AttnLaunch g;
+    int rc = build_attn(qkv, out, NB, T, C, g);
+    if (rc) return rc;
+    return launch_attn(g, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ UNet engine
 int ddpm_unet_create(const ddpm_unet_cfg* cfg, ddpm_unet** out) {
     if (!cfg || !out) return fail(-30, "null argument");
@@ -166,10 +173,12 @@ int ddpm_train_backward(ddpm_unet* h, const float* gscale, void* stream) {
 
 int ddpm_sampler_setup(ddpm_unet* h, int S, const int64_t* t_model_host, const float* coef_host) {
     if (!h || S <= 0) return fail(-30, "bad sampler setup");
-    if (h->d_tmodel) { cudaFree(h->d_tmodel); h->d_tmodel = nullptr; }
-    if (h->d_coef) { cudaFree(h->d_coef); h->d_coef = nullptr; }
-    DDPM_CUDA_OK(cudaMalloc(&h->d_tmodel, (size_t)S * 8));
-    DDPM_CUDA_OK(cudaMalloc(&h->d_coef, (size_t)S * 6 * 4));
+    if (h->S != S) {           // same length: keep the allocations (a captured sampler graph holds their addresses)
+        if (h->d_tmodel) { cudaFree(h->d_tmodel); h->d_tmodel = nullptr; }
+        if (h->d_coef) { cudaFree(h->d_coef); h->d_coef = nullptr; }
+        DDPM_CUDA_OK(cudaMalloc(&h->d_tmodel, (size_t)S * 8));
+        DDPM_CUDA_OK(cudaMalloc(&h->d_coef, (size_t)S * 6 * 4));
+    }
     DDPM_CUDA_OK(cudaMemcpy(h->d_tmodel, t_model_host, (size_t)S * 8, cudaMemcpyHostToDevice));
     DDPM_CUDA_OK(cudaMemcpy(h->d_coef, coef_host, (size_t)S * 6 * 4, cudaMemcpyHostToDevice));
     h->S = S;

@@ -9,6 +9,7 @@
 #include "gemm_build.cuh"
 #include "conv_halo.cuh"
 #include "conv_halo2.cuh"
+#include "attn_fused.cuh"
 #include "kernels_simt.cuh"
 
 namespace ddpm {

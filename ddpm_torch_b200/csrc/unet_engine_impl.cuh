@@ -126,15 +126,29 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     T4 qkv = newT(Bn, h, w, 3 * C);
     { ConvSpec c; c.name = p + ".project_in"; c.in = one(xn); c.ksize = 1; c.wp = win.fwd; c.ldw = win.ld_f; c.bias = PP(p + ".project_in.bias");
       c.out = qkv; c.Co = 3 * C; c.Ho = h; c.Wo = w; conv_op(fwd_ops, c, &fwd_flops); }
-    float* S = at<float>(alloc((size_t)Bn * T * T * 4));
-    bf16* Pm = at<bf16>(alloc((size_t)Bn * T * T * 2));
     const bf16* q = bp(qkv);
     const long long ldq = 3 * C, sq = (long long)T * 3 * C;
-    bmm(fwd_ops, p + ".qk", 0, q, ldq, sq, q + C, ldq, sq, S, T, (long long)T * T, true, Bn, T, C, scale, &fwd_flops);
-    { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
-      push(fwd_ops, p + ".softmax", 0, [=](cudaStream_t st) { launch_k(k_softmax_rows, nblk, 256, 0, st, S, Pm, rows, T); return (int)cudaGetLastError(); }); }
     T4 O = newT(Bn, h, w, C);
-    bmm(fwd_ops, p + ".pv", 1, Pm, T, (long long)T * T, q + 2 * C, ldq, sq, bp(O), C, (long long)T * C, false, Bn, T, C, 1.f, &fwd_flops);
+    float* S = nullptr; bf16* Pm = nullptr;
+    static const bool no_fused_attn = getenv("DDPM_NO_FUSED_ATTN") != nullptr;
+    if (!train && !no_fused_attn && attn_fused_eligible(T, C)) {
+        // inference plans: Q.K^T -> softmax -> P.V in ONE kernel, S and O in TMEM, P in shared memory (attn_fused.cuh)
+        const double fl = 4.0 * Bn * (double)T * T * C;
+        fwd_flops += fl; ++n_tc_gemms;
+        if (dry) push(fwd_ops, p + ".attn[fused]", fl, [](cudaStream_t) { return 0; });
+        else {
+            AttnLaunch g; const int rc = build_attn(q, bp(O), Bn, T, C, g);
+            if (rc) { plan_error = rc; return O; }
+            push(fwd_ops, p + ".attn[fused]", fl, [g](cudaStream_t st) { return launch_attn(g, st); });
+        }
+    } else {
+        S = at<float>(alloc((size_t)Bn * T * T * 4));
+        Pm = at<bf16>(alloc((size_t)Bn * T * T * 2));
+        bmm(fwd_ops, p + ".qk", 0, q, ldq, sq, q + C, ldq, sq, S, T, (long long)T * T, true, Bn, T, C, scale, &fwd_flops);
+        { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
+          push(fwd_ops, p + ".softmax", 0, [=](cudaStream_t st) { launch_k(k_softmax_rows, nblk, 256, 0, st, S, Pm, rows, T); return (int)cudaGetLastError(); }); }
+        bmm(fwd_ops, p + ".pv", 1, Pm, T, (long long)T * T, q + 2 * C, ldq, sq, bp(O), C, (long long)T * C, false, Bn, T, C, 1.f, &fwd_flops);
+    }
     const Packed wout = pack_conv(p + ".project_out", C, C, 1, 0, false, true);
     T4 out = newT(Bn, h, w, C);
     { ConvSpec c; c.name = p + ".project_out"; c.in = one(O); c.ksize = 1; c.wp = wout.fwd; c.ldw = wout.ld_f; c.bias = PP(p + ".project_out.bias");

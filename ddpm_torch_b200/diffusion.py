@@ -407,8 +407,27 @@ def _native_sample_loop_on_device(diffusion, model, x, gen, rng, seed, use_graph
     coef = diffusion._coef_rows()
     tmod = diffusion._model_timesteps().contiguous()
     S = coef.shape[0]
-    z = torch.empty_like(x) if rng == "torch" else None
     pseed = 0 if rng == "torch" else ((seed if seed is not None else torch.initial_seed()) | 1) & 0xFFFFFFFFFFFFFFFF
+    # The captured step graph is CACHED on the model per (plan, batch shape, chain length, generator kind): generate.py calls
+    # p_sample once per batch, and re-capturing ~150 kernels per call costs more than a dozen DDIM steps.  A cached graph owns
+    # persistent x / z buffers and (for seeded runs) a persistent registered generator that takes over the caller's generator state.
+    ent = None
+    if use_graph and rng == "torch" and S > 1:
+        key = (x.shape, split, S, gen is not None, model._plan_epoch, tuple(model._aux[i].get("epoch", 0) for i in range(1, split)))
+        ent = model._sampler_cache.get(key)
+        if ent is None:
+            if len(model._sampler_cache) >= 4:
+                model._sampler_cache.clear()
+            ent = model._sampler_cache[key] = {"x": torch.empty_like(x), "z": torch.empty_like(x), "graph": None,
+                                               "gen": torch.Generator(x.device) if gen is not None else None}
+        xb, z = ent["x"], ent["z"]
+        xb.copy_(x)
+        x = xb
+        if gen is not None:
+            ent["gen"].set_state(gen.get_state())      # continue the caller's stream (x_T may already have been drawn from it)
+            gen = ent["gen"]
+    else:
+        z = torch.empty_like(x) if rng == "torch" else None
     stream = torch.cuda.current_stream()
     for h in hs:
         _lib.check(L.ddpm_sampler_setup(h, S, tmod.data_ptr(), coef.data_ptr()), "sampler_setup")
@@ -434,29 +453,36 @@ def _native_sample_loop_on_device(diffusion, model, x, gen, rng, seed, use_graph
         if z is not None:
             z.normal_(generator=gen)            # diffusion.py:155 - the reference's stream, drawn on the device
 
-    graph = None
-    if use_graph:
+    def capture():
+        graph = torch.cuda.CUDAGraph()
+        if gen is not None and z is not None:
+            graph.register_generator_state(gen)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                draw()
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        return graph
+
+    if ent is not None:
         # ONE graph launch per timestep: the captured step holds the noise draw (the generator is registered with the graph, so
         # every replay advances its Philox offset exactly like an eager normal_ call), the step-table fetch, the UNet forward and
-        # the alpha/beta update fused into the final conv's gather.  Step 0 runs eagerly (allocator warm-up), then one step is
-        # captured and replayed for every remaining timestep.
-        draw()
-        step()
-        done = 1
-        if done < S:
-            graph = torch.cuda.CUDAGraph()
-            if gen is not None and z is not None:
-                graph.register_generator_state(gen)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(graph, stream=side):
-                    draw()
-                    step()
-            torch.cuda.current_stream().wait_stream(side)
-            # capture does not execute: the captured step is replayed below for every remaining timestep
-            for _ in range(done, S):
-                graph.replay()
+        # the alpha/beta update fused into the final conv's gather.
+        done = 0
+        if ent["graph"] is None:
+            draw(); step()                       # first use: one eager step (allocator warm-up), then capture (does not execute)
+            done = 1
+            ent["graph"] = capture()
+        for _ in range(done, S):
+            ent["graph"].replay()
+        return x.clone()
+    if use_graph and S > 1:                     # in-kernel Philox noise: the seed is a launch argument, so the graph is per call
+        draw(); step()
+        graph = capture()
+        for _ in range(1, S):
+            graph.replay()
     else:
         for _ in range(S):
             draw()

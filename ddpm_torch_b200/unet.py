@@ -89,6 +89,8 @@ class UNet(nn.Module):
         self._packed_version = None
         self._packed_epoch = 0
         self._drop_calls = 0
+        self._plan_epoch = 0
+        self._sampler_cache = {}
         self._acc = None                    # gradient-accumulation buffer (only exists when backward runs twice before a step)
         self._acc_pending = False
         self._bwd_since_zero = 0
@@ -122,6 +124,7 @@ class UNet(nn.Module):
         self._flat = flat
         self._plan_key = None
         self._packed_version = None
+        self._sampler_cache = {}
 
     def _views_ok(self):
         base = self._flat.data_ptr()
@@ -195,6 +198,7 @@ class UNet(nn.Module):
                                             self._grads.data_ptr() if training else None,
                                             self._ws.data_ptr(), self._ws.numel()), "unet_plan")
             self._plan_key = key
+            self._plan_epoch += 1                 # captured sampler graphs of older plans are stale (see diffusion._native_sample_loop)
             self._packed_version = None
         self.repack_if_needed(force=training or force_repack)
         return self._h
@@ -225,6 +229,7 @@ class UNet(nn.Module):
             with torch.cuda.device(self._flat.device):
                 _lib.check(L.ddpm_unet_plan(a["h"], B, H, W, 0, self._flat.data_ptr(), None, a["ws"].data_ptr(), a["ws"].numel()), "unet_plan")
             a["key"], a["ver"] = key, None
+            a["epoch"] = a.get("epoch", 0) + 1
         if force or a["ver"] != self._weights_version():
             with torch.cuda.device(self._flat.device):
                 _lib.check(L.ddpm_unet_repack(a["h"], _lib.stream_ptr(self._flat.device)), "unet_repack")

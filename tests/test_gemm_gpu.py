@@ -442,3 +442,22 @@ def test_conv_halo_pair_fused_groupnorm_input(B, H, W, Cin, Cout, skip):
     if skip:
         ref = ref + F.conv2d(x1.float().permute(0, 3, 1, 2), ws.to(torch.bfloat16).float())
     assert rel(out.float().permute(0, 3, 1, 2), ref) < 5e-3
+
+
+@pytest.mark.parametrize("NB", [1, 3, 64])
+def test_attention_fused_kernel(NB):
+    """softmax(Q K^T / sqrt(C)) V in one kernel (csrc/attn_fused.cuh) vs fp32 torch on the same bf16 q, k, v (unet.py:43-51)."""
+    from ddpm_torch_b200 import _lib
+    T, Cc = 256, 256
+    qkv = bf(NB, T, 3 * Cc, seed=NB, scale=1.0)
+    out = torch.full((NB, T, Cc), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ddpm_attn_fused_run(qkv.data_ptr(), out.data_ptr(), NB, T, Cc, _lib.stream_ptr()), "attn_fused_run")
+    torch.cuda.synchronize()
+    assert _lib.lib().ddpm_device_error_flag() == 0
+    q, k, v = qkv.float().chunk(3, dim=-1)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = torch.softmax(torch.einsum("btc,bsc->bts", q, k) / Cc ** 0.5, dim=-1)
+    ref = torch.einsum("bts,bsc->btc", w, v)
+    r = rel(out.float(), ref)
+    print(f"\n[fused attention NB={NB}] rel-L2 {r:.3e}")
+    assert r < 6e-3            # bf16 P (one rounding) + bf16 output

@@ -10,7 +10,7 @@ once = "--once" in sys.argv
 variants = [a for a in sys.argv[1:] if not a.startswith("--")] or ["plain_pair", "xf_pair", "xfnomath_pair", "xfnofence_pair"]
 B, H, W = 128, 32, 32
 L = _lib.lib(); st = _lib.stream_ptr()
-for (ci, co) in ((128, 128), (256, 256)):
+for (ci, co) in ((128, 128), (128, 384), (384, 128), (256, 256), (512, 256)):
     nbuf = 6
     xs = [torch.randn(B, H, W, ci, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     ys = [torch.empty(B, H, W, co, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
