@@ -81,7 +81,7 @@ def lib():
         vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_uint64
         sig = {
             "ddpm_conv_halo_run": ([C.POINTER(HaloDesc), vp], i32),
-            "ddpm_attn_fused_run": ([vp, vp, i32, i32, i32, vp], i32),
+            "ddpm_attn_fused_run": ([vp, vp, vp, i32, i32, i32, vp], i32),
             "ddpm_unet_create": ([C.POINTER(UnetCfg), C.POINTER(vp)], i32),
             "ddpm_unet_destroy": ([vp], None),
             "ddpm_unet_num_params": ([vp], i32),

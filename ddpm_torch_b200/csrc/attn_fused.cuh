@@ -10,13 +10,13 @@
 //              as bf16 into the swizzled P tile + row sum (pass 2), then O * (1 / sum) -> bf16 -> global.
 // The P tile uses exactly the layout TMA would produce for a K-major SWIZZLE_128B operand (rows of 128 B = 64 keys, 16-byte chunk j
 // of row r stored at chunk j ^ (r & 7), 16 KB per 64-key slab), so the UMMA descriptors are the ones of the GEMM engine.
-// Inference plans only: the backward pass of the training plan consumes the materialised P.
+// Training plans additionally get the normalised P written to HBM (p.pm) for the backward pass, from the same shared-memory tile.
 #pragma once
 #include "gemm_host.cuh"
 
 namespace ddpm {
 
-struct AttnParams { int NB; __nv_bfloat16* out; float scale_log2e; };
+struct AttnParams { int NB; __nv_bfloat16* out; float scale_log2e; __nv_bfloat16* pm; };   // pm: optional [NB][T][T] normalised probabilities (training)
 
 constexpr int ATTN_T = 256, ATTN_D = 256;
 constexpr int ATTN_STAGES = 3;
@@ -151,9 +151,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
+            const float inv = 1.f / sum;
+            if (p.pm) {
+                // training plans: the backward pass reads the normalised probabilities.  Written from the shared-memory tile
+                // while the tensor core runs P.V (these warps would otherwise idle on o_full).
+                __nv_bfloat16* prow = p.pm + ((long long)img * ATTN_T + half * 128 + r) * ATTN_T;
+#pragma unroll 1
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint8_t* rowp = smP + (ch >> 1) * 16384 + r * 128;
+                    uint32_t u[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        ld_shared_v4(rowp + ((((ch & 1) * 4 + i) ^ (r & 7)) << 4), u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+                        u[e] = pack_bf16x2(f.x * inv, f.y * inv);
+                    }
+                    st_global_256(prow + ch * 32, u); st_global_256(prow + ch * 32 + 16, u + 8);
+                }
+            }
             if (mbar_wait(o_full, 0, 17)) {
                 tc_fence_after();
-                const float inv = 1.f / sum;
                 __nv_bfloat16* orow = p.out + ((long long)img * ATTN_T + half * 128 + r) * ATTN_D;
 #pragma unroll 1
                 for (int ch = 0; ch < 8; ++ch) {
@@ -182,14 +201,14 @@ struct AttnLaunch { CUtensorMap q, k, v; AttnParams p; };
 inline bool attn_fused_eligible(int T, int C) { return T == ATTN_T && C == ATTN_D; }
 
 // qkv: bf16 [NB][T][3C] (unet.py:57 chunk order q, k, v); out: bf16 [NB][T][C]
-inline int build_attn(const void* qkv, void* out, int NB, int T, int C, AttnLaunch& g) {
+inline int build_attn(const void* qkv, void* out, int NB, int T, int C, AttnLaunch& g, void* pm = nullptr) {
     if (!attn_fused_eligible(T, C)) return fail(-13, "fused attention: T=%d C=%d unsupported (needs T=256, C=256)", T, C);
     memset(&g, 0, sizeof g);
     int rc;
     if ((rc = make_tmap_4d(&g.q, qkv, 3 * C, T, 1, NB, 3 * C, 64, 128, 1, 1))) return rc;
     if ((rc = make_tmap_4d(&g.k, qkv, 3 * C, T, 1, NB, 3 * C, 64, 256, 1, 1))) return rc;
     if ((rc = make_tmap_4d(&g.v, qkv, 3 * C, T, 1, NB, 3 * C, 64, 64, 1, 1))) return rc;
-    g.p.NB = NB; g.p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    g.p.NB = NB; g.p.out = reinterpret_cast<__nv_bfloat16*>(out); g.p.pm = reinterpret_cast<__nv_bfloat16*>(pm);
     g.p.scale_log2e = 1.4426950408889634f / sqrtf((float)C);
     return 0;
 }

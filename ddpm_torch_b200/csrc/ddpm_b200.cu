@@ -54,9 +54,9 @@ int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream) {
     return launch_halo(g, static_cast<cudaStream_t>(stream));
 }
 
-int ddpm_attn_fused_run(const void* qkv, void* out, int NB, int T, int C, void* stream) {
+int ddpm_attn_fused_run(const void* qkv, void* out, void* probs, int NB, int T, int C, void* stream) {
     AttnLaunch g;
-    int rc = build_attn(qkv, out, NB, T, C, g);
+    int rc = build_attn(qkv, out, NB, T, C, g, probs);
     if (rc) return rc;
     return launch_attn(g, static_cast<cudaStream_t>(stream));
 }

@@ -603,6 +603,12 @@ __global__ void __launch_bounds__(256, 2) k_gn_bwd_apply(const GnBwd a, float* c
     }
 }
 
+// (Two single-launch variants of this backward were built, verified against the oracle and measured in round 2 - a cluster per
+// image with the dy / x slabs staged in shared memory by bulk async copies, and a CTA per (image, group slice) with the pairs
+// resident in registers - and removed: both cut HBM traffic to the 3-4 pass minimum but serialise load -> reduce -> apply
+// inside a CTA that owns most of an SM, and the training step got slower (9.84-10.1 ms vs 9.20 ms);
+// profiles/r02_gn_backward_fused_experiment.txt.)
+
 // ============================================================================ generic conv (CUDA cores)
 // out[b,oy,ox,co] = sum_{tap,ci} in[b, iy(oy,ky), ix(ox,kx), ci] * Wp[co][tap*Cin + ci]  (+bias +rowvec[b] +residual)
 // map 0: iy = oy*stride + ky - pad ; map 1 (dgrad of the stride-2 conv): iy = (oy-ky)/2 when even ; map 2: nearest-2x
@@ -1076,6 +1082,132 @@ __global__ void __launch_bounds__(256) k_softmax_bwd(const bf16* __restrict__ P,
     dot = warp_sum(dot);
     for (int j = lane; j < T; j += 32)
         dS[row * T + j] = __float2bfloat16_rn(__bfloat162float(P[row * T + j]) * (dP[row * T + j] - dot) * scale);
+}
+
+// ============================================================================ whole attention for T = 16 tokens (4x4 level)
+// unet.py:37-60 at the 4x4 resolution: softmax(Q K^T / sqrt(C)) V is 2 x 16x16xC products per image - far below one MMA tile,
+// so the three launches of the generic route (SIMT GEMM, softmax, SIMT GEMM; five more in backward) are pure latency.  One CTA
+// per image keeps the image's [16][3C] q|k|v rows in shared memory and does scores, softmax and P.V (backward: dP, dS, dQ, dK,
+// dV) in one launch.  Rows are padded by 8 elements so the 16 K rows of a score column land in different banks.
+__device__ __forceinline__ float dot8_bf16(const uint4 a, const uint4 b) {
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pb[i]); acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc)); }
+    return acc;
+}
+constexpr int ATTN16_T = 16;
+inline size_t attn16_smem(int C, bool bwd) {
+    return (size_t)ATTN16_T * (3 * C + 8) * 2 + (bwd ? (size_t)ATTN16_T * (C + 8) * 2 : 0) + 2 * ATTN16_T * ATTN16_T * 4;
+}
+inline bool attn16_eligible(int T, int C) { return T == ATTN16_T && (C == 128 || C == 256 || C == 512); }
+
+__global__ void __launch_bounds__(256) k_attn16_fwd(const bf16* __restrict__ qkv, bf16* __restrict__ O, bf16* __restrict__ Pm, int C, float scale) {
+    pdl_entry();
+    constexpr int T = ATTN16_T;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int ld = 3 * C + 8;
+    bf16* s = reinterpret_cast<bf16*>(sm_raw);
+    float* P = reinterpret_cast<float*>(sm_raw + (size_t)T * ld * 2);
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const bf16* src = qkv + (long long)n * T * 3 * C;
+    const int oct = 3 * C / 8;
+    for (int i = tid; i < T * oct; i += 256) { const int r = i / oct, o = i % oct; *reinterpret_cast<uint4*>(s + r * ld + o * 8) = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * 3 * C) + o); }
+    __syncthreads();
+    {   // thread = one (query i, key j) pair; the 16 keys of a query sit in one half-warp
+        const int i = tid / T, j = tid % T;
+        const bf16* qi = s + i * ld; const bf16* kj = s + j * ld + C;
+        float acc = 0.f;
+        for (int c = 0; c < C; c += 8) acc += dot8_bf16(*reinterpret_cast<const uint4*>(qi + c), *reinterpret_cast<const uint4*>(kj + c));
+        acc *= scale;
+        float mx = acc;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = __expf(acc - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const bf16 pb = __float2bfloat16_rn(e / sum);      // the probabilities the backward pass reads are the ones applied here
+        P[tid] = __bfloat162float(pb);
+        if (Pm) Pm[(long long)n * T * T + tid] = pb;
+    }
+    __syncthreads();
+    const int npair = C / 2, groups = 256 / npair, rows = T / groups;
+    const int cp = tid % npair, r0 = (tid / npair) * rows;
+    float2 v[T];
+#pragma unroll
+    for (int j = 0; j < T; ++j) v[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(s + j * ld + 2 * C + 2 * cp));
+    for (int i = r0; i < r0 + rows; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < T; ++j) { const float p = P[i * T + j]; a0 = fmaf(p, v[j].x, a0); a1 = fmaf(p, v[j].y, a1); }
+        *reinterpret_cast<__nv_bfloat162*>(O + ((long long)n * T + i) * C + 2 * cp) = __floats2bfloat162_rn(a0, a1);
+    }
+}
+
+// dqkv[n][t][0:C | C:2C | 2C:3C] = dQ | dK | dV  from dO, the saved probabilities and q|k|v
+__global__ void __launch_bounds__(256) k_attn16_bwd(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, const bf16* __restrict__ Pm,
+                                                   bf16* __restrict__ dqkv, int C, float scale) {
+    pdl_entry();
+    constexpr int T = ATTN16_T;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int ld = 3 * C + 8, ldo = C + 8;
+    bf16* s = reinterpret_cast<bf16*>(sm_raw);
+    bf16* sdo = s + (size_t)T * ld;
+    float* P = reinterpret_cast<float*>(sm_raw + (size_t)T * ld * 2 + (size_t)T * ldo * 2);
+    float* dS = P + T * T;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const bf16* src = qkv + (long long)n * T * 3 * C;
+    const bf16* gsrc = dO + (long long)n * T * C;
+    const int oct = 3 * C / 8, octo = C / 8;
+    for (int i = tid; i < T * oct; i += 256) { const int r = i / oct, o = i % oct; *reinterpret_cast<uint4*>(s + r * ld + o * 8) = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * 3 * C) + o); }
+    for (int i = tid; i < T * octo; i += 256) { const int r = i / octo, o = i % octo; *reinterpret_cast<uint4*>(sdo + r * ldo + o * 8) = __ldg(reinterpret_cast<const uint4*>(gsrc + (long long)r * C) + o); }
+    {
+        const int i = tid / T, j = tid % T;
+        const float p = __bfloat162float(Pm[(long long)n * T * T + tid]);
+        P[tid] = p;
+        __syncthreads();
+        const bf16* gi = sdo + i * ldo; const bf16* vj = s + j * ld + 2 * C;
+        float dp = 0.f;
+        for (int c = 0; c < C; c += 8) dp += dot8_bf16(*reinterpret_cast<const uint4*>(gi + c), *reinterpret_cast<const uint4*>(vj + c));
+        float dot = p * dp;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        dS[tid] = __bfloat162float(__float2bfloat16_rn(p * (dp - dot) * scale));
+    }
+    __syncthreads();
+    const int npair = C / 2, groups = 256 / npair, rows = T / groups;
+    const int cp = tid % npair, r0 = (tid / npair) * rows;
+    bf16* dst = dqkv + (long long)n * T * 3 * C + 2 * cp;
+    float2 x[T];
+    // dQ[i] = sum_j dS[i][j] k[j]
+#pragma unroll
+    for (int j = 0; j < T; ++j) x[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(s + j * ld + C + 2 * cp));
+    for (int i = r0; i < r0 + rows; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < T; ++j) { const float w = dS[i * T + j]; a0 = fmaf(w, x[j].x, a0); a1 = fmaf(w, x[j].y, a1); }
+        *reinterpret_cast<__nv_bfloat162*>(dst + (long long)i * 3 * C) = __floats2bfloat162_rn(a0, a1);
+    }
+    // dK[j] = sum_i dS[i][j] q[i]
+#pragma unroll
+    for (int i = 0; i < T; ++i) x[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(s + i * ld + 2 * cp));
+    for (int j = r0; j < r0 + rows; ++j) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { const float w = dS[i * T + j]; a0 = fmaf(w, x[i].x, a0); a1 = fmaf(w, x[i].y, a1); }
+        *reinterpret_cast<__nv_bfloat162*>(dst + (long long)j * 3 * C + C) = __floats2bfloat162_rn(a0, a1);
+    }
+    // dV[j] = sum_i P[i][j] dO[i]
+#pragma unroll
+    for (int i = 0; i < T; ++i) x[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sdo + i * ldo + 2 * cp));
+    for (int j = r0; j < r0 + rows; ++j) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { const float w = P[i * T + j]; a0 = fmaf(w, x[i].x, a0); a1 = fmaf(w, x[i].y, a1); }
+        *reinterpret_cast<__nv_bfloat162*>(dst + (long long)j * 3 * C + 2 * C) = __floats2bfloat162_rn(a0, a1);
+    }
 }
 
 // ============================================================================ nearest 2x upsample (unet.py:199) and its adjoint

@@ -281,7 +281,8 @@ struct UnetEngine {
             if (!no_n128 && bn == 256 && tiles <= 74 && tiles * 2 <= 148) { bn = 128; tiles *= 2; d.block_n = 128; }
             const int slabs = (int)(K / 64);
             int splits = 1;
-            if (tiles <= 74 && slabs >= 16) { splits = 148 / tiles; if (splits > slabs / 8) splits = slabs / 8; if (splits > 16) splits = 16; if (splits < 1) splits = 1; }
+            // (a finalize launch + fp32 atomics cost more than a half-empty single wave: split only when under ~1/3 of the SMs have a tile)
+            if (tiles <= 48 && slabs >= 16) { splits = 148 / tiles; if (splits > slabs / 8) splits = slabs / 8; if (splits > 16) splits = 16; if (splits < 1) splits = 1; }
             if (splits > 1) {
                 float* scratch = at<float>(alloc_once_zero((size_t)Pout * c.Co * 4));
                 ddpm_gemm_desc ds = d;

@@ -131,16 +131,29 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     T4 O = newT(Bn, h, w, C);
     float* S = nullptr; bf16* Pm = nullptr;
     static const bool no_fused_attn = getenv("DDPM_NO_FUSED_ATTN") != nullptr;
-    if (!train && !no_fused_attn && attn_fused_eligible(T, C)) {
-        // inference plans: Q.K^T -> softmax -> P.V in ONE kernel, S and O in TMEM, P in shared memory (attn_fused.cuh)
+    static const bool no_attn16 = getenv("DDPM_NO_ATTN16") != nullptr;
+    const bool small16 = !no_attn16 && attn16_eligible(T, C);
+    static const bool no_fused_attn_train = getenv("DDPM_NO_FUSED_ATTN_TRAIN") != nullptr;
+    if (!(train && no_fused_attn_train) && !no_fused_attn && attn_fused_eligible(T, C)) {
+        // Q.K^T -> softmax -> P.V in ONE kernel, S and O in TMEM, P in shared memory (attn_fused.cuh); training plans also get
+        // the normalised P in HBM for the backward pass
+        if (train) Pm = at<bf16>(alloc((size_t)Bn * T * T * 2));
         const double fl = 4.0 * Bn * (double)T * T * C;
         fwd_flops += fl; ++n_tc_gemms;
         if (dry) push(fwd_ops, p + ".attn[fused]", fl, [](cudaStream_t) { return 0; });
         else {
-            AttnLaunch g; const int rc = build_attn(q, bp(O), Bn, T, C, g);
+            AttnLaunch g; const int rc = build_attn(q, bp(O), Bn, T, C, g, Pm);
             if (rc) { plan_error = rc; return O; }
             push(fwd_ops, p + ".attn[fused]", fl, [g](cudaStream_t st) { return launch_attn(g, st); });
         }
+    } else if (small16) {
+        // 4x4 level: one CTA per image does scores, softmax and P.V (k_attn16_fwd); P is kept only when a backward follows
+        if (train) Pm = at<bf16>(alloc((size_t)Bn * T * T * 2));
+        const double fl = 4.0 * Bn * (double)T * T * C;
+        fwd_flops += fl; ++n_generic;
+        bf16* Op = bp(O); bf16* Pk = Pm; const size_t shm = attn16_smem(C, false);
+        if (!dry) cudaFuncSetAttribute(k_attn16_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn16_smem(512, false));
+        push(fwd_ops, p + ".attn[t16]", fl, [=](cudaStream_t st) { launch_k(k_attn16_fwd, Bn, 256, shm, st, q, Op, Pk, C, scale); return (int)cudaGetLastError(); });
     } else {
         S = at<float>(alloc((size_t)Bn * T * T * 4));
         Pm = at<bf16>(alloc((size_t)Bn * T * T * 2));
@@ -161,16 +174,24 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
         { ConvSpec c; c.name = p + ".project_out.dgrad"; c.in = one(dY); c.ksize = 1; c.wp = wout.dgr; c.ldw = wout.ld_d; c.out = dO; c.Co = C; c.Ho = h; c.Wo = w;
           conv_op(bwd_ops, c, &bwd_flops); }
         wgrad_op(p + ".project_out.wgrad", dY, one(O), 1, 1, MAP_NORMAL, GP(p + ".project_out.weight"), C);
-        float* dP = at<float>(alloc((size_t)Bn * T * T * 4));
-        bf16* dS = at<bf16>(alloc((size_t)Bn * T * T * 2));
         T4 dqkv = newT(Bn, h, w, 3 * C);
         const bf16* dOp = bp(dO); bf16* dq = bp(dqkv);
+        if (small16) {
+            const double fl = 8.0 * Bn * (double)T * T * C;
+            bwd_flops += fl; ++n_generic;
+            const size_t shm = attn16_smem(C, true); const bf16* Pk = Pm;
+            if (!dry) cudaFuncSetAttribute(k_attn16_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn16_smem(512, true));
+            push(bwd_ops, p + ".attn_bwd[t16]", fl, [=](cudaStream_t st) { launch_k(k_attn16_bwd, Bn, 256, shm, st, q, dOp, Pk, dq, C, scale); return (int)cudaGetLastError(); });
+        } else {
+        float* dP = at<float>(alloc((size_t)Bn * T * T * 4));
+        bf16* dS = at<bf16>(alloc((size_t)Bn * T * T * 2));
         bmm(bwd_ops, p + ".dP", 0, dOp, C, (long long)T * C, q + 2 * C, ldq, sq, dP, T, (long long)T * T, true, Bn, T, C, 1.f, &bwd_flops);
         bmm(bwd_ops, p + ".dV", 2, Pm, T, (long long)T * T, dOp, C, (long long)T * C, dq + 2 * C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         { const long long rows = (long long)Bn * T; const int nblk = (int)((rows + 7) / 8);
           push(bwd_ops, p + ".softmax_bwd", 0, [=](cudaStream_t st) { launch_k(k_softmax_bwd, nblk, 256, 0, st, Pm, dP, dS, rows, T, scale); return (int)cudaGetLastError(); }); }
         bmm(bwd_ops, p + ".dQ", 1, dS, T, (long long)T * T, q + C, ldq, sq, dq, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         bmm(bwd_ops, p + ".dK", 2, dS, T, (long long)T * T, q, ldq, sq, dq + C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
+        }
         colsum_op(p + ".project_in.bias", dqkv, nullptr, 0, GP(p + ".project_in.bias"), nullptr, 3 * C);
         T4 dxn = newT(Bn, h, w, C);
         { ConvSpec c; c.name = p + ".project_in.dgrad"; c.in = one(dqkv); c.ksize = 1; c.wp = win.dgr; c.ldw = win.ld_d; c.out = dxn; c.Co = C; c.Ho = h; c.Wo = w;

@@ -93,8 +93,10 @@ int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream);
 
 /* Low-level operator: the attention core of AttentionBlock.forward (unet.py:43-51) as ONE kernel (csrc/attn_fused.cuh):
  * out[b] = softmax(Q K^T / sqrt(C)) V with q, k, v = the three C-channel thirds of qkv bf16 [NB][T][3C] (chunk order of unet.py:57),
- * out bf16 [NB][T][C].  S and O stay in tensor memory, P in shared memory.  Supported: T = 256 tokens (the 16x16 level), C = 256. */
-int ddpm_attn_fused_run(const void* qkv, void* out, int NB, int T, int C, void* stream);
+ * out bf16 [NB][T][C].  S and O stay in tensor memory, P in shared memory.  Supported: T = 256 tokens (the 16x16 level), C = 256.
+ * probs (optional, NULL = off): bf16 [NB][T][T], receives the softmax probabilities that the backward pass of a training plan
+ * consumes (written from the shared-memory tile while P.V runs). */
+int ddpm_attn_fused_run(const void* qkv, void* out, void* probs, int NB, int T, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * UNet engine.  replaces: UNet.__init__/forward (ddpm_torch/models/unet.py:96-233), its autograd backward,

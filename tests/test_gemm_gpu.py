@@ -451,7 +451,10 @@ def test_attention_fused_kernel(NB):
     T, Cc = 256, 256
     qkv = bf(NB, T, 3 * Cc, seed=NB, scale=1.0)
     out = torch.full((NB, T, Cc), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().ddpm_attn_fused_run(qkv.data_ptr(), out.data_ptr(), NB, T, Cc, _lib.stream_ptr()), "attn_fused_run")
+    probs = torch.full((NB, T, T), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ddpm_attn_fused_run(qkv.data_ptr(), out.data_ptr(), None, NB, T, Cc, _lib.stream_ptr()), "attn_fused_run")
+    out2 = torch.full_like(out, float("nan"))
+    _lib.check(_lib.lib().ddpm_attn_fused_run(qkv.data_ptr(), out2.data_ptr(), probs.data_ptr(), NB, T, Cc, _lib.stream_ptr()), "attn_fused_run")
     torch.cuda.synchronize()
     assert _lib.lib().ddpm_device_error_flag() == 0
     q, k, v = qkv.float().chunk(3, dim=-1)
@@ -459,5 +462,8 @@ def test_attention_fused_kernel(NB):
     w = torch.softmax(torch.einsum("btc,bsc->bts", q, k) / Cc ** 0.5, dim=-1)
     ref = torch.einsum("bts,bsc->btc", w, v)
     r = rel(out.float(), ref)
-    print(f"\n[fused attention NB={NB}] rel-L2 {r:.3e}")
+    rp = rel(probs.float(), w)
+    print(f"\n[fused attention NB={NB}] rel-L2 {r:.3e}  probs {rp:.3e}")
     assert r < 6e-3            # bf16 P (one rounding) + bf16 output
+    assert torch.equal(out, out2)          # writing the probabilities does not change the product
+    assert rp < 8e-3           # bf16 probabilities (two roundings), the tensor the training backward reads
