@@ -82,6 +82,7 @@ void ddpm_unet_destroy(ddpm_unet* h) {
     if (h->e.side_stream) { cudaStreamDestroy(h->e.side_stream); cudaEventDestroy(h->e.ev_fork); cudaEventDestroy(h->e.ev_join); }
     for (auto& c : h->e.chunks) if (c.ev) cudaEventDestroy(c.ev);
     if (h->e.hp_stream) { cudaStreamDestroy(h->e.hp_stream); cudaEventDestroy(h->e.ev_hp_fork); cudaEventDestroy(h->e.ev_hp_join); }
+    if (h->e.ev_pack_all) { cudaEventDestroy(h->e.ev_pack_fork); cudaEventDestroy(h->e.ev_pack_fc); cudaEventDestroy(h->e.ev_pack_all); }
     delete h;
 }
 int ddpm_unet_num_params(const ddpm_unet* h) { return (int)h->e.params.size(); }
@@ -121,7 +122,7 @@ int ddpm_unet_plan(ddpm_unet* h, int B, int H, int W, int training, float* param
 }
 #define NEED_PLAN(h) do { if (!(h) || !(h)->e.planned) return fail(-33, "ddpm_unet_plan has not been called"); } while (0)
 
-int ddpm_unet_repack(ddpm_unet* h, void* stream) { NEED_PLAN(h); return h->e.run_list(h->e.pack_ops, static_cast<cudaStream_t>(stream)); }
+int ddpm_unet_repack(ddpm_unet* h, void* stream) { NEED_PLAN(h); return h->e.repack(static_cast<cudaStream_t>(stream)); }
 
 int ddpm_unet_forward(ddpm_unet* h, const float* x, const int64_t* t, float* eps, uint64_t dropout_seed, void* stream) {
     NEED_PLAN(h);

@@ -1363,12 +1363,16 @@ __global__ void k_pack_tapco_t(const float* __restrict__ w, bf16* __restrict__ o
 // 3x3 im2col of a narrow NCHW fp32 image (CI <= 7 channels) into NHWC bf16 rows of 64: dst[p][t*CI + ci] = src[ci][p + sign*o_t],
 // o_t = (t/3 - 1, t%3 - 1), zero outside the image and for columns >= 9*CI.  sign = +1: the conv's input patches (weight
 // gradient of in_conv); sign = -1: the patches the transposed conv sees (data and weight gradients of out_conv over d_eps).
+// With qp.noise set the source is x_t = q_sample(x0, t, noise) formed on the fly (same arithmetic as k_in_conv); the centre tap
+// also stores x_t to qp.xt_out.
 template <int CI>
-__global__ void __launch_bounds__(256) k_im2col3(const float* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int sign) {
+__global__ void __launch_bounds__(256) k_im2col3(const float* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int sign, const QsamplePro qp) {
     pdl_entry();
     const long long P = (long long)B * H * W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W), y = (int)((i / W) % H); const long long b = i / ((long long)W * H);
+        float qa = 1.f, qs_ = 0.f;
+        if (qp.noise) { const long long tb = qp.t[b]; qa = __ldg(qp.tab_a + tb); qs_ = __ldg(qp.tab_s + tb); }
         __align__(16) bf16 row[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) row[j] = __float2bfloat16_rn(0.f);
@@ -1377,12 +1381,28 @@ __global__ void __launch_bounds__(256) k_im2col3(const float* __restrict__ src, 
             const int yy = y + sign * (t / 3 - 1), xx = x + sign * (t % 3 - 1);
             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
 #pragma unroll
-            for (int ci = 0; ci < CI; ++ci) row[t * CI + ci] = __float2bfloat16_rn(__ldg(src + ((b * CI + ci) * H + yy) * W + xx));
+            for (int ci = 0; ci < CI; ++ci) {
+                const long long j = ((b * CI + ci) * H + yy) * W + xx;
+                float v = __ldg(src + j);
+                if (qp.noise) {
+                    v = __fadd_rn(__fmul_rn(qa, v), __fmul_rn(qs_, __ldg(qp.noise + j)));
+                    if (t == 4) qp.xt_out[j] = v;
+                }
+                row[t * CI + ci] = __float2bfloat16_rn(v);
+            }
         }
         uint4* o = reinterpret_cast<uint4*>(dst + i * 64);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = reinterpret_cast<const uint4*>(row)[j];
     }
+}
+// in_conv weights OIHW fp32 [Co][CI][3][3] -> bf16 [Co][64], column t*CI + ci (the patch order of k_im2col3), zero padded
+__global__ void k_pack_in(const float* __restrict__ w, bf16* __restrict__ wp, int Co, int CI) {
+    pdl_entry();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Co * 64) return;
+    const int co = i >> 6, k = i & 63, t = k / CI, ci = k % CI;
+    wp[i] = __float2bfloat16_rn(k < 9 * CI ? w[(co * CI + ci) * 9 + t] : 0.f);
 }
 // tap-major GEMM results back to OIHW fp32 gradients:
 //   mode 0 (out_conv):  gw[(co*C + c)*9 + t]  = S[(t*CO + co)*C + c]      S = [64][C]

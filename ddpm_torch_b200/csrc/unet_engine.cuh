@@ -21,6 +21,7 @@ struct T4 { long long off = -1; int B = 0, H = 0, W = 0, C = 0;
 struct Src { T4 t0, t1; bool two = false; int C() const { return t0.C + (two ? t1.C : 0); } };
 enum { OP_TEMB = 1 };
 struct Op { std::string name; double flops; std::function<int(cudaStream_t)> run; int launches = 1; bool side = false; int tag = 0;
+            int wait_pack = 0;   // forward list: 1 = needs the packed timestep-MLP weights, 2 = first consumer of the packed conv weights
             int chunk = -1;   // >= 0: gradient-chunk boundary of the backward list (see UnetEngine::chunks)
 };
 // A contiguous range [lo, hi) of the flat gradient buffer that is FINAL once `ev` has fired (recorded by the backward pass on the
@@ -44,6 +45,7 @@ struct UnetEngine {
     // plan state
     int B = 0, H = 0, W = 0; bool train = false; bool dry = true; size_t cursor = 0; bool planned = false;
     std::vector<Op> pack_ops, fwd_ops, bwd_ops;
+    size_t first_packed_op = 0;
     std::vector<std::function<void()>> tape;
     std::vector<std::string> tape_tag; std::string cur_tag = "late";       // gradient-chunk group of every tape entry
     void tape_push(std::function<void()> f) { tape.push_back(std::move(f)); tape_tag.push_back(cur_tag); }
@@ -546,6 +548,28 @@ struct UnetEngine {
     // caller's stream) so that at every kernel boundary the block scheduler prefers the critical path over the leaf work.
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t hp_stream = nullptr; cudaEvent_t ev_hp_fork = nullptr, ev_hp_join = nullptr;
+    // Weight repack of a TRAINING plan (every step, after the optimizer): issued on the side stream so that it overlaps the ops
+    // of the next forward that do not read packed weights (timestep embedding MLP on the fp32 masters, q_sample + in_conv);
+    // the forward list waits on ev_pack_fc / ev_pack_all right before the first consumer (Op::wait_pack).
+    cudaEvent_t ev_pack_fork = nullptr, ev_pack_fc = nullptr, ev_pack_all = nullptr; bool pack_pending = false;
+    int repack(cudaStream_t st) {
+        static const bool inline_pack = getenv("DDPM_PACK_INLINE") != nullptr;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone; cudaStreamIsCapturing(st, &cs);
+        if (!train || !side_stream || !ev_pack_all || inline_pack || cs != cudaStreamCaptureStatusNone || getenv("DDPM_DEBUG_SYNC") || getenv("DDPM_NO_SIDE_STREAM"))
+            return run_list(pack_ops, st);
+        if (cudaEventRecord(ev_pack_fork, st) || cudaStreamWaitEvent(side_stream, ev_pack_fork, 0)) return fail(-20, "repack fork failed");
+        for (int pass = 0; pass < 2; ++pass) {        // early packs (in_conv, timestep MLP: Op::wait_pack == 1) first, then the rest
+            for (auto& o : pack_ops) {
+                if ((o.wait_pack == 1) != (pass == 0)) continue;
+                const int rc = o.run(side_stream);
+                if (rc) return fail(-20, "op '%s' failed: %s", o.name.c_str(), cudaGetErrorString((cudaError_t)rc));
+            }
+            if (pass == 0 && cudaEventRecord(ev_pack_fc, side_stream)) return fail(-20, "repack event failed");
+        }
+        if (cudaEventRecord(ev_pack_all, side_stream)) return fail(-20, "repack event failed");
+        pack_pending = true;
+        return 0;
+    }
     int run_list(std::vector<Op>& L, cudaStream_t caller_st) {
         static const bool hp_main = getenv("DDPM_HP_MAIN") != nullptr;
         cudaStream_t st = caller_st;
@@ -571,6 +595,10 @@ struct UnetEngine {
                 if (o.name == "temb.sin") for (auto& u : temb_uni_ops) { rc = u.run(st); if (rc) return fail(-20, "op '%s' failed: %s", u.name.c_str(), cudaGetErrorString((cudaError_t)rc)); }
                 if (!tev.empty()) cudaEventRecord(tev[oi], st);
                 continue;
+            }
+            if (o.wait_pack && pack_pending) {
+                if (cudaStreamWaitEvent(st, o.wait_pack == 1 ? ev_pack_fc : ev_pack_all, 0)) return fail(-20, "repack join failed");
+                if (o.wait_pack == 2) pack_pending = false;
             }
             if (o.chunk >= 0) {
                 // gradient-chunk boundary: everything the main chain has written so far is joined into the side stream (which

@@ -345,6 +345,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             const dim3 gp(E / 32, maxc / 32, nblocks);
             bf16* WcatT_p = train ? WcatT : nullptr;
             push(pack_ops, "temb.pack_fc", 0, [=](cudaStream_t st) { launch_k(k_pack_fc, gp, dim3(32, 8), 0, st, ftab, Wcat, WcatT_p, bias_cat, E, tp_ld); return (int)cudaGetLastError(); });
+            pack_ops.back().wait_pack = 1;
             const long long nE = (long long)B * E;
             push(fwd_ops, "temb.silu_cast", 0, [=](cudaStream_t st) { launch_k(k_cast_bf16, grid_for(nE), 256, 0, st, e1, A_f, nE, 1); return (int)cudaGetLastError(); });
             ddpm_gemm_desc d; memset(&d, 0, sizeof d);
@@ -359,6 +360,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                 if (rc) return rc;
                 push(fwd_ops, "temb.proj", 0, [g](cudaStream_t st) { return launch_gemm(g, st); });
             } else push(fwd_ops, "temb.proj", 0, [](cudaStream_t) { return 0; });
+            fwd_ops.back().wait_pack = 1;
         } else
         push(fwd_ops, "temb.proj", 0, [tab, g1](cudaStream_t st) { launch_k(k_sgemm_table, g1, 256, 0, st, tab, (int)KS); return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * E * ch + 2.0 * B * E * E;
@@ -474,6 +476,34 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
         // h0 feeds the first norm1 and (as the last skip) the final up block's norm1: its statistics come out of this kernel
         double* qs0 = nullptr;
         if (ch % 32 == 0 && (H * W) % 32 == 0 && !getenv("DDPM_NO_GN_EPI")) { h0.qs = (long long)zero_fwd((size_t)B * (ch / 4) * 2 * 8); qs0 = at<double>((size_t)h0.qs); }
+        // tensor-core route: X = im2col(x) [P][64] bf16 (27 patch columns, zero padded to one K slab) and a 1x1 "conv" over it;
+        // the training backward reuses X for the weight gradient.  (CUDA-core k_in_conv otherwise.)
+        static const bool no_tc_inconv = getenv("DDPM_NO_TC_INCONV") != nullptr;
+        const bool tc_in = !no_tc_inconv && ch % 64 == 0 && tc_ok_geom(H, W) && 9 * Cin <= 64 && Cin <= 4;
+        T4 Xcol;
+        if (tc_in) {
+            Xcol = newT(B, H, W, 64);
+            bf16* Xp = bp(Xcol);
+            bf16* wpk = at<bf16>(alloc((size_t)ch * 64 * 2));
+            const int npk = (ch * 64 + 255) / 256; const int chn = ch, cin = Cin;
+            push(pack_ops, "in_conv.pack", 0, [=](cudaStream_t st) { launch_k(k_pack_in, npk, 256, 0, st, wi, wpk, chn, cin); return (int)cudaGetLastError(); });
+            pack_ops.back().wait_pack = 1;             // "early" pack: in_conv is the first consumer of the forward pass
+            const int nim = grid_for((long long)B * H * W);
+            push(fwd_ops, "in_conv.im2col", 0, [=](cudaStream_t st) {
+                const QsamplePro qp = self->qs_pro;   // training: x_t = q_sample(x0, t, noise) is formed while the patches are gathered
+                switch (cin) {
+                    case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, qp); break;
+                    case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, qp); break;
+                    case 3: launch_k(k_im2col3<3>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, qp); break;
+                    default: launch_k(k_im2col3<4>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, qp); break;
+                }
+                return (int)cudaGetLastError(); });
+            ConvSpec c; c.name = "in_conv"; c.in = one(Xcol); c.ksize = 1; c.wp = wpk; c.ldw = 64; c.bias = bi; c.out = h0; c.Co = ch; c.Ho = H; c.Wo = W;
+            c.want_qstats = true;
+            const size_t first_conv = fwd_ops.size();
+            h0.qs = conv_op(fwd_ops, c, nullptr);
+            if (first_conv < fwd_ops.size()) fwd_ops[first_conv].wait_pack = 1;
+        } else
         push(fwd_ops, "in_conv", 2.0 * B * H * W * ch * Cin * 9, [=](cudaStream_t st) {
             const QsamplePro qp = self->qs_pro;       // training: x_t = q_sample(x0, t, noise) is formed while the taps are loaded
             switch (Cin) {
@@ -484,6 +514,7 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             }
             return (int)cudaGetLastError(); });
         fwd_flops += 2.0 * B * H * W * ch * Cin * 9;
+        first_packed_op = fwd_ops.size();          // in_conv reads the fp32 master weights; everything after it reads packed ones
         if (train) tape_push([=]() {
             const T4 dY = grad_of(h0, nullptr);
             float* gw = GP("in_conv.weight"); float* gb = GP("in_conv.bias"); const bf16* d = bp(dY);
@@ -493,15 +524,16 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
             static const bool no_tc_in = getenv("DDPM_NO_TC_OUTCONV") != nullptr;
             if (!no_tc_in && ch % 64 == 0 && tc_ok_geom(H, W) && 9 * Cin <= 64) {
                 // weight gradient on the tensor cores: X = im2col(x) [P][64] bf16, S[ch][64] = dY^T x X (MN-major GEMM, side stream)
-                T4 X = newT(B, H, W, 64);
+                T4 X = tc_in ? Xcol : newT(B, H, W, 64);
                 bf16* Xp = bp(X);
                 const int nim = grid_for(P);
-                push(bwd_ops, "in_conv.im2col", 0, [=](cudaStream_t st) {
+                if (!tc_in) push(bwd_ops, "in_conv.im2col", 0, [=](cudaStream_t st) {
+                    const QsamplePro q0{nullptr, nullptr, nullptr, nullptr, nullptr};
                     switch (Cin) {
-                        case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
-                        case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
-                        case 3: launch_k(k_im2col3<3>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
-                        default: launch_k(k_im2col3<4>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1); break;
+                        case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, q0); break;
+                        case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, q0); break;
+                        case 3: launch_k(k_im2col3<3>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, q0); break;
+                        default: launch_k(k_im2col3<4>, nim, 256, 0, st, self->x_in, Xp, Bn, Hn, Wn, 1, q0); break;
                     }
                     return (int)cudaGetLastError(); }, 1, true);
                 float* S2 = at<float>(zero_bwd((size_t)ch * 64 * 4));
@@ -628,9 +660,9 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
                         const float* de = self->deps_src;
                         launch_k(k_chansum_nchw, dim3(64, Cout), 256, 0, st, de, gb, Bn, Cout, Hn * Wn);
                         switch (Cout) {
-                            case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1); break;
-                            case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1); break;
-                            default: launch_k(k_im2col3<3>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1); break;
+                            case 1: launch_k(k_im2col3<1>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1, QsamplePro{nullptr, nullptr, nullptr, nullptr, nullptr}); break;
+                            case 2: launch_k(k_im2col3<2>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1, QsamplePro{nullptr, nullptr, nullptr, nullptr, nullptr}); break;
+                            default: launch_k(k_im2col3<3>, nim, 256, 0, st, de, Ep, Bn, Hn, Wn, -1, QsamplePro{nullptr, nullptr, nullptr, nullptr, nullptr}); break;
                         }
                         return (int)cudaGetLastError(); }, 2);
                     ConvSpec cs; cs.name = "out_conv.2.dgrad"; cs.in = one(E); cs.ksize = 1; cs.wp = w27t; cs.ldw = 64;
@@ -741,7 +773,10 @@ inline int UnetEngine::build() {
         int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest);
         if (cudaStreamCreateWithPriority(&hp_stream, cudaStreamNonBlocking, greatest) || cudaEventCreateWithFlags(&ev_hp_fork, cudaEventDisableTiming) ||
             cudaEventCreateWithFlags(&ev_hp_join, cudaEventDisableTiming)) return fail(-2, "priority stream creation failed");
+        if (cudaEventCreateWithFlags(&ev_pack_fork, cudaEventDisableTiming) || cudaEventCreateWithFlags(&ev_pack_fc, cudaEventDisableTiming) ||
+            cudaEventCreateWithFlags(&ev_pack_all, cudaEventDisableTiming)) return fail(-2, "repack event creation failed");
     }
+    if (first_packed_op < fwd_ops.size()) fwd_ops[first_packed_op].wait_pack = 2;
     for (auto& c : chunks)
         if (!c.ev && cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming)) return fail(-2, "gradient-chunk event creation failed");
     planned = true;

@@ -123,7 +123,10 @@ long long ddpm_unet_workspace_bytes(ddpm_unet* h, int B, int H, int W, int train
 /* Bind caller-owned device buffers and compile the launch plan. grads_flat may be NULL when training == 0. */
 int ddpm_unet_plan(ddpm_unet* h, int B, int H, int W, int training, float* params_flat, float* grads_flat,
                    void* workspace, long long workspace_bytes);
-/* Re-pack fp32 master weights into the bf16 kernel layouts; call after every parameter update / load_state_dict. */
+/* Re-pack fp32 master weights into the bf16 kernel layouts; call after every parameter update / load_state_dict.
+ * Ordered after everything queued on `stream` so far.  For a TRAINING plan the pack kernels run on the engine's internal stream
+ * and the next forward/train_forward call joins them right before its first packed-weight consumer, so the pack overlaps the
+ * timestep-embedding MLP and q_sample + in_conv of that forward; inference plans pack in `stream`. */
 int ddpm_unet_repack(ddpm_unet* h, void* stream);
 /* eps = UNet(x, t):  x f32[B,Cin,H,W] NCHW, t i64[B], eps f32[B,Cout,H,W]   (unet.py:205-233) */
 int ddpm_unet_forward(ddpm_unet* h, const float* x, const int64_t* t, float* eps, uint64_t dropout_seed, void* stream);

@@ -1,15 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gemm_gpu.py -q --timeout 120 -x -k "fused_groupnorm_input" 2>&1 | tail -2
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-stock > gpurun_out/r2_bench7.json 2>/dev/null
-python - <<PY
+timeout 1500 python -m pytest tests -q -m gpu --timeout 900 -x > gpurun_out/r2_tests6.txt 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_tests6.txt
+grep -E "FAILED|Error" gpurun_out/r2_tests6.txt | head
+for v in "X=0" "DDPM_PACK_INLINE=1" "DDPM_NO_TC_INCONV=1" "X=0"; do
+  echo "== $v"
+  env $v timeout 600 python bench.py --no-cpu-baseline --no-stock --no-hq > gpurun_out/r2_bench6_ab.json 2>gpurun_out/ab.err || tail -3 gpurun_out/ab.err
+  python - <<PY
 import json
-d=json.load(open("gpurun_out/r2_bench7.json")); print("XF: ddim50", d["sampler"]["ddim50"]["ms_per_step"], "anc", d["sampler"]["ancestral1000"]["ms_per_step"], "hq_ddim", d["hq_ddim100"]["ms_per_step"])
+d=json.load(open("gpurun_out/r2_bench6_ab.json")); print("BENCH ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"]), "ddim50", round(d["sampler"]["ddim50"]["ms_per_step"],3), "anc", round(d["sampler"]["ancestral1000"]["ms_per_step"],3))
 PY
-DDPM_NO_XF=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-stock > gpurun_out/r2_bench7_noxf.json 2>/dev/null
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r2_bench7_noxf.json")); print("NO_XF: ddim50", d["sampler"]["ddim50"]["ms_per_step"], "anc", d["sampler"]["ancestral1000"]["ms_per_step"], "hq_ddim", d["hq_ddim100"]["ms_per_step"])
-PY
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_fwd256_d.csv python tools/profile_step.py fwd 256 > gpurun_out/r2_ncu_fwd_d.log 2>&1
-python tools/agg_launches.py gpurun_out/r2_launches_fwd256_d.csv 8
+done
