@@ -82,6 +82,7 @@ def lib():
         sig = {
             "ddpm_conv_halo_run": ([C.POINTER(HaloDesc), vp], i32),
             "ddpm_attn_fused_run": ([vp, vp, vp, i32, i32, i32, vp], i32),
+            "ddpm_attn_fused_bwd_run": ([vp, vp, vp, vp, vp, i32, i32, i32, vp], i32),
             "ddpm_unet_create": ([C.POINTER(UnetCfg), C.POINTER(vp)], i32),
             "ddpm_unet_destroy": ([vp], None),
             "ddpm_unet_num_params": ([vp], i32),
@@ -115,7 +116,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "ddpm_gemm_run", "ddpm_conv_halo_run", "ddpm_attn_fused_run",
+EXPORTS = ["ddpm_last_error", "ddpm_runtime_check", "ddpm_device_error_flag", "ddpm_gemm_run", "ddpm_conv_halo_run", "ddpm_attn_fused_run", "ddpm_attn_fused_bwd_run",
            "ddpm_unet_create", "ddpm_unet_destroy", "ddpm_unet_num_params", "ddpm_unet_param_info",
            "ddpm_unet_flat_elems", "ddpm_unet_workspace_bytes", "ddpm_unet_plan", "ddpm_unet_repack",
            "ddpm_unet_forward", "ddpm_unet_backward", "ddpm_train_forward", "ddpm_train_backward",

@@ -16,7 +16,13 @@
 
 namespace ddpm {
 
-struct AttnParams { int NB; __nv_bfloat16* out; float scale_log2e; __nv_bfloat16* pm; };   // pm: optional [NB][T][T] normalised probabilities (training)
+struct AttnParams {
+    int NB; __nv_bfloat16* out; float scale_log2e;
+    __nv_bfloat16* pm;             // forward: optional [NB][T][T] normalised probabilities out (training).  backward: the saved P (in)
+    __nv_bfloat16* ds;             // backward: [NB][T][T] dS out (the dK / dV GEMMs read it)
+    int out_ld;                    // row stride of `out` in elements (forward C; backward 3C: dQ lands in the q third of dqkv)
+    float scale;                   // backward: 1/sqrt(C)
+};
 
 constexpr int ATTN_T = 256, ATTN_D = 256;
 constexpr int ATTN_STAGES = 3;
@@ -25,9 +31,17 @@ constexpr int ATTN_P_BYTES = 128 * ATTN_T * 2;            // 64 KB
 constexpr int ATTN_SMEM = ATTN_STAGES * ATTN_STAGE_BYTES + ATTN_P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int ATTN_THREADS = 192;
 
+// BWD = false: the forward described above.
+// BWD = true : the query-side half of the backward pass with the same pipeline, operands swapped:
+//                dP[128 x 256] = dO . V^T   (A = dO chunks through tmQ, B = V rows through tmK at channel offset 2C)
+//                dS = P o (dP - rowsum(P o dP)) / sqrt(C)     (softmax warps; P read from HBM, dS -> shared tile + HBM)
+//                dQ[128 x 256] = dS . K     (A = dS tile, B = K rows MN-major through tmV at channel offset C)
+//              replacing three launches (dP GEMM -> fp32 in HBM, softmax backward, dQ GEMM); dK = dS^T Q and dV = P^T dO stay
+//              GEMM launches that read dS / P from HBM.
+template <bool BWD>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -65,7 +79,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 uint8_t* sb = smem + st * ATTN_STAGE_BYTES;
                 mbar_expect_tx(&full_bar[st], 16384 + 32768);
                 tma_load_4d(sb, &tmQ, &full_bar[st], kc * 64, half * 128, 0, img);
-                tma_load_4d(sb + 16384, &tmK, &full_bar[st], ATTN_D + kc * 64, 0, 0, img);
+                tma_load_4d(sb + 16384, &tmK, &full_bar[st], (BWD ? 2 * ATTN_D : ATTN_D) + kc * 64, 0, 0, img);
             }
             for (int j = 0; j < ATTN_T / 64 && ok; ++j, ++stg) {         // V key chunks (prefetched while the softmax runs)
                 const int st = stg % ATTN_STAGES; const uint32_t ph = (stg / ATTN_STAGES) & 1;
@@ -74,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_expect_tx(&full_bar[st], 32768);
 #pragma unroll
                 for (int b = 0; b < ATTN_D / 64; ++b)
-                    tma_load_4d(sb + b * 8192, &tmV, &full_bar[st], 2 * ATTN_D + b * 64, j * 64, 0, img);
+                    tma_load_4d(sb + b * 8192, &tmV, &full_bar[st], (BWD ? ATTN_D : 2 * ATTN_D) + b * 64, j * 64, 0, img);
             }
         }
     } else if (warp == 1) {
@@ -113,6 +127,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int q = warp & 3;                       // TMEM lane quarter of this warp (warps 2,3,4,5 -> 2,3,0,1)
         const int r = q * 32 + lane;                  // row of the tile
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (BWD) {
+          if (mbar_wait(s_full, 0, 16)) {
+            tc_fence_after();
+            const __nv_bfloat16* prow = p.pm + ((long long)img * ATTN_T + half * 128 + r) * ATTN_T;
+            __nv_bfloat16* dsrow = p.ds + ((long long)img * ATTN_T + half * 128 + r) * ATTN_T;
+            float delta = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < 8; ++ch) {
+                uint32_t v[32], pr[16];
+                tmem_ld32(t_row + (uint32_t)(ch * 32), v);
+                ld_global_nc_256(prow + ch * 32, pr); ld_global_nc_256(prow + ch * 32 + 16, pr + 8);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float2 pp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr[e]));
+                    delta = fmaf(pp.x, __uint_as_float(v[2 * e]), fmaf(pp.y, __uint_as_float(v[2 * e + 1]), delta));
+                }
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < 8; ++ch) {
+                uint32_t v[32], pr[16], pk[16];
+                tmem_ld32(t_row + (uint32_t)(ch * 32), v);
+                ld_global_nc_256(prow + ch * 32, pr); ld_global_nc_256(prow + ch * 32 + 16, pr + 8);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float2 pp = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr[e]));
+                    pk[e] = pack_bf16x2(pp.x * (__uint_as_float(v[2 * e]) - delta) * p.scale, pp.y * (__uint_as_float(v[2 * e + 1]) - delta) * p.scale);
+                }
+                uint8_t* rowp = smP + (ch >> 1) * 16384 + r * 128;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    st_shared_v4(rowp + ((((ch & 1) * 4 + i) ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                st_global_256(dsrow + ch * 32, pk); st_global_256(dsrow + ch * 32 + 16, pk + 8);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+            if (mbar_wait(o_full, 0, 17)) {
+                tc_fence_after();
+                __nv_bfloat16* orow = p.out + ((long long)img * ATTN_T + half * 128 + r) * p.out_ld;
+#pragma unroll 1
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + 256u + (uint32_t)(ch * 32), v);
+                    tmem_ld_wait();
+                    uint32_t u[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) u[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    st_global_256(orow + ch * 32, u); st_global_256(orow + ch * 32 + 16, u + 8);
+                }
+            }
+          }
+        } else
         if (mbar_wait(s_full, 0, 16)) {
             tc_fence_after();
             float m = -3.0e38f;
@@ -173,7 +242,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             if (mbar_wait(o_full, 0, 17)) {
                 tc_fence_after();
-                __nv_bfloat16* orow = p.out + ((long long)img * ATTN_T + half * 128 + r) * ATTN_D;
+                __nv_bfloat16* orow = p.out + ((long long)img * ATTN_T + half * 128 + r) * p.out_ld;
 #pragma unroll 1
                 for (int ch = 0; ch < 8; ++ch) {
                     uint32_t v[32];
@@ -209,13 +278,34 @@ inline int build_attn(const void* qkv, void* out, int NB, int T, int C, AttnLaun
     if ((rc = make_tmap_4d(&g.k, qkv, 3 * C, T, 1, NB, 3 * C, 64, 256, 1, 1))) return rc;
     if ((rc = make_tmap_4d(&g.v, qkv, 3 * C, T, 1, NB, 3 * C, 64, 64, 1, 1))) return rc;
     g.p.NB = NB; g.p.out = reinterpret_cast<__nv_bfloat16*>(out); g.p.pm = reinterpret_cast<__nv_bfloat16*>(pm);
-    g.p.scale_log2e = 1.4426950408889634f / sqrtf((float)C);
+    g.p.scale_log2e = 1.4426950408889634f / sqrtf((float)C); g.p.out_ld = C; g.p.scale = 1.f / sqrtf((float)C);
+    return 0;
+}
+// backward, query side: qkv bf16 [NB][T][3C], dO bf16 [NB][T][C], probs bf16 [NB][T][T] (saved by the forward) ->
+// ds bf16 [NB][T][T] and dQ into the q third of dqkv bf16 [NB][T][3C]
+inline int build_attn_bwd(const void* qkv, const void* dO, const void* probs, void* ds, void* dqkv, int NB, int T, int C, AttnLaunch& g) {
+    if (!attn_fused_eligible(T, C)) return fail(-13, "fused attention backward: T=%d C=%d unsupported (needs T=256, C=256)", T, C);
+    memset(&g, 0, sizeof g);
+    int rc;
+    if ((rc = make_tmap_4d(&g.q, dO, C, T, 1, NB, C, 64, 128, 1, 1))) return rc;
+    if ((rc = make_tmap_4d(&g.k, qkv, 3 * C, T, 1, NB, 3 * C, 64, 256, 1, 1))) return rc;
+    if ((rc = make_tmap_4d(&g.v, qkv, 3 * C, T, 1, NB, 3 * C, 64, 64, 1, 1))) return rc;
+    g.p.NB = NB; g.p.out = reinterpret_cast<__nv_bfloat16*>(dqkv); g.p.out_ld = 3 * C;
+    g.p.pm = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(probs)); g.p.ds = reinterpret_cast<__nv_bfloat16*>(ds);
+    g.p.scale = 1.f / sqrtf((float)C); g.p.scale_log2e = 0.f;
     return 0;
 }
 inline int launch_attn(const AttnLaunch& g, cudaStream_t st) {
     static bool attr_done = false;
-    if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM)); attr_done = true; }
-    launch_k(attn_fwd_kernel, 2 * g.p.NB, ATTN_THREADS, ATTN_SMEM, st, g.q, g.k, g.v, g.p);
+    if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM)); attr_done = true; }
+    launch_k(attn_kernel<false>, 2 * g.p.NB, ATTN_THREADS, ATTN_SMEM, st, g.q, g.k, g.v, g.p);
+    DDPM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+inline int launch_attn_bwd(const AttnLaunch& g, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) { DDPM_CUDA_OK(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM)); attr_done = true; }
+    launch_k(attn_kernel<true>, 2 * g.p.NB, ATTN_THREADS, ATTN_SMEM, st, g.q, g.k, g.v, g.p);
     DDPM_CUDA_OK(cudaGetLastError());
     return 0;
 }

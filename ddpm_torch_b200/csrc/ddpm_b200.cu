@@ -61,6 +61,13 @@ int ddpm_attn_fused_run(const void* qkv, void* out, void* probs, int NB, int T, 
     return launch_attn(g, static_cast<cudaStream_t>(stream));
 }
 
+int ddpm_attn_fused_bwd_run(const void* qkv, const void* d_out, const void* probs, void* d_scores, void* d_qkv, int NB, int T, int C, void* stream) {
+    AttnLaunch g;
+    int rc = build_attn_bwd(qkv, d_out, probs, d_scores, d_qkv, NB, T, C, g);
+    if (rc) return rc;
+    return launch_attn_bwd(g, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ UNet engine
 int ddpm_unet_create(const ddpm_unet_cfg* cfg, ddpm_unet** out) {
     if (!cfg || !out) return fail(-30, "null argument");

@@ -133,6 +133,11 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     static const bool no_fused_attn = getenv("DDPM_NO_FUSED_ATTN") != nullptr;
     static const bool no_attn16 = getenv("DDPM_NO_ATTN16") != nullptr;
     const bool small16 = !no_attn16 && attn16_eligible(T, C);
+    // OPT-IN (DDPM_FUSED_ATTN_BWD=1, read at plan time): dP -> softmax backward -> dQ as one launch is parity-green and 3x shorter than
+    // the three launches it replaces, but its 214 KB CTAs cannot co-reside with the weight-gradient GEMMs of the side stream
+    // and the whole step is 0.3 % slower (9.21 vs 9.18 ms); profiles/r02_attention_backward_experiment.txt
+    static const bool fused_attn_bwd = getenv("DDPM_FUSED_ATTN_BWD") != nullptr;
+    const bool fused_bwd = train && fused_attn_bwd && !no_fused_attn && attn_fused_eligible(T, C);
     static const bool no_fused_attn_train = getenv("DDPM_NO_FUSED_ATTN_TRAIN") != nullptr;
     if (!(train && no_fused_attn_train) && !no_fused_attn && attn_fused_eligible(T, C)) {
         // Q.K^T -> softmax -> P.V in ONE kernel, S and O in TMEM, P in shared memory (attn_fused.cuh); training plans also get
@@ -182,6 +187,19 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
             const size_t shm = attn16_smem(C, true); const bf16* Pk = Pm;
             if (!dry) cudaFuncSetAttribute(k_attn16_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn16_smem(512, true));
             push(bwd_ops, p + ".attn_bwd[t16]", fl, [=](cudaStream_t st) { launch_k(k_attn16_bwd, Bn, 256, shm, st, q, dOp, Pk, dq, C, scale); return (int)cudaGetLastError(); });
+        } else if (fused_bwd) {
+            // dP -> softmax backward -> dQ in one launch (attn_kernel<true>); dK and dV read dS / P back as GEMM operands
+            bf16* dS = at<bf16>(alloc((size_t)Bn * T * T * 2));
+            const double fl = 4.0 * Bn * (double)T * T * C;
+            bwd_flops += fl; ++n_tc_gemms;
+            if (dry) push(bwd_ops, p + ".attn_bwd[fused]", fl, [](cudaStream_t) { return 0; });
+            else {
+                AttnLaunch g; const int rc = build_attn_bwd(q, dOp, Pm, dS, dq, Bn, T, C, g);
+                if (rc) { plan_error = rc; return; }
+                push(bwd_ops, p + ".attn_bwd[fused]", fl, [g](cudaStream_t st) { return launch_attn_bwd(g, st); });
+            }
+            bmm(bwd_ops, p + ".dV", 2, Pm, T, (long long)T * T, dOp, C, (long long)T * C, dq + 2 * C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
+            bmm(bwd_ops, p + ".dK", 2, dS, T, (long long)T * T, q, ldq, sq, dq + C, ldq, sq, false, Bn, T, C, 1.f, &bwd_flops);
         } else {
         float* dP = at<float>(alloc((size_t)Bn * T * T * 4));
         bf16* dS = at<bf16>(alloc((size_t)Bn * T * T * 2));

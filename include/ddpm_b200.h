@@ -97,6 +97,10 @@ int ddpm_conv_halo_run(const ddpm_halo_desc* d, void* stream);
  * probs (optional, NULL = off): bf16 [NB][T][T], receives the softmax probabilities that the backward pass of a training plan
  * consumes (written from the shared-memory tile while P.V runs). */
 int ddpm_attn_fused_run(const void* qkv, void* out, void* probs, int NB, int T, int C, void* stream);
+/* Query-side half of the attention backward (autograd of unet.py:43-51) as ONE kernel: with P = probs saved by the forward,
+ * dP = d_out V^T,  dS = P o (dP - rowsum(P o dP)) / sqrt(C)  -> d_scores bf16 [NB][T][T],  dQ = dS K -> the q third of
+ * d_qkv bf16 [NB][T][3C].  dK = dS^T Q and dV = P^T d_out are plain GEMMs over d_scores / probs (ddpm_gemm_run).  T = 256, C = 256. */
+int ddpm_attn_fused_bwd_run(const void* qkv, const void* d_out, const void* probs, void* d_scores, void* d_qkv, int NB, int T, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * UNet engine.  replaces: UNet.__init__/forward (ddpm_torch/models/unet.py:96-233), its autograd backward,

@@ -467,3 +467,29 @@ def test_attention_fused_kernel(NB):
     assert r < 6e-3            # bf16 P (one rounding) + bf16 output
     assert torch.equal(out, out2)          # writing the probabilities does not change the product
     assert rp < 8e-3           # bf16 probabilities (two roundings), the tensor the training backward reads
+
+
+@pytest.mark.parametrize("NB", [1, 5, 64])
+def test_attention_fused_backward_kernel(NB):
+    """dP -> softmax backward -> dQ in one kernel (attn_kernel<true>) vs fp32 torch autograd formulas on the same bf16 operands."""
+    from ddpm_torch_b200 import _lib
+    T, Cc = 256, 256
+    qkv = bf(NB, T, 3 * Cc, seed=10 + NB, scale=1.0)
+    dO = bf(NB, T, Cc, seed=20 + NB, scale=1.0)
+    q, k, v = qkv.float().chunk(3, dim=-1)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    P = torch.softmax(torch.einsum("btc,bsc->bts", q, k) / Cc ** 0.5, dim=-1).to(torch.bfloat16)
+    dS = torch.full((NB, T, T), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dqkv = torch.zeros(NB, T, 3 * Cc, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ddpm_attn_fused_bwd_run(qkv.data_ptr(), dO.data_ptr(), P.data_ptr(), dS.data_ptr(), dqkv.data_ptr(),
+                                                  NB, T, Cc, _lib.stream_ptr()), "attn_fused_bwd_run")
+    torch.cuda.synchronize()
+    assert _lib.lib().ddpm_device_error_flag() == 0
+    Pf = P.float()
+    dP = torch.einsum("btc,bsc->bts", dO.float(), v)
+    dS_ref = Pf * (dP - (Pf * dP).sum(-1, keepdim=True)) / Cc ** 0.5
+    dQ_ref = torch.einsum("bts,bsc->btc", dS_ref, k)
+    r_s = rel(dS.float(), dS_ref); r_q = rel(dqkv[..., :Cc].float(), dQ_ref)
+    print(f"\n[fused attention backward NB={NB}] rel-L2 dS {r_s:.3e}  dQ {r_q:.3e}")
+    assert r_s < 6e-3 and r_q < 8e-3          # bf16 dS (one rounding), bf16 dQ over the rounded dS
+    assert torch.count_nonzero(dqkv[..., Cc:]) == 0           # only the q third is written
