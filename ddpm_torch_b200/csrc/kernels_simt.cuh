@@ -1546,7 +1546,7 @@ __global__ void k_pack_conv_w_s2dgrad(const float* __restrict__ w, bf16* __restr
     }
 }
 // ---- table-driven weight maintenance: ONE launch re-packs every conv weight (grid.y = table entry)
-enum PackKind { PK_CONV = 0, PK_BIAS_ADD = 1, PK_FLIP_T = 2, PK_UNPACK_GRAD = 3 };
+enum PackKind { PK_CONV = 0, PK_BIAS_ADD = 1, PK_FLIP_T = 2, PK_UNPACK_GRAD = 3, PK_UPFOLD = 4 };
 struct PackEntry {
     int kind; int Co, Ci, taps; int k_off; int dkind;   // dkind: 0 none, 1 dgrad, 2 dgrad flipped taps, 3 stride-2 parity dgrad
     const float* w; const float* w2; bf16* fwd; long long ld_f; bf16* dgr; long long ld_d; float* fout; float* scratch;
@@ -1572,6 +1572,29 @@ __global__ void __launch_bounds__(256) k_pack_table(const PackEntry* __restrict_
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
             const int t = (int)(i % e.taps); const long long r = i / e.taps; const int ci = (int)(r % e.Ci), co = (int)(r / e.Ci);
             e.fout[((long long)ci * e.Co + co) * 9 + (8 - t)] = e.w[i];
+        }
+        return;
+    }
+    if (e.kind == PK_UPFOLD) {
+        // nearest-2x upsample folded into the 3x3 conv that follows it (unet.py:199-202): output pixel (2y+py, 2x+px) sees a 2x2
+        // neighbourhood of the LOW-resolution input, with the 3x3 taps that land on the same input pixel summed:
+        //   rows  py=0: {ky=0} -> y-1, {ky=1,2} -> y      py=1: {ky=0,1} -> y, {ky=2} -> y+1      (columns alike)
+        // fwd[co][(q*4 + a*2 + b)*Ci + ci], q = py*2+px, (a, b) = the 2x2 tap in (row, column) order
+        const long long total = (long long)e.Co * 16 * (e.Ci / 8);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int o = (int)(i % (e.Ci / 8)); const int tq = (int)((i / (e.Ci / 8)) % 16); const int co = (int)(i / ((long long)16 * (e.Ci / 8)));
+            const int q = tq >> 2, a = (tq >> 1) & 1, b = tq & 1, py = q >> 1, px = q & 1;
+            const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+            const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+            float f[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float* wp = e.w + ((long long)co * e.Ci + o * 8 + u) * 9;
+                float acc = 0.f;
+                for (int ky = ky0; ky <= ky1; ++ky) for (int kx = kx0; kx <= kx1; ++kx) acc += wp[ky * 3 + kx];
+                f[u] = acc;
+            }
+            *reinterpret_cast<uint4*>(e.fwd + (long long)co * e.ld_f + (long long)tq * e.Ci + o * 8) = pack8(f);
         }
         return;
     }

@@ -136,7 +136,7 @@ inline T4 UnetEngine::attn_block(const std::string& p, const T4& x) {
     // OPT-IN (DDPM_FUSED_ATTN_BWD=1, read at plan time): dP -> softmax backward -> dQ as one launch is parity-green and 3x shorter than
     // the three launches it replaces, but its 214 KB CTAs cannot co-reside with the weight-gradient GEMMs of the side stream
     // and the whole step is 0.3 % slower (9.21 vs 9.18 ms); profiles/r02_attention_backward_experiment.txt
-    static const bool fused_attn_bwd = getenv("DDPM_FUSED_ATTN_BWD") != nullptr;
+    const bool fused_attn_bwd = getenv("DDPM_FUSED_ATTN_BWD") != nullptr;
     const bool fused_bwd = train && fused_attn_bwd && !no_fused_attn && attn_fused_eligible(T, C);
     static const bool no_fused_attn_train = getenv("DDPM_NO_FUSED_ATTN_TRAIN") != nullptr;
     if (!(train && no_fused_attn_train) && !no_fused_attn && attn_fused_eligible(T, C)) {
@@ -273,6 +273,42 @@ inline T4 UnetEngine::down_conv(const std::string& p, const T4& x) {
 // Upsample (unet.py:199-202): nearest x2 then 3x3 conv
 inline T4 UnetEngine::up_conv(const std::string& p, const T4& x) {
     const int C = x.C, Bn = x.B, h = x.H, w = x.W;
+    static const bool no_fold = getenv("DDPM_NO_UPFOLD") != nullptr;
+    // (128-channel layers keep the explicit form: their folded GEMMs have 128-wide tiles, which the shared-memory operand
+    // bandwidth caps at ~2/3 of the MMA rate, and the haloed kernel on the 2x grid wins - CelebA-HQ 256^2: 6.16 vs 6.26 ms/step)
+    if (!train && !no_fold && C % 256 == 0 && tc_ok_geom(h, w)) {
+        // Inference plans: the upsampled tensor is never materialised.  Four output-parity sub-convolutions with 2x2 taps over the
+        // low-resolution input (merged weights, PK_UPFOLD) scatter to the (2y+py, 2x+px) pixels: 4/9 of the MACs, no 2x copy.
+        // (Training keeps the explicit form: the weight gradient wants the upsampled tensor as its operand.)
+        Packed pk; pk.ld_f = 16LL * C; pk.fwd = at<bf16>(alloc((size_t)C * pk.ld_f * 2));
+        { PackEntry e; memset(&e, 0, sizeof e); e.kind = PK_UPFOLD; e.Co = C; e.Ci = C; e.taps = 9; e.w = PP(p + ".weight"); e.fwd = pk.fwd; e.ld_f = pk.ld_f;
+          pack_table_host.push_back(e); }
+        T4 out = newT(Bn, 2 * h, 2 * w, C);
+        const double fl = 2.0 * out.pix() * C * 9.0 * C;       // the reference's count (the folded form does 4/9 of it)
+        fwd_flops += fl;
+        ddpm_gn_epi gn; memset(&gn, 0, sizeof gn);
+        static const bool no_fuse = getenv("DDPM_NO_GN_EPI") != nullptr;
+        if (!no_fuse && C % 32 == 0 && (h * w) % 32 == 0) { out.qs = (long long)zero_fwd((size_t)Bn * (C / 4) * 2 * 8); gn.qstats = at<double>((size_t)out.qs); }
+        for (int q = 0; q < 4; ++q) {
+            const int py = q >> 1, px = q & 1;
+            ddpm_gemm_desc d; memset(&d, 0, sizeof d);
+            d.mode = GEMM_KK; d.M = (int)x.pix(); d.N = C; d.W = w; d.H = h; d.NB = Bn;
+            d.a_ptr[0] = bp(x); d.a_C[0] = C; d.a_ld[0] = C;
+            d.nseg = 1; d.seg_map[0] = 0; d.seg_kchunks[0] = C / 64; d.seg_cbase[0] = 0; d.seg_custom[0] = 1; d.seg_cmul[0] = 1; d.seg_taps[0] = 4;
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+                d.seg_dy[0][a * 2 + b] = (signed char)(py == 0 ? a - 1 : a); d.seg_dx[0][a * 2 + b] = (signed char)(px == 0 ? b - 1 : b);
+            }
+            d.b_ptr = pk.fwd; d.b_K = 16 * C; d.b_rows = C; d.b_batch = 1; d.b_ld = pk.ld_f; d.b_k_base = q * 4 * C;
+            d.out = bp(out); d.ldo = C; d.alpha = 1.f; d.grid_z = 1; d.o_mul = 2; d.o_py = py; d.o_px = px;
+            d.bias = PP(p + ".bias"); d.gn = gn;
+            ++n_tc_gemms;
+            if (dry) { push(fwd_ops, p + "[fold]", q ? 0 : fl, [](cudaStream_t) { return 0; }); continue; }
+            GemmLaunch g; const int rc = build_gemm(d, g);
+            if (rc) { plan_error = rc; return out; }
+            push(fwd_ops, p + "[fold]", q ? 0 : fl, [g](cudaStream_t st) { return launch_gemm(g, st); });
+        }
+        return out;
+    }
     T4 up = newT(Bn, 2 * h, 2 * w, C);
     { const bf16* src = bp(x); bf16* dst = bp(up); const int n = grid_for((long long)Bn * 4 * h * w * (C / 8));
       push(fwd_ops, p + ".upsample", 0, [=](cudaStream_t st) { launch_k(k_upsample2x, n, 256, 0, st, src, dst, Bn, h, w, C); return (int)cudaGetLastError(); }); }

@@ -386,3 +386,16 @@ def test_operand_path_groupnorm_optin(golden, monkeypatch):
     print(f"\n[DDPM_XF=1] eps rel-L2 {r:.3e}")
     assert r < 1e-2
     flag_ok()
+
+
+def test_fused_attention_backward_optin(golden, monkeypatch):
+    """DDPM_FUSED_ATTN_BWD=1 (opt-in, measured neutral - profiles/r02_attention_backward_experiment.txt): dP -> softmax backward -> dQ of
+    the 16x16 attention blocks as one launch.  Same parity bar as the default training plan."""
+    monkeypatch.setenv("DDPM_FUSED_ATTN_BWD", "1")
+    fx = golden("unet_cifar10_bs4.pt")
+    m, sd = build(fx["cfg"], fx["seed"], train=True)
+    g = torch.Generator(DEV).manual_seed(77)
+    x0 = torch.rand(8, 3, 32, 32, device=DEV, generator=g) * 2 - 1
+    t = torch.randint(1000, (8,), device=DEV, generator=g)
+    noise = torch.randn(8, 3, 32, 32, device=DEV, generator=g)
+    grads_vs_oracle(m, sd, fx["cfg"], x0, t, noise, "cifar10 bs=8 train, fused attention backward")
