@@ -254,7 +254,7 @@ def stock_cuda_reference(dev, my_train_ms, my_sampler_ms, bs=128, sbs=256):
 
 def dominant_kernel_roofline(pk, iters=30):
     """Time the dominant tcgen05 launch of the step in isolation, live, with CUDA events on the launching stream:
-    3x3 conv Ci=Co=128 at 32x32, batch 128 (conv3x3_halo_kernel<128,1>; 7 forward + 7 dgrad launches per step share this
+    3x3 conv Ci=Co=128 at 32x32, batch 128 (conv3x3_halo2_kernel<128,0>, the CTA-pair kernel; 7 forward + 7 dgrad launches per step share this
     shape, 17% of the step's FLOPs).  Inputs (33.5 MB in + 33.5 MB out per launch) rotate over 8 buffer pairs
     (537 MB > 126 MB L2).  achieved = 2*B*H*W*Co*9*Ci FLOPs / mean launch time."""
     import ctypes as C
@@ -288,10 +288,10 @@ def dominant_kernel_roofline(pk, iters=30):
     flops = 2.0 * B * H * W * Co * 9 * Ci
     ach = flops / (ms * 1e-3) / 1e12
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape from the committed ncu --set full capture
-    # (profiles/r01_ncu_full_conv3x3_halo_128.txt): 33.94 MB read + 0.13 MB written per launch; algorithmic bytes are
+    # (profiles/r02_ncu_full_conv3x3_halo2.txt, first launch): 34.01 MB read + 0.40 MB written per launch; algorithmic bytes are
     # 33.5 MB in + 33.5 MB out + 0.3 MB weights (the output is still resident in the 126 MB L2 when the kernel ends)
-    return {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": 34.47e6,
-            "kernel": "conv3x3_halo_kernel<128,1>: conv3x3 128->128 @32x32 B=128 (isolated, rotating buffers > L2)",
+    return {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "traffic": 34.41e6,
+            "kernel": "conv3x3_halo2_kernel<128,0> (cta_group::2 pair): conv3x3 128->128 @32x32 B=128 (isolated, rotating buffers > L2)",
             "ms_per_launch": ms, "gflop_per_launch": flops / 1e9, "peak_source": f"{pk['src']} bf16 burst (MEASURED_PEAKS.json)"}
 
 
