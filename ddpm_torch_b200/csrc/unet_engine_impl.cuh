@@ -805,6 +805,10 @@ inline int UnetEngine::plan(int B_, int H_, int W_, bool train_, bool dry_) {
 }
 
 inline int UnetEngine::build() {
+    // a re-plan moves the workspace offsets: a weight re-pack of the PREVIOUS plan that is still queued on the (non-blocking) side
+    // stream must have drained before the tables are rewritten and before the new plan's first ops touch the workspace
+    if (side_stream) cudaStreamSynchronize(side_stream);
+    pack_pending = false;
     // tables -> device ; plan-time zeroed arenas
     auto up = [&](size_t off, const std::vector<SgemmParams>& v) -> int {
         if (v.empty()) return 0;
