@@ -189,6 +189,8 @@ class UNet(nn.Module):
                 _lib.check(int(need), "workspace_bytes")
             dev = self._flat.device
             if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                if self._ws is not None:
+                    torch.cuda.synchronize(self._ws.device)     # the engine's side stream may still hold a queued weight re-pack into it
                 self._ws = None
                 self._ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
             if training and (self._grads is None or self._grads.device != dev):
