@@ -89,7 +89,6 @@ void ddpm_unet_destroy(ddpm_unet* h) {
     if (h->e.side_stream) { cudaStreamSynchronize(h->e.side_stream);   // a queued weight re-pack still writes into the caller's workspace
         cudaStreamDestroy(h->e.side_stream); cudaEventDestroy(h->e.ev_fork); cudaEventDestroy(h->e.ev_join); }
     for (auto& c : h->e.chunks) if (c.ev) cudaEventDestroy(c.ev);
-    if (h->e.hp_stream) { cudaStreamDestroy(h->e.hp_stream); cudaEventDestroy(h->e.ev_hp_fork); cudaEventDestroy(h->e.ev_hp_join); }
     if (h->e.ev_pack_all) { cudaEventDestroy(h->e.ev_pack_fork); cudaEventDestroy(h->e.ev_pack_fc); cudaEventDestroy(h->e.ev_pack_all); }
     delete h;
 }

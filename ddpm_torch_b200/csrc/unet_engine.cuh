@@ -546,10 +546,9 @@ struct UnetEngine {
     // Ops flagged `side` (bias-gradient column sums, gradient unpacks: small, memory-bound, nothing downstream needs them
     // before the end of the pass) are forked onto a second stream so they overlap the tensor-core kernels, and joined at
     // the end of the list.  Fork/join are event edges, so the pattern is CUDA-graph capturable.
-    // With side work in the list, the dependent main chain itself moves to a HIGH-priority stream (forked from / joined to the
-    // caller's stream) so that at every kernel boundary the block scheduler prefers the critical path over the leaf work.
+    // (Stream priorities were measured both ways on the whole step - main chain high: 10.17 ms, side stream high: 9.46 ms, equal: 9.06 ms -
+    // and are not used; profiles/r02_scheduling_ab.txt.)
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaStream_t hp_stream = nullptr; cudaEvent_t ev_hp_fork = nullptr, ev_hp_join = nullptr;
     // Weight repack of a TRAINING plan (every step, after the optimizer): issued on the side stream so that it overlaps the ops
     // of the next forward that do not read packed weights (timestep embedding MLP on the fp32 masters, q_sample + in_conv);
     // the forward list waits on ev_pack_fc / ev_pack_all right before the first consumer (Op::wait_pack).
@@ -573,14 +572,7 @@ struct UnetEngine {
         return 0;
     }
     int run_list(std::vector<Op>& L, cudaStream_t caller_st) {
-        static const bool hp_main = getenv("DDPM_HP_MAIN") != nullptr;
         cudaStream_t st = caller_st;
-        bool any_side = false; for (auto& o : L) any_side |= o.side;
-        const bool use_hp = hp_main && hp_stream && any_side && !getenv("DDPM_DEBUG_SYNC") && !getenv("DDPM_NO_SIDE_STREAM");
-        if (use_hp) {
-            if (cudaEventRecord(ev_hp_fork, caller_st) || cudaStreamWaitEvent(hp_stream, ev_hp_fork, 0)) return fail(-20, "priority-stream fork failed");
-            st = hp_stream;
-        }
         static const bool dbg = getenv("DDPM_DEBUG_SYNC") != nullptr;   // serialise + attribute faults to an op (never under graph capture)
         static const bool no_side = getenv("DDPM_NO_SIDE_STREAM") != nullptr;
         bool forked = false;
@@ -645,9 +637,6 @@ struct UnetEngine {
             }
             for (auto& e : tev) cudaEventDestroy(e);
             cudaEventDestroy(fin);
-        }
-        if (use_hp) {
-            if (cudaEventRecord(ev_hp_join, hp_stream) || cudaStreamWaitEvent(caller_st, ev_hp_join, 0)) return fail(-20, "priority-stream join failed");
         }
         return 0;
     }

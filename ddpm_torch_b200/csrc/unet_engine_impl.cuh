@@ -828,9 +828,6 @@ inline int UnetEngine::build() {
     if (!side_stream) {
         if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) ||
             cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)) return fail(-2, "side stream creation failed");
-        int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        if (cudaStreamCreateWithPriority(&hp_stream, cudaStreamNonBlocking, greatest) || cudaEventCreateWithFlags(&ev_hp_fork, cudaEventDisableTiming) ||
-            cudaEventCreateWithFlags(&ev_hp_join, cudaEventDisableTiming)) return fail(-2, "priority stream creation failed");
         if (cudaEventCreateWithFlags(&ev_pack_fork, cudaEventDisableTiming) || cudaEventCreateWithFlags(&ev_pack_fc, cudaEventDisableTiming) ||
             cudaEventCreateWithFlags(&ev_pack_all, cudaEventDisableTiming)) return fail(-2, "repack event creation failed");
     }
