@@ -81,10 +81,11 @@ conv3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * HALO_EPI_WARPS); }
         fence_mbar_init();
     }
+    cluster_sync_all();                              // both CTAs synchronised before the collective TMEM allocation; the peer's
+                                                     // barriers are initialised before anything arrives on them
     if (warp == 1) tmem_alloc2(tmem_slot, CF::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                              // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     pdl_wait();
     const uint32_t tmem_base = *tmem_slot;

@@ -156,10 +156,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (PAIR ? 2 : 1) * gemm_epi_warps(MODE)); }
         fence_mbar_init();
     }
+    // pair: both CTAs are synchronised BEFORE the collective TMEM allocation (and the peer's barriers are initialised before
+    // anything arrives on them)
+    if (PAIR) cluster_sync_all();
     if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();                   // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     pdl_wait();                                     // prologue above overlapped the previous kernel's tail; its data is visible from here
     const uint32_t tmem_base = *tmem_slot;
