@@ -1546,7 +1546,7 @@ __global__ void k_pack_conv_w_s2dgrad(const float* __restrict__ w, bf16* __restr
     }
 }
 // ---- table-driven weight maintenance: ONE launch re-packs every conv weight (grid.y = table entry)
-enum PackKind { PK_CONV = 0, PK_BIAS_ADD = 1, PK_FLIP_T = 2, PK_UNPACK_GRAD = 3, PK_UPFOLD = 4 };
+enum PackKind { PK_CONV = 0, PK_BIAS_ADD = 1, PK_FLIP_T = 2, PK_UNPACK_GRAD = 3, PK_UPFOLD = 4, PK_IDENTITY = 5 };
 struct PackEntry {
     int kind; int Co, Ci, taps; int k_off; int dkind;   // dkind: 0 none, 1 dgrad, 2 dgrad flipped taps, 3 stride-2 parity dgrad
     const float* w; const float* w2; bf16* fwd; long long ld_f; bf16* dgr; long long ld_d; float* fout; float* scratch;
@@ -1572,6 +1572,17 @@ __global__ void __launch_bounds__(256) k_pack_table(const PackEntry* __restrict_
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
             const int t = (int)(i % e.taps); const long long r = i / e.taps; const int ci = (int)(r % e.Ci), co = (int)(r / e.Ci);
             e.fout[((long long)ci * e.Co + co) * 9 + (8 - t)] = e.w[i];
+        }
+        return;
+    }
+    if (e.kind == PK_IDENTITY) {     // fwd[co][k_off + ci] = (co == ci): the residual of a ResidualBlock as extra K chunks of its conv2
+        const long long total = (long long)e.Co * (e.Ci / 8);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int o = (int)(i % (e.Ci / 8)), co = (int)(i / (e.Ci / 8));
+            float f[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = (o * 8 + u == co) ? 1.f : 0.f;
+            *reinterpret_cast<uint4*>(e.fwd + (long long)co * e.ld_f + e.k_off + o * 8) = pack8(f);
         }
         return;
     }

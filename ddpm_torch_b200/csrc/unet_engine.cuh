@@ -166,6 +166,7 @@ struct UnetEngine {
     struct ConvSpec {
         std::string name; Src in; int ksize = 3, stride = 1, map = MAP_NORMAL;
         const bf16* wp = nullptr; long long ldw = 0; bool has_skip = false; Src skip_in;
+        bool skip_identity = false;        // the skip chunks carry identity weights (the block's residual): no FLOPs of the reference's count
         const float* bias = nullptr; const float* rowvec = nullptr; int rowvec_ld = 0; const bf16* residual = nullptr;
         T4 out; float* out_nchw = nullptr; int Co = 0; int Ho = 0, Wo = 0; bool accumulate = false;
         bool want_qstats = false;          // the output feeds a GroupNorm -> statistics in the epilogue when the kernel can
@@ -215,7 +216,7 @@ struct UnetEngine {
         const T4& i0 = c.in.t0;
         const int Bn = i0.B;
         const long long Pout = (long long)Bn * c.Ho * c.Wo;
-        double fl = 2.0 * Pout * c.Co * (double)(taps * Cin + (c.has_skip ? c.skip_in.C() : 0));
+        double fl = 2.0 * Pout * c.Co * (double)(taps * Cin + ((c.has_skip && !c.skip_identity) ? c.skip_in.C() : 0));
         if (flops_acc) *flops_acc += fl;
         const bool s2 = c.stride == 2 && c.map == MAP_NORMAL && c.ksize == 3 && !c.has_skip && c.Ho * 2 == i0.H && c.Wo * 2 == i0.W;
         bool tc = (c.stride == 1 || s2) && c.map == MAP_NORMAL && !c.out_nchw && !c.in.two && (i0.C % 64 == 0) && (c.Co % 64 == 0) &&
@@ -526,6 +527,11 @@ struct UnetEngine {
         PackEntry e; memset(&e, 0, sizeof e);
         e.kind = PK_CONV; e.Co = Co; e.Ci = Ci; e.taps = 1; e.k_off = k_off; e.w = PP(pname + ".weight");
         e.fwd = into.fwd; e.ld_f = into.ld_f; e.dgr = dgr; e.ld_d = ld_d; e.dkind = dgr ? 1 : 0;
+        pack_table_host.push_back(e);
+    }
+    void pack_identity(const Packed& into, int k_off, int C) {
+        PackEntry e; memset(&e, 0, sizeof e);
+        e.kind = PK_IDENTITY; e.Co = C; e.Ci = C; e.taps = 1; e.k_off = k_off; e.fwd = into.fwd; e.ld_f = into.ld_f;
         pack_table_host.push_back(e);
     }
     void pack_bias_add(float* dst, const float* a, const float* b, int n) {
