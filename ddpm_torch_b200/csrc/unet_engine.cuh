@@ -360,9 +360,10 @@ struct UnetEngine {
                 const int tiles = ((Co + 127) / 128) * (a.C / bn) * taps;
                 // split-K so that the launch is ONE full wave (<= 148 CTAs): more splits only add epilogue atomics,
                 // and 148*k + 1 CTAs would cost a whole extra wave
-                // (1x1 weight gradients are one or two output tiles and HBM-bound: half a wave is faster in isolation - 23.3 vs 27.0 us for
-                // 256->128 at 32x32, profiles/r02_wgrad_microbench.txt - and leaves the other SMs to the main chain: step 9.12 -> 9.07 ms)
-                int splits = ((taps == 1 && tiles <= 2) ? 74 : 148) / tiles; if (splits > d.kblocks / 4) splits = d.kblocks / 4; if (splits < 1) splits = 1;
+                // (1x1 weight gradients are a few output tiles and HBM-bound: half a wave is faster in isolation - 23.3 vs 27.0 us for
+                // 256->128 at 32x32, profiles/r02_wgrad_microbench.txt - and leaves the other SMs to the main chain: step 9.12 -> 9.07 ms for the 1-2 tile
+                // ones, 9.047 -> 9.028 ms more with the 6-12 tile ones (project_in / project_out) included)
+                int splits = ((taps == 1 && tiles <= 12) ? 74 : 148) / tiles; if (splits > d.kblocks / 4) splits = d.kblocks / 4; if (splits < 1) splits = 1;
                 d.splits = splits; d.grid_z = taps * splits;
                 d.flags = EPI_OUT_F32 | EPI_ATOMIC; d.alpha = 1.f;
                 if (taps == 9) { d.out = scratch + coff; d.ldo = Cin; d.out_tap_stride = (long long)Co * Cin; }
